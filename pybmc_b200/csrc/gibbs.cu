@@ -1,0 +1,118 @@
+// C ABI: conjugate Gibbs sampler (see include/bmc_b200.h; pybmc/inference_utils.py:4-56).
+#include <algorithm>
+#include "common.h"
+#include "gibbs_kernels.cuh"
+
+using namespace bmc;
+
+namespace {
+
+template <typename real, int KP>
+int launch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream_t stream) {
+    const unsigned blocks = static_cast<unsigned>((a.n_chains + threads - 1) / threads);
+    switch (stats_mode) {
+        case BMC_STATS_NONE:
+            gibbs_conjugate_kernel<real, KP, 0><<<blocks, threads, 0, stream>>>(a);
+            break;
+        case BMC_STATS_DIAG:
+            gibbs_conjugate_kernel<real, KP, 1><<<blocks, threads, 0, stream>>>(a);
+            break;
+        default:
+            if constexpr (KP <= 16) {
+                gibbs_conjugate_kernel<real, KP, 2><<<blocks, threads, 0, stream>>>(a);
+            } else {
+                set_error("bmc_gibbs_run: BMC_STATS_FULL needs k <= 16");
+                return BMC_ERR_ARG;
+            }
+    }
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+template <typename real>
+int dispatch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream_t stream) {
+    if (a.k <= 4) return launch_conjugate<real, 4>(a, stats_mode, threads, stream);
+    if (a.k <= 8) return launch_conjugate<real, 8>(a, stats_mode, threads, stream);
+    if (a.k <= 16) return launch_conjugate<real, 16>(a, stats_mode, threads, stream);
+    if (a.k <= 32) return launch_conjugate<real, 32>(a, stats_mode, threads, stream);
+    return launch_conjugate<real, 64>(a, stats_mode, threads, stream);
+}
+
+int pick_threads(long long n_chains) {
+    // small blocks spread few chains over all 148 SMs; 128 once there is plenty of work
+    if (n_chains >= 148ll * 128 * 8) return 128;
+    if (n_chains >= 148ll * 64 * 2) return 64;
+    return 32;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bmc_padded_components(int k) { return k <= 4 ? 4 : k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 64; }
+
+int64_t bmc_gibbs_n_stat(int k, int stats_mode) {
+    const int64_t d = k + 1;
+    if (stats_mode == BMC_STATS_NONE) return 0;
+    if (stats_mode == BMC_STATS_DIAG) return 2 * d;
+    return d + d * (d + 1) / 2;
+}
+
+int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t chain0, int64_t n_chains,
+                  int64_t iterations, int64_t store_from, int64_t thin, int64_t n_kept, void* samples,
+                  double* chain_stats, int stats_mode, void* stream) {
+    BMC_REQUIRE(p, "bmc_gibbs_run: problem is NULL");
+    BMC_REQUIRE(dtype == BMC_F32 || dtype == BMC_F64, "bmc_gibbs_run: bad dtype %d", dtype);
+    BMC_REQUIRE(p->k >= 1 && p->k <= BMC_MAX_COMPONENTS, "bmc_gibbs_run: k=%d outside 1..%d", p->k,
+                BMC_MAX_COMPONENTS);
+    BMC_REQUIRE(p->d && p->pull && p->g_ols && p->w, "bmc_gibbs_run: problem constants missing");
+    BMC_REQUIRE(n_chains >= 1 && iterations >= 0, "bmc_gibbs_run: n_chains=%lld iterations=%lld",
+                (long long)n_chains, (long long)iterations);
+    BMC_REQUIRE(iterations < (1ll << 32), "bmc_gibbs_run: iterations must fit 32 bits");
+    BMC_REQUIRE(stats_mode >= 0 && stats_mode <= 2, "bmc_gibbs_run: bad stats_mode");
+    BMC_REQUIRE(stats_mode == 0 || chain_stats, "bmc_gibbs_run: chain_stats is NULL");
+    BMC_REQUIRE(p->nu0 + p->n_obs > 0 && p->sigma2_init > 0, "bmc_gibbs_run: bad variance prior");
+    if (samples) {
+        BMC_REQUIRE(thin >= 1 && store_from >= 0, "bmc_gibbs_run: thin=%lld store_from=%lld", (long long)thin,
+                    (long long)store_from);
+        const int64_t need = iterations > store_from ? (iterations - store_from + thin - 1) / thin : 0;
+        BMC_REQUIRE(n_kept >= need, "bmc_gibbs_run: n_kept=%lld < %lld kept iterations", (long long)n_kept,
+                    (long long)need);
+    }
+    cudaStream_t st = as_stream(stream);
+    GibbsArgs a{};
+    a.d = p->d;
+    a.pull = p->pull;
+    a.g_ols = p->g_ols;
+    a.w = p->w;
+    a.k = p->k;
+    a.dense_w = p->dense_w;
+    a.rss_min = p->rss_min;
+    a.shape = 0.5 * (p->nu0 + p->n_obs);                      // inference_utils.py:50
+    a.prior_scale = p->nu0 * p->sigma20;                      // :51
+    a.sigma2_init = p->sigma2_init;
+    a.sigma_ref = sqrt(p->sigma2_init);
+    a.key0 = static_cast<uint32_t>(seed);
+    a.key1 = static_cast<uint32_t>(seed >> 32);
+    a.chain0 = chain0;
+    a.n_chains = n_chains;
+    a.iterations = iterations;
+    a.store_from = store_from;
+    a.thin = thin;
+    a.n_kept = n_kept;
+    a.samples = samples;
+    a.chain_stats = chain_stats;
+    a.stats_mode = stats_mode;
+    if (stats_mode != 0) {
+        // the kernel accumulates with the padded component count kp = bmc_padded_components(k)
+        const int kp = bmc_padded_components(p->k);
+        BMC_CUDA(cudaMemsetAsync(chain_stats, 0,
+                                 sizeof(double) * static_cast<size_t>(bmc_gibbs_n_stat(kp, stats_mode)) * n_chains, st));
+    }
+    if (iterations == 0) return BMC_OK;
+    const int threads = pick_threads(n_chains);
+    return dtype == BMC_F32 ? dispatch_conjugate<float>(a, stats_mode, threads, st)
+                            : dispatch_conjugate<double>(a, stats_mode, threads, st);
+}
+
+}  // extern "C"

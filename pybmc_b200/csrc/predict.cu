@@ -1,0 +1,435 @@
+// C ABI: fused posterior prediction + UQ (see include/bmc_b200.h;
+// pybmc/sampling_utils.py:40-84 and :4-37).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "common.h"
+#include "predict_kernels.cuh"
+
+using namespace bmc;
+
+namespace {
+
+constexpr int kMaxPasses = 64;
+constexpr double kWindowSigmas = 4.0;   // half-width in sampling standard errors of the order statistic
+constexpr double kWindowSlack = 0.005;  // plus this fraction of the predictive spread (model error of the guess)
+
+// Acklam's rational approximation of the standard normal quantile (|rel err| < 1.2e-9): only used to
+// place the first window, never in a result.
+double norm_ppf(double p) {
+    static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                               1.383577518672690e+02,  -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                               6.680131188771972e+01,  -1.328068155288572e+01};
+    static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                               -2.549732539343734e+00, 4.374664141464968e+00,  2.938163982698783e+00};
+    static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                               3.754408661907416e+00};
+    const double plow = 0.02425;
+    if (p < plow) {
+        const double q = std::sqrt(-2 * std::log(p));
+        return (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+               ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+    }
+    if (p > 1 - plow) return -norm_ppf(1 - p);
+    const double q = p - 0.5, r = q * q;
+    return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+           (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
+}
+
+struct QuantPlan {
+    int nq;
+    long long rank[kMaxQuant];
+    double frac[kMaxQuant], zq[kMaxQuant], hw[kMaxQuant];
+    int cand_cap;
+};
+
+// np.percentile(..., method="linear"): virtual index v = q/100 (S-1), order statistics floor(v), floor(v)+1
+// (pybmc/sampling_utils.py:80-82).
+QuantPlan make_plan(const double* probs, int nq, long long s) {
+    QuantPlan pl{};
+    pl.nq = nq;
+    double max_expected = 16.0;
+    for (int j = 0; j < nq; ++j) {
+        const double v = (probs[j] / 100.0) * static_cast<double>(s - 1);
+        long long r = static_cast<long long>(std::floor(v));
+        double f = v - static_cast<double>(r);
+        if (r >= s - 1) {
+            r = s - 1;
+            f = 0.0;
+        }
+        if (r < 0) r = 0;
+        pl.rank[j] = r;
+        pl.frac[j] = f;
+        double p = (static_cast<double>(r) + 0.5 + f) / static_cast<double>(s);
+        p = std::min(std::max(p, 0.5 / s), 1.0 - 0.5 / s);
+        const double z = norm_ppf(p);
+        const double pdf = std::exp(-0.5 * z * z) / std::sqrt(2.0 * M_PI);
+        const double se = std::sqrt(p * (1.0 - p) / static_cast<double>(s)) / pdf;
+        pl.zq[j] = z;
+        pl.hw[j] = kWindowSigmas * se + kWindowSlack;
+        max_expected = std::max(max_expected, 2.0 * pl.hw[j] * pdf * static_cast<double>(s));
+    }
+    long long cap = static_cast<long long>(1.5 * max_expected) + 32;
+    cap = (cap + 31) / 32 * 32;
+    pl.cand_cap = static_cast<int>(std::min<long long>(cap, 4096));
+    return pl;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Layout {
+    // byte offsets inside the workspace for a chunk of nc nuclei
+    size_t center, scale, win_lo, win_hi, brk_lo, brk_hi, brk_below, cnt_below, cnt_in, resolved, cand, mom, c_lt,
+        c_le, flag, list_a, list_b, counter, plan, total;
+};
+
+Layout make_layout(long long nc, int nq, int cap, size_t sz, int max_slots) {
+    Layout l{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = off;
+        off = align_up(off + bytes);
+        return at;
+    };
+    const size_t nqn = static_cast<size_t>(nc) * nq;
+    const size_t quads = static_cast<size_t>((nc + 3) / 4);
+    l.plan = take(kMaxQuant * (sizeof(long long) + 3 * sizeof(double)));
+    l.counter = take(sizeof(int));
+    l.center = take(nc * sz);
+    l.scale = take(nc * sz);
+    l.win_lo = take(nqn * sz);
+    l.win_hi = take(nqn * sz);
+    l.brk_lo = take(nqn * sz);
+    l.brk_hi = take(nqn * sz);
+    l.brk_below = take(nqn * 4);
+    l.cnt_below = take(nqn * 4);
+    l.cnt_in = take(nqn * 4);
+    l.resolved = take(nqn);
+    l.cand = take(nqn * cap * sz);
+    l.mom = take(static_cast<size_t>(max_slots) * 2 * nc * sizeof(double));
+    l.c_lt = take(nc * 4);
+    l.c_le = take(nc * 4);
+    l.flag = take(quads * 4);
+    l.list_a = take(quads * 4);
+    l.list_b = take(quads * 4);
+    l.total = off;
+    return l;
+}
+
+constexpr int kMaxSlots = 64;
+
+template <typename real>
+__global__ void copy_guess_kernel(const double* c, const double* s, long long n, void* center, void* scale) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    static_cast<real*>(center)[i] = static_cast<real>(c[i]);
+    static_cast<real*>(scale)[i] = static_cast<real>(s[i]);
+}
+
+template <typename real, int KP, int NQ>
+int launch_pass(const PredictArgs& a, cudaStream_t st) {
+    const int qpb = kPredWarps / a.warps_per_quad;
+    dim3 grid((a.n_quads + qpb - 1) / qpb, a.s_splits);
+    const size_t smem = a.theta_t ? 2 * static_cast<size_t>(a.k + 1) * kPredTile * sizeof(real) : 16;
+    auto kern = predict_pass_kernel<real, KP, NQ>;
+    if (smem > 48 * 1024) BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kPredWarps * 32, smem, st>>>(a);
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+template <typename real, int KP>
+int dispatch_nq(const PredictArgs& a, cudaStream_t st) {
+    if (a.nq <= 3) return launch_pass<real, KP, 3>(a, st);
+    if (a.nq <= 5) return launch_pass<real, KP, 5>(a, st);
+    return launch_pass<real, KP, 8>(a, st);
+}
+
+template <typename real>
+int dispatch_pass(const PredictArgs& a, cudaStream_t st) {
+    if (a.k <= 4) return dispatch_nq<real, 4>(a, st);
+    if (a.k <= 8) return dispatch_nq<real, 8>(a, st);
+    return dispatch_nq<real, 16>(a, st);
+}
+
+void pick_split(int n_quads, long long n_draws, int* wpq, int* splits) {
+    const int target = 296;                         // two blocks per SM
+    const int tiles = static_cast<int>((n_draws + kPredTile - 1) / kPredTile);
+    int w = 1;
+    while (w < 8 && (n_quads + (8 / w) - 1) / (8 / w) < target) w *= 2;
+    const int blocks = (n_quads + (8 / w) - 1) / (8 / w);
+    int s = 1;
+    if (blocks < target) s = std::min(std::max(1, (target + blocks - 1) / blocks), std::max(1, tiles));
+    s = std::min(s, kMaxSlots / w);
+    *wpq = w;
+    *splits = std::max(1, s);
+}
+
+template <typename real>
+int run_predict(const bmc_predict_problem* p, double* mean, double* var, double* quant, int64_t* c_lt,
+                int64_t* c_le, double* draws_out, int64_t ld_out, void* workspace, size_t workspace_bytes,
+                int* passes_out, cudaStream_t st) {
+    const size_t sz = sizeof(real);
+    const QuantPlan plan = make_plan(p->probs, p->nq, p->n_draws);
+    // largest chunk of nuclei the workspace can hold
+    long long nc = (p->n_points + 3) / 4 * 4;
+    while (nc > 4 && make_layout(nc, p->nq, plan.cand_cap, sz, kMaxSlots).total > workspace_bytes) {
+        const long long half = (nc / 2 + 3) / 4 * 4;
+        nc = half < nc ? half : nc - 4;
+    }
+    if (make_layout(nc, p->nq, plan.cand_cap, sz, kMaxSlots).total > workspace_bytes) {
+        set_error("bmc_predict_fused: workspace of %zu bytes cannot hold even 4 nuclei", workspace_bytes);
+        return BMC_ERR_WORKSPACE;
+    }
+    const Layout lay = make_layout(nc, p->nq, plan.cand_cap, sz, kMaxSlots);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+
+    // quantile plan to the device
+    long long* d_rank = reinterpret_cast<long long*>(ws + lay.plan);
+    double* d_frac = reinterpret_cast<double*>(d_rank + kMaxQuant);
+    double* d_zq = d_frac + kMaxQuant;
+    double* d_hw = d_zq + kMaxQuant;
+    BMC_CUDA(cudaMemcpyAsync(d_rank, plan.rank, sizeof(plan.rank), cudaMemcpyHostToDevice, st));
+    BMC_CUDA(cudaMemcpyAsync(d_frac, plan.frac, sizeof(plan.frac), cudaMemcpyHostToDevice, st));
+    BMC_CUDA(cudaMemcpyAsync(d_zq, plan.zq, sizeof(plan.zq), cudaMemcpyHostToDevice, st));
+    BMC_CUDA(cudaMemcpyAsync(d_hw, plan.hw, sizeof(plan.hw), cudaMemcpyHostToDevice, st));
+    BMC_CUDA(cudaStreamSynchronize(st));   // the plan lives on this stack frame
+
+    int pow2cap = 1;
+    while (pow2cap < plan.cand_cap) pow2cap <<= 1;
+    const size_t select_smem = 4 * static_cast<size_t>(pow2cap) * sz;
+    auto select_kern = predict_select_kernel<real>;
+    if (select_smem > 48 * 1024)
+        BMC_CUDA(cudaFuncSetAttribute(select_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem));
+
+    int max_passes = 0;
+    for (long long c0 = 0; c0 < p->n_points; c0 += nc) {
+        const long long n = std::min<long long>(nc, p->n_points - c0);
+        const int n_quads = static_cast<int>((n + 3) / 4);
+        const size_t nqn = static_cast<size_t>(n) * p->nq;
+        int* d_counter = reinterpret_cast<int*>(ws + lay.counter);
+        BMC_CUDA(cudaMemsetAsync(ws + lay.c_lt, 0, n * 4, st));
+        BMC_CUDA(cudaMemsetAsync(ws + lay.c_le, 0, n * 4, st));
+        BMC_CUDA(cudaMemsetAsync(ws + lay.flag, 0, static_cast<size_t>(n_quads) * 4, st));
+        BMC_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
+
+        const unsigned gb = static_cast<unsigned>((n + 255) / 256);
+        const real* u_chunk = static_cast<const real*>(p->u) + c0 * p->k;
+        if (p->center && p->scale) {
+            copy_guess_kernel<real><<<gb, 256, 0, st>>>(p->center + c0, p->scale + c0, n, ws + lay.center,
+                                                        ws + lay.scale);
+        } else {
+            predict_guess_kernel<real><<<gb, 256, 0, st>>>(u_chunk, n, p->k, p->theta_mean, p->theta_cov,
+                                                           p->noise_mode != BMC_NOISE_NONE, ws + lay.center,
+                                                           ws + lay.scale);
+        }
+        BMC_LAUNCH_CHECK();
+        predict_window_kernel<real><<<static_cast<unsigned>((nqn + 255) / 256), 256, 0, st>>>(
+            n, p->nq, ws + lay.center, ws + lay.scale, d_zq, d_hw, ws + lay.win_lo, ws + lay.win_hi, ws + lay.brk_lo,
+            ws + lay.brk_hi, reinterpret_cast<unsigned int*>(ws + lay.brk_below),
+            reinterpret_cast<unsigned int*>(ws + lay.cnt_below), reinterpret_cast<unsigned int*>(ws + lay.cnt_in),
+            ws + lay.resolved);
+        BMC_LAUNCH_CHECK();
+
+        PredictArgs a{};
+        a.u = u_chunk;
+        a.mu = p->mu ? p->mu + c0 : nullptr;
+        a.truth = p->truth ? p->truth + c0 : nullptr;
+        a.n_points = n;
+        a.point0 = p->point0 + static_cast<unsigned long long>(c0);
+        a.theta_t = p->theta_t;
+        a.n_draws = p->n_draws;
+        a.k = p->k;
+        a.noise_mode = p->noise_mode;
+        a.key0 = static_cast<uint32_t>(p->seed);
+        a.key1 = static_cast<uint32_t>(p->seed >> 32);
+        a.noise = p->noise ? static_cast<const unsigned char*>(p->noise) + static_cast<size_t>(c0) * sz : nullptr;
+        a.ld_noise = p->ld_noise;
+        a.nq = p->nq;
+        a.win_lo = ws + lay.win_lo;
+        a.win_hi = ws + lay.win_hi;
+        a.cnt_below = reinterpret_cast<unsigned int*>(ws + lay.cnt_below);
+        a.cnt_in = reinterpret_cast<unsigned int*>(ws + lay.cnt_in);
+        a.cand = ws + lay.cand;
+        a.cand_cap = plan.cand_cap;
+        a.first = 1;
+        a.center = ws + lay.center;
+        a.mom_part = reinterpret_cast<double*>(ws + lay.mom);
+        a.c_lt = reinterpret_cast<unsigned int*>(ws + lay.c_lt);
+        a.c_le = reinterpret_cast<unsigned int*>(ws + lay.c_le);
+        a.draws_out = draws_out ? draws_out + c0 : nullptr;
+        a.ld_out = ld_out;
+        a.quad_list = nullptr;
+        a.n_quads = n_quads;
+        pick_split(n_quads, p->n_draws, &a.warps_per_quad, &a.s_splits);
+
+        SelectArgs s{};
+        s.n_points = n;
+        s.n_draws = p->n_draws;
+        s.nq = p->nq;
+        s.rank = d_rank;
+        s.frac = d_frac;
+        s.win_lo = a.win_lo;
+        s.win_hi = a.win_hi;
+        s.brk_lo = ws + lay.brk_lo;
+        s.brk_hi = ws + lay.brk_hi;
+        s.brk_below = reinterpret_cast<unsigned int*>(ws + lay.brk_below);
+        s.cnt_below = a.cnt_below;
+        s.cnt_in = a.cnt_in;
+        s.cand = a.cand;
+        s.cand_cap = plan.cand_cap;
+        s.resolved = ws + lay.resolved;
+        s.mu = a.mu;
+        s.out_quant = quant;
+        s.ld_quant = p->n_points;
+        s.out_offset = c0;
+        s.first = 1;
+        s.mom_part = a.mom_part;
+        s.n_slots = a.warps_per_quad * a.s_splits;
+        s.center = a.center;
+        s.out_mean = mean;
+        s.out_var = var;
+        s.c_lt = a.c_lt;
+        s.c_le = a.c_le;
+        s.out_c_lt = p->truth ? reinterpret_cast<long long*>(c_lt) : nullptr;
+        s.out_c_le = p->truth ? reinterpret_cast<long long*>(c_le) : nullptr;
+        s.quad_list = nullptr;
+        s.n_quads = n_quads;
+        s.quad_flag = reinterpret_cast<int*>(ws + lay.flag);
+        int* list_cur = reinterpret_cast<int*>(ws + lay.list_a);
+        int* list_next = reinterpret_cast<int*>(ws + lay.list_b);
+        s.next_list = list_next;
+        s.next_count = d_counter;
+
+        int pass = 0;
+        for (;;) {
+            ++pass;
+            const int rc = dispatch_pass<real>(a, st);
+            if (rc != BMC_OK) return rc;
+            const long long items = 4ll * s.n_quads * p->nq;
+            select_kern<<<static_cast<unsigned>((items + 3) / 4), 128, select_smem, st>>>(s);
+            BMC_LAUNCH_CHECK();
+            int pending = 0;
+            BMC_CUDA(cudaMemcpyAsync(&pending, d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+            BMC_CUDA(cudaStreamSynchronize(st));
+            if (pending == 0) break;
+            if (pass >= kMaxPasses) {
+                set_error("bmc_predict_fused: %d nuclei quads unresolved after %d passes", pending, pass);
+                return BMC_ERR_CONVERGE;
+            }
+            // next pass: only the quads that asked for it
+            std::swap(list_cur, list_next);
+            BMC_CUDA(cudaMemsetAsync(ws + lay.flag, 0, static_cast<size_t>(n_quads) * 4, st));
+            BMC_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
+            a.first = 0;
+            a.draws_out = nullptr;
+            a.quad_list = list_cur;
+            a.n_quads = pending;
+            a.warps_per_quad = 8;
+            a.s_splits = std::min<int>(std::max(1, 296 / pending),
+                                       std::max<int>(1, static_cast<int>((p->n_draws + kPredTile - 1) / kPredTile)));
+            s.first = 0;
+            s.quad_list = list_cur;
+            s.n_quads = pending;
+            s.next_list = list_next;
+        }
+        max_passes = std::max(max_passes, pass);
+    }
+    if (passes_out) *passes_out = max_passes;
+    return BMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t bmc_predict_workspace_bytes(int dtype, int64_t n_points, int nq, int64_t n_draws) {
+    if (n_points < 1 || nq < 1 || nq > kMaxQuant || n_draws < 1) return 0;
+    double probs[kMaxQuant];
+    for (int j = 0; j < nq; ++j) probs[j] = 50.0;   // the median has the widest window
+    const QuantPlan plan = make_plan(probs, nq, n_draws);
+    const size_t sz = dtype == BMC_F32 ? 4 : 8;
+    // cap the recommendation: chunks of 32768 nuclei keep the candidate buffers in the hundreds of MB
+    const long long nc = std::min<long long>((n_points + 3) / 4 * 4, 32768);
+    return make_layout(nc, nq, plan.cand_cap, sz, kMaxSlots).total;
+}
+
+int bmc_predict_fused(int dtype, const bmc_predict_problem* p, double* mean, double* var, double* quant,
+                      int64_t* c_lt, int64_t* c_le, double* draws_out, int64_t ld_out, void* workspace,
+                      size_t workspace_bytes, int* passes_out, void* stream) {
+    BMC_REQUIRE(p, "bmc_predict_fused: problem is NULL");
+    BMC_REQUIRE(dtype == BMC_F32 || dtype == BMC_F64, "bmc_predict_fused: bad dtype %d", dtype);
+    BMC_REQUIRE(p->n_points >= 1 && p->n_draws >= 1, "bmc_predict_fused: n_points=%lld n_draws=%lld",
+                (long long)p->n_points, (long long)p->n_draws);
+    BMC_REQUIRE(p->n_draws < (1ll << 31), "bmc_predict_fused: n_draws must fit 31 bits");
+    BMC_REQUIRE((p->point0 & 3) == 0, "bmc_predict_fused: point0 must be a multiple of 4");
+    BMC_REQUIRE(p->nq >= 1 && p->nq <= kMaxQuant && p->probs, "bmc_predict_fused: nq=%d", p->nq);
+    for (int j = 0; j < p->nq; ++j)
+        BMC_REQUIRE(p->probs[j] >= 0.0 && p->probs[j] <= 100.0, "Percentiles must be in the range [0, 100]");
+    BMC_REQUIRE(mean && var && quant && workspace, "bmc_predict_fused: null output");
+    BMC_REQUIRE(!p->truth || (c_lt && c_le), "bmc_predict_fused: truth given without count outputs");
+    if (p->theta_t) {
+        BMC_REQUIRE(p->k >= 0 && p->k <= 16, "bmc_predict_fused: k=%d outside 0..16", p->k);
+        BMC_REQUIRE(p->k == 0 || p->u, "bmc_predict_fused: u is NULL");
+        BMC_REQUIRE((p->theta_mean && p->theta_cov) || (p->center && p->scale),
+                    "bmc_predict_fused: need theta moments or a centre/scale guess");
+    } else {
+        BMC_REQUIRE(p->noise_mode == BMC_NOISE_EXTERNAL && p->noise && p->center && p->scale,
+                    "bmc_predict_fused: matrix mode needs noise, center and scale");
+    }
+    BMC_REQUIRE(p->noise_mode != BMC_NOISE_EXTERNAL || (p->noise && p->ld_noise >= p->n_points),
+                "bmc_predict_fused: external noise needs a pointer and ld_noise >= n_points");
+    BMC_REQUIRE(!draws_out || ld_out >= p->n_points, "bmc_predict_fused: ld_out < n_points");
+    cudaStream_t st = as_stream(stream);
+    return dtype == BMC_F32 ? run_predict<float>(p, mean, var, quant, c_lt, c_le, draws_out, ld_out, workspace,
+                                                 workspace_bytes, passes_out, st)
+                            : run_predict<double>(p, mean, var, quant, c_lt, c_le, draws_out, ld_out, workspace,
+                                                  workspace_bytes, passes_out, st);
+}
+
+int bmc_coverage_counts(const double* matrix, int64_t s_rows, int64_t n_cols, int64_t ld, const double* truth,
+                        int64_t* c_lt, int64_t* c_le, void* stream) {
+    BMC_REQUIRE(matrix && truth && c_lt && c_le, "bmc_coverage_counts: null pointer");
+    BMC_REQUIRE(s_rows >= 1 && n_cols >= 1 && ld >= n_cols, "bmc_coverage_counts: bad shape");
+    cudaStream_t st = as_stream(stream);
+    BMC_CUDA(cudaMemsetAsync(c_lt, 0, sizeof(int64_t) * n_cols, st));
+    BMC_CUDA(cudaMemsetAsync(c_le, 0, sizeof(int64_t) * n_cols, st));
+    const unsigned gx = static_cast<unsigned>((n_cols + 255) / 256);
+    // enough row blocks to cover the machine a few times over
+    long long gy = std::max<long long>(1, std::min<long long>((148 * 8 + gx - 1) / gx, (s_rows + 63) / 64));
+    const long long rows_per_block = (s_rows + gy - 1) / gy;
+    gy = (s_rows + rows_per_block - 1) / rows_per_block;
+    coverage_counts_kernel<<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, st>>>(
+        matrix, s_rows, n_cols, ld, truth, rows_per_block, reinterpret_cast<unsigned long long*>(c_lt),
+        reinterpret_cast<unsigned long long*>(c_le));
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+int bmc_column_moments(const double* matrix, int64_t s_rows, int64_t n_cols, int64_t ld, double* center,
+                       double* scale, void* stream) {
+    BMC_REQUIRE(matrix && center && scale, "bmc_column_moments: null pointer");
+    BMC_REQUIRE(s_rows >= 1 && n_cols >= 1 && ld >= n_cols, "bmc_column_moments: bad shape");
+    column_moments_kernel<<<static_cast<unsigned>((n_cols + 255) / 256), 256, 0, as_stream(stream)>>>(
+        matrix, s_rows, n_cols, ld, center, scale);
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+int bmc_coverage_levels(const int64_t* c_lt, const int64_t* c_le, int64_t n_points, const int64_t* lo_idx,
+                        const int64_t* hi_idx, int n_levels, int64_t* covered, void* stream) {
+    BMC_REQUIRE(c_lt && c_le && lo_idx && hi_idx && covered, "bmc_coverage_levels: null pointer");
+    BMC_REQUIRE(n_points >= 1 && n_levels >= 1, "bmc_coverage_levels: bad shape");
+    cudaStream_t st = as_stream(stream);
+    BMC_CUDA(cudaMemsetAsync(covered, 0, sizeof(int64_t) * n_levels, st));
+    const unsigned gx = static_cast<unsigned>(std::min<long long>((n_points + 255) / 256, 148 * 4));
+    coverage_levels_kernel<<<dim3(gx, n_levels), 256, 0, st>>>(
+        reinterpret_cast<const long long*>(c_lt), reinterpret_cast<const long long*>(c_le), n_points,
+        reinterpret_cast<const long long*>(lo_idx), reinterpret_cast<const long long*>(hi_idx), n_levels,
+        reinterpret_cast<unsigned long long*>(covered));
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// Counter-based random numbers for the sampler and predictive kernels.
+//
+// Replaces the reference's NumPy call sites: np.random.multivariate_normal
+// (pybmc/inference_utils.py:45,98,121), np.random.default_rng().gamma (:52,117,140),
+// np.random.uniform (:110,132) and Generator.standard_normal (pybmc/sampling_utils.py:76).
+// The stream layout (key, counter words, block numbers, tags) is the contract written
+// down in DESIGN.md "RNG contract" and restated on the CPU in oracle/philox.py.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bmc {
+
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+
+constexpr uint32_t kTagGibbs = 1u;
+constexpr uint32_t kTagSimplex = 2u;
+constexpr uint32_t kTagNoise = 3u;
+constexpr uint32_t kBlockGamma = 0x10000u;
+constexpr uint32_t kBlockUniform = 0x20000u;
+constexpr int kGammaMaxAttempts = 64;
+
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+// Philox-4x32, ten rounds (Salmon et al., SC'11).  Two IMAD.WIDE + two LOP3 per round.
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = static_cast<uint64_t>(kPhiloxM0) * c0;
+        const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;
+        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ (k0 + static_cast<uint32_t>(r) * kPhiloxW0);
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ (k1 + static_cast<uint32_t>(r) * kPhiloxW1);
+        c1 = static_cast<uint32_t>(p1);
+        c3 = static_cast<uint32_t>(p0);
+        c0 = n0;
+        c2 = n2;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+template <typename real>
+struct Math;
+
+template <>
+struct Math<float> {
+    // (r + 1/2) 2^-32, evaluated in one FFMA; never 0, at most 1.
+    static __device__ __forceinline__ float u01(uint32_t r) {
+        return fmaf(__uint2float_rn(r), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    }
+    // Box-Muller on the MUFU pipe: lg2, sqrt, sin, cos.
+    static __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& za, float& zb) {
+        const float l2 = __log2f(u01(ra));                         // <= 0
+        float rad;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(l2 * -1.3862943611198906f));  // -2 ln2 * log2(u)
+        float t = u01(rb);
+        t -= rintf(t);                                             // [-1/2, 1/2]: same angle mod 2 pi
+        const float ang = t * 6.283185307179586f;
+        za = rad * __cosf(ang);
+        zb = rad * __sinf(ang);
+    }
+    static __device__ __forceinline__ float log(float x) { return __logf(x); }
+    static __device__ __forceinline__ float exp(float x) { return __expf(x); }
+    static __device__ __forceinline__ float sqrt(float x) {
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ float pow(float a, float b) { return powf(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+};
+
+template <>
+struct Math<double> {
+    static __device__ __forceinline__ double u01(uint32_t r) {
+        return (static_cast<double>(r) + 0.5) * 2.3283064365386963e-10;
+    }
+    static __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, double& za, double& zb) {
+        const double rad = ::sqrt(-2.0 * ::log(u01(ra)));
+        double s, c;
+        sincospi(2.0 * u01(rb), &s, &c);
+        za = rad * c;
+        zb = rad * s;
+    }
+    static __device__ __forceinline__ double log(double x) { return ::log(x); }
+    static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+    static __device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+};
+
+template <typename real>
+__device__ __forceinline__ void normals4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                         uint32_t k1, real (&z)[4]) {
+    const Philox4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    Math<real>::box_muller(r.x, r.y, z[0], z[1]);
+    Math<real>::box_muller(r.z, r.w, z[2], z[3]);
+}
+
+// Gamma(shape, 1): Marsaglia & Tsang (2000).  shape >= 1 is the sampler's case
+// ((nu0 + n)/2); smaller shapes use the U^(1/a) boost.  d and c are passed in because they
+// are the same for every draw of a run.
+template <typename real>
+struct GammaConst {
+    real d, c, inv_shape;
+    int boost;
+};
+
+template <typename real>
+__host__ __device__ inline GammaConst<real> make_gamma_const(double shape) {
+    GammaConst<real> g;
+    g.boost = shape < 1.0;
+    const double a = g.boost ? shape + 1.0 : shape;
+    const double d = a - 1.0 / 3.0;
+    g.d = static_cast<real>(d);
+#ifdef __CUDA_ARCH__
+    g.c = static_cast<real>(1.0 / ::sqrt(9.0 * d));
+#else
+    g.c = static_cast<real>(1.0 / __builtin_sqrt(9.0 * d));
+#endif
+    g.inv_shape = static_cast<real>(1.0 / shape);
+    return g;
+}
+
+template <typename real>
+__device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
+                                                 uint32_t tag, uint32_t k0, uint32_t k1) {
+    using M = Math<real>;
+    real v = real(1);
+    Philox4 r{0u, 0u, 0u, 0u};
+    for (int t = 0; t < kGammaMaxAttempts; ++t) {
+        r = philox4x32_10(it, kBlockGamma + static_cast<uint32_t>(t), chain, tag, k0, k1);
+        real x, unused;
+        M::box_muller(r.x, r.y, x, unused);
+        v = M::fma(g.c, x, real(1));
+        if (v <= real(0)) {
+            v = real(1);
+            continue;
+        }
+        v = v * v * v;
+        const real u = M::u01(r.z);
+        const real x2 = x * x;
+        if (u < real(1) - real(0.0331) * x2 * x2) break;
+        if (M::log(u) < real(0.5) * x2 + g.d * (real(1) - v + M::log(v))) break;
+    }
+    real out = g.d * v;
+    if (g.boost) out *= M::pow(M::u01(r.w), g.inv_shape);
+    return out;
+}
+
+}  // namespace bmc

@@ -1,0 +1,116 @@
+// C ABI: simplex-constrained sampler (see include/bmc_b200.h; pybmc/inference_utils.py:59-144).
+#include <algorithm>
+#include "common.h"
+#include "gibbs_kernels.cuh"
+
+using namespace bmc;
+
+namespace {
+
+template <typename real, int KP>
+int launch_simplex(const SimplexArgs& a, int stats_mode, int threads, cudaStream_t stream) {
+    const unsigned blocks = static_cast<unsigned>((a.n_chains + threads - 1) / threads);
+    const int m4 = (a.m + 3) & ~3;
+    const size_t smem = sizeof(real) * (static_cast<size_t>(KP) * m4 + static_cast<size_t>(KP) * KP);
+    if (smem > 200 * 1024) {
+        set_error("bmc_gibbs_simplex_run: k=%d, m=%d needs %zu bytes of shared memory", a.k, a.m, smem);
+        return BMC_ERR_ARG;
+    }
+#define BMC_SIMPLEX_LAUNCH(MODE)                                                                              \
+    do {                                                                                                      \
+        auto kern = gibbs_simplex_kernel<real, KP, MODE>;                                                     \
+        if (smem > 48 * 1024)                                                                                 \
+            BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        kern<<<blocks, threads, smem, stream>>>(a);                                                           \
+    } while (0)
+    switch (stats_mode) {
+        case BMC_STATS_NONE:
+            BMC_SIMPLEX_LAUNCH(0);
+            break;
+        case BMC_STATS_DIAG:
+            BMC_SIMPLEX_LAUNCH(1);
+            break;
+        default:
+            if constexpr (KP <= 16) {
+                BMC_SIMPLEX_LAUNCH(2);
+            } else {
+                set_error("bmc_gibbs_simplex_run: BMC_STATS_FULL needs k <= 16");
+                return BMC_ERR_ARG;
+            }
+    }
+#undef BMC_SIMPLEX_LAUNCH
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+template <typename real>
+int dispatch_simplex(const SimplexArgs& a, int stats_mode, int threads, cudaStream_t stream) {
+    if (a.k <= 4) return launch_simplex<real, 4>(a, stats_mode, threads, stream);
+    if (a.k <= 8) return launch_simplex<real, 8>(a, stats_mode, threads, stream);
+    if (a.k <= 16) return launch_simplex<real, 16>(a, stats_mode, threads, stream);
+    if (a.k <= 32) return launch_simplex<real, 32>(a, stats_mode, threads, stream);
+    return launch_simplex<real, 64>(a, stats_mode, threads, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bmc_gibbs_simplex_run(int dtype, const bmc_simplex_problem* p, uint64_t seed, uint64_t chain0,
+                          int64_t n_chains, int64_t burn, int64_t iterations, int64_t thin, int64_t n_kept,
+                          void* samples, double* chain_stats, int stats_mode, int32_t* accepted, void* stream) {
+    BMC_REQUIRE(p, "bmc_gibbs_simplex_run: problem is NULL");
+    BMC_REQUIRE(dtype == BMC_F32 || dtype == BMC_F64, "bmc_gibbs_simplex_run: bad dtype %d", dtype);
+    // the reference's own checks, pybmc/inference_utils.py:91-94 (the Python layer raises ValueError)
+    BMC_REQUIRE(burn >= 0, "Burn-in iterations must be non-negative.");
+    BMC_REQUIRE(p->k >= 1 && p->k <= BMC_MAX_COMPONENTS && p->m >= 1, "bmc_gibbs_simplex_run: k=%d m=%d", p->k,
+                p->m);
+    BMC_REQUIRE(p->gram && p->b_ols && p->step && p->vt_hat, "bmc_gibbs_simplex_run: problem constants missing");
+    BMC_REQUIRE(n_chains >= 1 && iterations >= 0, "bmc_gibbs_simplex_run: n_chains=%lld iterations=%lld",
+                (long long)n_chains, (long long)iterations);
+    BMC_REQUIRE(burn + iterations < (1ll << 32), "bmc_gibbs_simplex_run: burn + iterations must fit 32 bits");
+    BMC_REQUIRE(stats_mode >= 0 && stats_mode <= 2, "bmc_gibbs_simplex_run: bad stats_mode");
+    BMC_REQUIRE(stats_mode == 0 || chain_stats, "bmc_gibbs_simplex_run: chain_stats is NULL");
+    BMC_REQUIRE(p->n_obs > 0 && p->nu0 + p->n_obs > 0, "bmc_gibbs_simplex_run: bad n_obs / nu0");
+    if (samples) {
+        BMC_REQUIRE(thin >= 1, "bmc_gibbs_simplex_run: thin=%lld", (long long)thin);
+        BMC_REQUIRE(n_kept >= (iterations + thin - 1) / thin, "bmc_gibbs_simplex_run: n_kept too small");
+    }
+    cudaStream_t st = as_stream(stream);
+    SimplexArgs a{};
+    a.gram = p->gram;
+    a.b_ols = p->b_ols;
+    a.step = p->step;
+    a.vt = p->vt_hat;
+    a.k = p->k;
+    a.m = p->m;
+    a.rss_min = p->rss_min;
+    a.shape = 0.5 * (p->nu0 + p->n_obs);                     // inference_utils.py:115 / :138
+    a.prior_scale = p->nu0 * p->sigma20;                     // :116 / :139
+    a.sigma2_init = p->rss_zero / p->n_obs;                  // :86
+    a.sigma_ref = sqrt(a.sigma2_init > 0 ? a.sigma2_init : 1.0);
+    a.key0 = static_cast<uint32_t>(seed);
+    a.key1 = static_cast<uint32_t>(seed >> 32);
+    a.chain0 = chain0;
+    a.n_chains = n_chains;
+    a.burn = burn;
+    a.iterations = iterations;
+    a.thin = thin;
+    a.n_kept = n_kept;
+    a.samples = samples;
+    a.chain_stats = chain_stats;
+    a.stats_mode = stats_mode;
+    a.accepted = accepted;
+    if (stats_mode != 0) {
+        const int kp = bmc_padded_components(p->k);
+        BMC_CUDA(cudaMemsetAsync(chain_stats, 0,
+                                 sizeof(double) * static_cast<size_t>(bmc_gibbs_n_stat(kp, stats_mode)) * n_chains, st));
+    }
+    if (accepted) BMC_CUDA(cudaMemsetAsync(accepted, 0, sizeof(int32_t) * n_chains, st));
+    if (burn + iterations == 0) return BMC_OK;
+    const int threads = n_chains >= 148ll * 128 * 8 ? 128 : (n_chains >= 148ll * 64 * 2 ? 64 : 32);
+    return dtype == BMC_F32 ? dispatch_simplex<float>(a, stats_mode, threads, st)
+                            : dispatch_simplex<double>(a, stats_mode, threads, st);
+}
+
+}  // extern "C"
