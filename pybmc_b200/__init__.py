@@ -1,0 +1,26 @@
+"""pybmc_b200: pyBMC's Bayesian-model-combination inference path on B200 (sm_100a) kernels.
+
+Same public names as upstream ``pybmc`` (pybmc/__init__.py:11-24) for the inference path:
+
+    BayesianModelCombination, gibbs_sampler, USVt_hat_extraction, coverage
+
+plus, importable from their submodules as upstream, ``gibbs_sampler_simplex`` and
+``rndm_m_random_calculator``.  Importing the package does not touch the GPU; the first call
+loads ``csrc/libbmc_b200.so`` and raises if it or a CUDA device is missing (no CPU path).
+"""
+from .bmc import BayesianModelCombination, orthogonalize_arrays
+from .inference_utils import (ConjugateSampler, GibbsResult, SimplexSampler, USVt_hat_extraction, gibbs_sampler,
+                              gibbs_sampler_literal, gibbs_sampler_simplex, run_gibbs, run_gibbs_simplex)
+from .sampling_utils import (PredictiveProblem, PredictiveResult, column_percentiles, coverage,
+                             coverage_from_counts, predictive_summary, rndm_m_random_calculator)
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "BayesianModelCombination",
+    "gibbs_sampler",
+    "gibbs_sampler_simplex",
+    "USVt_hat_extraction",
+    "coverage",
+    "rndm_m_random_calculator",
+]

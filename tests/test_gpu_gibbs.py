@@ -1,0 +1,219 @@
+"""Sampler parity on the GPU.
+
+Deterministic part: a device chain and the oracle driven by the same Philox stream must agree
+value by value (the oracle redoes the reference's per-iteration inverse / residual literally).
+Stochastic part: device posterior moments vs replicated runs of the oracle on NumPy's own
+generators (= the reference sampler, see tests/test_oracle_golden.py) within 3 Monte-Carlo
+standard errors.
+"""
+import numpy as np
+import pytest
+
+import cases
+from oracle import bmc_oracle as oc
+from oracle import philox as px
+
+pytestmark = pytest.mark.gpu
+
+
+def _ens():
+    frame, models = cases.ensemble_frame(11, 40, 5)
+    tr = frame.iloc[:28]
+    return oc.orthogonalize_arrays(tr[models].values, tr["truth"].values, 3)
+
+
+def _w_factor(w):
+    """cov = W diag(v) W'  ->  W diag(sqrt v): the colouring the sufficient-statistic kernel uses."""
+    w_inv = np.linalg.inv(w)
+
+    def factor(cov):
+        v = np.diag(w_inv @ cov @ w_inv.T)
+        return w * np.sqrt(v)[None, :]
+    return factor
+
+
+CASES = {
+    "toy_identity_prior": lambda: (*cases.toy_regression(), (np.array([0.0, 0.0]), np.eye(2), 1.0, 1.0)),
+    "toy_dense_prior": lambda: (*cases.toy_regression(),
+                                (np.array([0.3, -0.2]), np.array([[2.0, 0.3], [0.3, 0.5]]), 2.5, 0.7)),
+    "ensemble_default": lambda: (lambda r: (r["y"], r["U_hat"],
+                                            [np.zeros(3), np.diag(r["S_hat"] ** 2), 1.0, 0.02]))(_ens()),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_conjugate_chain_matches_oracle_fp64(name):
+    from pybmc_b200.inference_utils import ConjugateSampler, _finish_samples
+    y, X, prior = CASES[name]()
+    X = np.asarray(X, dtype=float)
+    sampler = ConjugateSampler(y, X, prior)
+    T, C, seed = 150, 3, 0xB200
+    samples, _, _ = sampler.run(T, n_chains=C, seed=seed, dtype="float64", stats="none")
+    got = _finish_samples(samples, True).reshape(C, T, -1)
+    for c in range(C):
+        ref = oc.gibbs_conjugate(y, X, T, prior, oc.PhiloxDraws(seed, c, px.TAG_GIBBS, _w_factor(sampler.w)))
+        np.testing.assert_allclose(got[c], ref, rtol=2e-9, atol=1e-12)
+
+
+def test_conjugate_fp32_tracks_fp64():
+    import pybmc_b200 as pb
+    r = _ens()
+    prior = [np.zeros(3), np.diag(r["S_hat"] ** 2), 1.0, 0.02]
+    a = pb.gibbs_sampler(r["y"], r["U_hat"], 50, prior, seed=5, dtype="float64")
+    b = pb.gibbs_sampler(r["y"], r["U_hat"], 50, prior, seed=5, dtype="float32")
+    assert a.shape == b.shape == (50, 4) and a.dtype == np.float64
+    # same Philox stream, fp32 arithmetic: 1e-5 relative (north-star fp32 tolerance) on the scale of each column
+    scale = np.abs(a).max(axis=0)
+    assert np.max(np.abs(a - b) / scale) < 2e-4
+    assert np.median(np.abs(a - b) / scale) < 1e-5
+
+
+def test_chain_ids_are_global():
+    """Chains are keyed by their global id: one launch of 8 == two launches of 4 (what sharding relies on)."""
+    import pybmc_b200 as pb
+    y, X, prior = CASES["toy_dense_prior"]()
+    whole = pb.run_gibbs(y, X, 40, prior, n_chains=8, seed=3).samples.reshape(8, 40, 3)
+    lo = pb.run_gibbs(y, X, 40, prior, n_chains=4, seed=3, chain_offset=0).samples.reshape(4, 40, 3)
+    hi = pb.run_gibbs(y, X, 40, prior, n_chains=4, seed=3, chain_offset=4).samples.reshape(4, 40, 3)
+    assert np.array_equal(whole[:4], lo) and np.array_equal(whole[4:], hi)
+
+
+def test_thinning_and_discard_select_the_same_iterates():
+    import pybmc_b200 as pb
+    y, X, prior = CASES["toy_identity_prior"]()
+    full = pb.gibbs_sampler(y, X, 60, prior, seed=9)
+    thin = pb.gibbs_sampler(y, X, 60, prior, seed=9, thin=7, discard=4)
+    assert np.array_equal(thin, full[4::7])
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 2e-4)])
+def test_device_moments_match_stored_samples(dtype, tol):
+    """fp64 moment sums accumulated in the kernel == moments of the samples it wrote."""
+    import pybmc_b200 as pb
+    y, X, prior = CASES["toy_dense_prior"]()
+    res = pb.run_gibbs(y, X, 300, prior, n_chains=64, seed=21, dtype=dtype, stats="full")
+    s = res.samples
+    np.testing.assert_allclose(res.mean, s.mean(axis=0), rtol=tol, atol=tol)
+    np.testing.assert_allclose(res.cov, np.cov(s.T, ddof=0), rtol=10 * tol, atol=tol)
+    per_chain = s.reshape(64, 300, 3).mean(axis=1)
+    np.testing.assert_allclose(res.chain_mean, per_chain, rtol=tol, atol=tol)
+
+
+def test_literal_kernel_matches_oracle_and_sufficient_statistic_law():
+    import pybmc_b200 as pb
+    r = _ens()
+    prior = [np.zeros(3), np.diag(r["S_hat"] ** 2), 1.0, 0.02]
+    T, seed = 80, 77
+    got = pb.gibbs_sampler_literal(r["y"], r["U_hat"], T, prior, n_chains=2, seed=seed).reshape(2, T, 4)
+
+    def precision_cholesky(cov):          # b = mean + L^-T z with A = inv(cov) = L L'
+        return np.linalg.inv(np.linalg.cholesky(np.linalg.inv(cov))).T
+    for c in range(2):
+        ref = oc.gibbs_conjugate(r["y"], r["U_hat"], T, prior,
+                                 oc.PhiloxDraws(seed, c, px.TAG_GIBBS, precision_cholesky))
+        np.testing.assert_allclose(got[c], ref, rtol=5e-8, atol=1e-10)
+    # non-orthonormal toy design, dense prior
+    y, X, prior = CASES["toy_dense_prior"]()
+    got = pb.gibbs_sampler_literal(y, X, 50, prior, n_chains=1, seed=4)
+    ref = oc.gibbs_conjugate(y, np.asarray(X, float), 50, prior, oc.PhiloxDraws(4, 0, px.TAG_GIBBS, precision_cholesky))
+    np.testing.assert_allclose(got, ref, rtol=5e-8, atol=1e-10)
+
+
+def _replicated_reference(fn, reps, base_seed):
+    out = []
+    for r in range(reps):
+        np.random.seed(base_seed + r)
+        out.append(fn(oc.NumpyDraws(cases.SeededFactory(10_000 * (base_seed + r)))))
+    return out
+
+
+def _assert_within_mcse(gpu_value, rep_values, gpu_se, label, k=3.0):
+    rep_values = np.asarray(rep_values)
+    centre = rep_values.mean(axis=0)
+    se = rep_values.std(axis=0, ddof=1) / np.sqrt(len(rep_values))
+    z = np.abs(gpu_value - centre) / np.sqrt(se ** 2 + gpu_se ** 2)
+    assert np.all(z < k), f"{label}: z = {z}"
+
+
+def test_conjugate_posterior_matches_reference_sampler_statistically():
+    import pybmc_b200 as pb
+    r = _ens()
+    prior = [np.zeros(3), np.diag(r["S_hat"] ** 2), 1.0, 0.02]
+    T_ref, reps = 1500, 12
+    runs = _replicated_reference(lambda d: oc.gibbs_conjugate(r["y"], r["U_hat"], T_ref, prior, d), reps, 100)
+    for dtype in ("float64", "float32"):
+        res = pb.run_gibbs(r["y"], r["U_hat"], 400, prior, n_chains=2048, seed=1, dtype=dtype, keep_samples=False)
+        n_eff = 400 * 2048
+        sd = np.sqrt(np.diag(res.cov))
+        _assert_within_mcse(res.mean, [s.mean(axis=0) for s in runs], sd / np.sqrt(n_eff), f"mean {dtype}")
+        _assert_within_mcse(sd, [s.std(axis=0) for s in runs], sd / np.sqrt(2 * n_eff), f"sd {dtype}")
+        corr = res.cov / np.outer(sd, sd)
+        ref_corr = [np.corrcoef(s.T) for s in runs]
+        _assert_within_mcse(corr[np.triu_indices(4, 1)], [c[np.triu_indices(4, 1)] for c in ref_corr],
+                            1.0 / np.sqrt(n_eff), f"corr {dtype}")
+        # analytic anchor for default priors: E[b_k] ~ c_k / (1 + s2 / S_k^2)
+        c = r["U_hat"].T @ r["y"]
+        s2 = res.mean[-1] ** 2
+        assert np.allclose(res.mean[:3], c / (1 + s2 / r["S_hat"] ** 2), rtol=2e-3, atol=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+def _simplex_case():
+    r = _ens()
+    return r["y"], r["U_hat"], r["Vt_hat"], r["S_hat"]
+
+
+def test_simplex_chain_matches_oracle_fp64(capsys):
+    import pybmc_b200 as pb
+    y, X, Vt, S = _simplex_case()
+    burn, T, seed = 120, 200, 0xB202
+    res = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02, n_chains=3, seed=seed)
+    got = res.samples.reshape(3, T, 4)
+    for c in range(3):
+        ref, acc = oc.gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02,
+                                    draws=oc.PhiloxDraws(seed, c, px.TAG_SIMPLEX, lambda cov: np.sqrt(cov)),
+                                    return_acceptance=True)
+        np.testing.assert_allclose(got[c], ref, rtol=1e-8, atol=1e-11)
+        assert round(res.acceptance[c] * T) == acc
+        assert 0 < acc < T
+    # toy case of the upstream tests (non-orthonormal X, weights on the boundary)
+    y, X, Vt, S = cases.toy_simplex()
+    got = pb.gibbs_sampler_simplex(y, X, Vt, S, 100, [1.0, 1.0], burn=10, stepsize=0.01, seed=6)
+    assert "Acceptance rate:" in capsys.readouterr().out
+    ref = oc.gibbs_simplex(y, X, Vt, S, 100, [1.0, 1.0], burn=10, stepsize=0.01,
+                           draws=oc.PhiloxDraws(6, 0, px.TAG_SIMPLEX, lambda cov: np.sqrt(cov)))
+    np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-11)
+
+
+def test_simplex_validation_errors():
+    import pybmc_b200 as pb
+    y, X, Vt, S = cases.toy_simplex()
+    with pytest.raises(ValueError):
+        pb.gibbs_sampler_simplex(y, X, Vt, S, 10, [1.0, 1.0], burn=-1)
+    with pytest.raises(ValueError):
+        pb.gibbs_sampler_simplex(y, X, Vt, S, 10, [1.0, 1.0], stepsize=-0.01)
+
+
+def test_simplex_posterior_matches_reference_sampler_statistically():
+    """Slow-mixing chain: Monte-Carlo errors come from replicated reference chains, not a formula."""
+    import pybmc_b200 as pb
+    y, X, Vt, S = _simplex_case()
+    burn, T, reps = 400, 1500, 12
+    runs = _replicated_reference(
+        lambda d: oc.gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02, draws=d), reps, 300)
+    for dtype in ("float64", "float32"):
+        res = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02, n_chains=1024, seed=2,
+                                   dtype=dtype, keep_samples=False)
+        # the device estimate averages 1024 chains of the same length: its error is the replicate spread / 32
+        rep_means = np.array([s.mean(axis=0) for s in runs])
+        gpu_se = rep_means.std(axis=0, ddof=1) / np.sqrt(1024)
+        _assert_within_mcse(res.mean, rep_means, gpu_se, f"simplex mean {dtype}")
+        rep_sd = np.array([s.std(axis=0) for s in runs])
+        chain_sd_se = rep_sd.std(axis=0, ddof=1) / np.sqrt(1024)
+        # pooled sd over chains includes between-chain spread of the means; compare within-chain sd instead
+        within = np.sqrt(np.maximum(np.diag(res.cov) - res.chain_mean.var(axis=0), 0.0))
+        _assert_within_mcse(within, rep_sd, chain_sd_se + 0.02 * rep_sd.mean(axis=0), f"simplex sd {dtype}")
+        w = res.mean[:3] @ Vt + 1.0 / Vt.shape[1]
+        assert np.all(w > -1e-6) and abs(w.sum() - 1.0) < 1e-8
+        acc_ref = np.mean([np.mean(np.any(np.diff(s[:, :3], axis=0) != 0, axis=1)) for s in runs])
+        assert abs(res.acceptance.mean() - acc_ref) < 0.03
