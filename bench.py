@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""Benchmark of the pyBMC inference hot path on B200 (driver contract: see README / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+Headline workload = BASELINE.json configs[2]: synthetic ensemble of 16 models x 3000 points,
+K = 8 SVD components, 65,536 conjugate-Gibbs chains x 10,000 iterations per GPU (chains shard
+across ranks with no data-path collective: weak scaling).  A "step" is one full run of those chains.
+
+  value  chain-iterations / s, whole job, problem constants resident in HBM (CUDA events)
+  e2e    the same metric through the public API `pybmc_b200.run_gibbs` with host NumPy inputs:
+         H2D of (y, X), sufficient statistics, sampler, D2H of moments + the kept samples
+  extra  the other metric of BASELINE.json (posterior-pred samples x points / s, configs[3]),
+         the simplex sampler (configs[1]), the fp64 sampler and an HBM-bound kernel of the path
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gibbs_chain_iters_per_sec"
+UNIT = "chain-iters/s"
+CHAINS_PER_GPU = 65536
+ITERATIONS = 10000
+KEEP_PER_CHAIN = 10
+SEED = 0xB200 + 3
+
+# warp-level instructions the conjugate kernel issues per chain-iteration and warp (fp32, K=8, full
+# cross moments), from profiles/ (ncu smsp__inst_executed.sum / (chains/32 * iterations)); the
+# roofline "achieved" below is this constant x measured chain-iterations/s
+INST_PER_CHAIN_ITER = {"f32": None}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------------
+def config3_ensemble():
+    rng = np.random.default_rng(1003)
+    n, m = 3000, 16
+    t = np.cumsum(rng.uniform(5, 15, n))
+    preds = t[:, None] * (1 + rng.normal(0, 0.003, m))[None, :] + rng.normal(0, 2, m)[None, :] \
+        + rng.normal(0, 0.5, (n, m))
+    truth = t + rng.normal(0, 0.15, n)
+    return preds, truth
+
+
+def config1_ensemble():
+    """Seeded surrogate of the missing selected_data.h5: 629 nuclei x 15 mass models."""
+    rng = np.random.default_rng(1001)
+    pts = [(nn, z) for z in range(8, 111, 2) for nn in range(z, min(161, int(1.6 * z) + 12), 2)]
+    pts = np.array(pts[:: max(1, len(pts) // 629)][:629], dtype=float)
+    nn, z = pts[:, 0], pts[:, 1]
+    a = nn + z
+
+    def semf(c):
+        av, as_, ac, aa, ap = c
+        return av * a - as_ * a ** (2 / 3) - ac * z * (z - 1) / a ** (1 / 3) - aa * (nn - z) ** 2 / a + ap / np.sqrt(a)
+    base = np.array([15.8, 18.3, 0.714, 23.2, 12.0])
+    truth = semf(base) + rng.normal(0, 0.15, len(a))
+    preds = np.column_stack([semf(base * (1 + rng.normal(0, 0.003, 5))) + rng.normal(0, 2.0)
+                             + rng.normal(0, 0.5, len(a)) for _ in range(15)])
+    return preds, truth
+
+
+def config4_inputs(n_points, n_draws, k=16):
+    rng = np.random.default_rng(1004)
+    m = 24
+    preds = rng.uniform(100, 2000, n_points)[:, None] + rng.normal(0, 3.0, (n_points, m))
+    vt = rng.normal(size=(k, m)) * 0.03
+    beta_star = rng.normal(0, 1, k)
+    theta = np.column_stack([beta_star[None, :] + 0.1 * rng.normal(size=(n_draws, k)),
+                             np.abs(rng.normal(0.15, 0.01, n_draws))])
+    u = preds @ vt.T
+    truth = preds.mean(axis=1) + u @ beta_star + rng.normal(0, 0.15, n_points)
+    return preds, vt, theta, truth
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def flush_l2(torch, buf):
+    buf.add_(1)          # 512 MiB read + write > 126 MB L2
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on NumPy's generators (= the reference algorithm)
+# ------------------------------------------------------------------------------------------------
+def _cpu_chain(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    y, X, prior, iters, seed = args
+    from oracle import bmc_oracle as oc
+    np.random.seed(seed)
+    t0 = time.perf_counter()
+    oc.gibbs_conjugate(y, X, iters, prior)
+    return time.perf_counter() - t0
+
+
+def cpu_problem():
+    from oracle import bmc_oracle as oc
+    preds, truth = config3_ensemble()
+    r = oc.orthogonalize_arrays(preds, truth, 8, full_matrices=False)
+    prior = [np.zeros(8), np.diag(r["S_hat"] ** 2), 1.0, 0.02]
+    return r["y"], np.ascontiguousarray(r["U_hat"]), prior
+
+
+def cpu_sampler_rate(iters_per_chain, pool, cores, problem):
+    y, X, prior = problem
+    t0 = time.perf_counter()
+    pool.map(_cpu_chain, [(y, X, prior, iters_per_chain, 1000 + c) for c in range(cores)])
+    dt = time.perf_counter() - t0
+    return cores * iters_per_chain / dt, dt
+
+
+def run_reference(args):
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ["OMP_NUM_THREADS"] = "1"
+    cores = os.cpu_count() or 1
+    problem = cpu_problem()
+    iters = 1500
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_sampler_rate(200, pool, cores, problem)
+        times = []
+        for _ in range(args.steps):
+            _, dt = cpu_sampler_rate(iters, pool, cores, problem)
+            times.append(dt)
+    total = float(np.sum(times))
+    value = cores * iters * args.steps / total
+    sample = f"{cores} chains x {iters} iterations per step on {cores} host processes (oracle port, NumPy RNG)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[2]: synthetic ensemble 16 models x 3000 points, K=8 SVD components, "
+                        "conjugate Gibbs, 65536 chains x 10000 iterations per GPU",
+            "n_points": 3000, "n_models": 16, "components": 8, "chains_per_gpu": CHAINS_PER_GPU,
+            "chains_total": CHAINS_PER_GPU * n_gpus, "iterations": ITERATIONS, "kept_per_chain": KEEP_PER_CHAIN,
+            "moments": "full cross moments in fp64", "sharding": f"chains over {n_gpus} GPU(s), no data-path collective; "
+            "one all-reduce of the 54 moment sums per step",
+            "l2": "512 MiB buffer rewritten between timed steps (working set is K-sized, not L2-resident data)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import pybmc_b200 as pb
+    from pybmc_b200 import _lib
+    from pybmc_b200.inference_utils import ConjugateSampler, SimplexSampler
+    from pybmc_b200.sampling_utils import PredictiveProblem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pybmc_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- set-up (untimed): orthogonalise on the device, build the resident sampler -----------------
+    preds, truth = config3_ensemble()
+    orth = pb.orthogonalize_arrays(preds, truth, 8)
+    y, X = orth["y"], orth["U_hat"]
+    prior = [np.zeros(8), np.diag(orth["S_hat"] ** 2), 1.0, 0.02]
+    sampler = ConjugateSampler(y, X, prior, device=dev)
+    thin = ITERATIONS // KEEP_PER_CHAIN
+    chain0 = rank * CHAINS_PER_GPU
+    flush = torch.zeros(128 * 2 ** 20, dtype=torch.float32, device=dev)
+
+    def device_step(dtype="float32"):
+        samples, cstats, meta = sampler.run(ITERATIONS, CHAINS_PER_GPU, SEED, dtype, thin, 0, True, "full", chain0)
+        total = cstats.sum(dim=1)
+        if world > 1:
+            dist.all_reduce(total)              # the only collective: 54 fp64 moment sums
+        return samples, total
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        ms = []
+        for _ in range(steps):
+            flush_l2(torch, flush)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        barrier()
+        return max_over_ranks(float(np.sum(ms))) / steps
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_step = timed(device_step, args.steps, args.warmup)
+    clock_info = clocks.stop() if rank == 0 else None
+    units = CHAINS_PER_GPU * world * ITERATIONS
+    value = units / (ms_step * 1e-3)
+
+    # ---- e2e through the public API, host buffers in, host results out ------------------------------
+    y_h, X_h = np.ascontiguousarray(y), np.ascontiguousarray(X)
+
+    def e2e_step():
+        res = pb.run_gibbs(y_h, X_h, ITERATIONS, prior, n_chains=CHAINS_PER_GPU, seed=SEED, dtype="float32",
+                           thin=thin, stats="full", device=dev, chain_offset=chain0)
+        return res
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    barrier()
+    h2d = y_h.nbytes + X_h.nbytes + 8 * (8 + 4 * 8)            # design + OLS vector + problem constants
+    d2h = res.samples.nbytes + 8 * (54 + 9 * 9 + 1 + 9 * CHAINS_PER_GPU)
+    e2e = {"value": units / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": 1e3 * e2e_s}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "e2e": e2e, "gpu_launches": args.steps + args.steps, "clocks": clock_info}
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sm_mhz = (clock_info or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    per_gpu_rate = value / world
+    alg_bytes = CHAINS_PER_GPU * (KEEP_PER_CHAIN * 9 * 4 + 54 * 8 * 2 * (ITERATIONS // 64))
+    kernel_s = ms_step * 1e-3
+    inst = load_inst_per_iter()
+    issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9                    # warp-instructions / ns -> Ginst/s
+    line["roofline"] = {
+        "kernel": "gibbs_conjugate_kernel<float,8,2>",
+        "bound": "issue", "unit": "Gwarp-inst/s",
+        "achieved": (inst * per_gpu_rate / 32 / 1e9) if inst else None,
+        "peak": issue_peak, "frac": (inst * per_gpu_rate / 32 / 1e9 / issue_peak) if inst else None,
+        "peak_source": "148 SMs x 4 schedulers x 1 warp-inst/clk x SM clock sampled during the run",
+        "warp_inst_per_chain_iter": inst,
+        "traffic": load_dram_bytes(),
+        "hbm": {"bound": "hbm", "achieved": alg_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / kernel_s / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs"
+                if peaks else "fallback 6650 GB/s",
+                "note": "algorithmic bytes = kept samples + fp64 moment flushes; the sampler's state is K-sized "
+                        "and lives in registers, so HBM is not the bound (SURVEY.md section 8d)"}}
+
+    # ---- the rest of BASELINE.json's metric, measured the same way -------------------------------------
+    if rank == 0 or world > 1:
+        line["extra"] = extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ranks, barrier,
+                               flush, hbm_peak)
+    if rank == 0 and world == 1:
+        line["cpu_baseline"] = cpu_baseline()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_inst_per_iter():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))[
+            "gibbs_conjugate_f32_k8_full"]["warp_inst_per_chain_iter"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def load_dram_bytes():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))[
+            "gibbs_conjugate_f32_k8_full"]["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ranks, barrier, flush, hbm_peak):
+    from pybmc_b200.inference_utils import SimplexSampler
+    from pybmc_b200.sampling_utils import PredictiveProblem
+    from pybmc_b200 import _lib
+    lib = _lib.load()
+    out = {}
+    steps = max(1, min(args.steps, 3))
+    chain0 = rank * CHAINS_PER_GPU
+    thin = ITERATIONS // KEEP_PER_CHAIN
+
+    # conjugate sampler in fp64 (the reference's arithmetic type)
+    ms = timed(lambda: sampler.run(ITERATIONS // 4, CHAINS_PER_GPU, SEED, "float64", thin, 0, True, "full", chain0),
+               steps, 1)
+    out["gibbs_f64"] = {"value": CHAINS_PER_GPU * world * (ITERATIONS // 4) / (ms * 1e-3), "unit": UNIT,
+                        "ms_per_step": ms, "config": "same problem, fp64 arithmetic, 2500 iterations per chain"}
+
+    # simplex sampler, BASELINE configs[1]: nuclear-mass surrogate, 4096 chains per GPU
+    preds, truth = config1_ensemble()
+    rng = np.random.default_rng(1)
+    idx = rng.permutation(len(truth))[:377]
+    o = pb.orthogonalize_arrays(preds[idx], truth[idx], 3)
+    simplex = SimplexSampler(o["y"], o["U_hat"], o["Vt_hat"], o["S_hat"], [1.0, 0.02], 0.001, device=dev)
+    burn, iters, chains = 10000, 50000, 4096
+    ms = timed(lambda: simplex.run(iters, burn, chains, SEED, "float32", iters // 10, True, "full", rank * chains),
+               steps, 1)
+    out["simplex_f32"] = {"value": chains * world * (burn + iters) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                          "config": "configs[1] surrogate: 377 x 15, K=3, 4096 chains/GPU x (10000 burn + 50000)"}
+
+    # fused prediction, BASELINE configs[3]: 1e5 nuclei (sharded over ranks) x 1e5 draws x K=16
+    n_total, n_draws = 100_000, 100_000
+    per = -(-n_total // world) // 4 * 4 + (4 if (-(-n_total // world)) % 4 else 0)
+    lo, hi = min(rank * per, n_total), min((rank + 1) * per, n_total)
+    preds, vt, theta, truth = config4_inputs(n_total, n_draws)
+    prob = PredictiveProblem(preds[lo:hi], theta, vt, truth=truth[lo:hi], dtype="float32", device=dev, point0=lo)
+    nbytes = int(lib.bmc_predict_workspace_bytes(_lib.F32, hi - lo, 5, n_draws))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    q = [2.5, 16.0, 50.0, 84.0, 97.5]
+    holder = {}
+
+    def pred_step():
+        holder["r"] = prob.run(percentiles=q, seed=SEED, as_numpy=False, workspace=ws)
+    ms = timed(pred_step, steps, 1)
+    out["predict_f32"] = {"metric": "posterior_pred_samples_x_points_per_sec",
+                          "value": n_total * n_draws / (ms * 1e-3), "unit": "samples*points/s", "ms_per_step": ms,
+                          "passes": holder["r"].passes,
+                          "config": "configs[3]: 1e5 nuclei x 1e5 draws x K=16, mean/var/5 percentiles/coverage "
+                                    "counts, no S x N matrix, nuclei sharded over ranks"}
+    del prob, ws
+
+    # an HBM-bound kernel of the path: order counts of a materialised matrix (coverage())
+    if rank == 0:
+        s_rows, n_cols = 10000, 65536
+        mat = torch.randn((s_rows, n_cols), dtype=torch.float64, device=dev)
+        tr = torch.zeros(n_cols, dtype=torch.float64, device=dev)
+        c1 = torch.empty(n_cols, dtype=torch.int64, device=dev)
+        c2 = torch.empty(n_cols, dtype=torch.int64, device=dev)
+
+        def cov_step():
+            _lib.check(lib.bmc_coverage_counts(mat.data_ptr(), s_rows, n_cols, n_cols, tr.data_ptr(), c1.data_ptr(),
+                                               c2.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        for _ in range(2):
+            cov_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush_l2(torch, flush)
+        e0.record(); cov_step(); e1.record(); e1.synchronize()
+        gbs = mat.numel() * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        out["coverage_counts_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": gbs / hbm_peak, "config": "10000 x 65536 fp64 matrix read once"}
+        del mat
+    barrier()
+    return out
+
+
+def cpu_baseline():
+    """Reference algorithm (oracle port) on the host cores, bounded sample of the same workload."""
+    import multiprocessing as mp
+    os.environ["OMP_NUM_THREADS"] = "1"
+    cores = os.cpu_count() or 1
+    problem = cpu_problem()
+    iters = 4000
+    with mp.get_context("fork").Pool(cores) as pool:
+        cpu_sampler_rate(100, pool, cores, problem)
+        rate, dt = cpu_sampler_rate(iters, pool, cores, problem)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores} chains x {iters} iterations of the same 3000 x 8 problem, one process per core, "
+                      f"{dt:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

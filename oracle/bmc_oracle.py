@@ -81,7 +81,7 @@ class PhiloxDraws:
         z = np.array(px.normal_vector(k, self.it, self.chain, self.tag, self.key))
         f = np.linalg.cholesky(cov) if self.factor is None else self.factor(cov)
         # a wrong factor would silently sample another law: refuse it
-        if not np.allclose(f @ f.T, cov, rtol=1e-9, atol=1e-300):
+        if not np.allclose(f @ f.T, cov, rtol=1e-9, atol=1e-12 * np.abs(cov).max()):
             raise AssertionError("factor does not reproduce the covariance")
         return np.asarray(mean, dtype=float) + f @ z
 

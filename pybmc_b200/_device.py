@@ -45,7 +45,7 @@ def to_device(a, dev, dtype=torch.float64):
     """Host array -> contiguous device tensor through pinned staging memory."""
     if isinstance(a, torch.Tensor):
         return a.to(device=dev, dtype=dtype).contiguous()
-    host = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+    host = torch.from_numpy(np.array(a, dtype=np.float64, order="C", copy=True))
     if host.numel() > 4096:
         host = host.pin_memory()
     t = host.to(dev, non_blocking=True)

@@ -80,7 +80,7 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct Layout {
     // byte offsets inside the workspace for a chunk of nc nuclei
-    size_t center, scale, win_lo, win_hi, brk_lo, brk_hi, brk_below, cnt_below, cnt_in, resolved, cand, mom, c_lt,
+    size_t center, scale, win_lo, win_hi, brk_lo, brk_hi, pair_hi, aux, phase, cnt_below, cnt_in, sub, resolved, cand, mom, c_lt,
         c_le, flag, list_a, list_b, counter, plan, total;
 };
 
@@ -102,9 +102,12 @@ Layout make_layout(long long nc, int nq, int cap, size_t sz, int max_slots) {
     l.win_hi = take(nqn * sz);
     l.brk_lo = take(nqn * sz);
     l.brk_hi = take(nqn * sz);
-    l.brk_below = take(nqn * 4);
+    l.pair_hi = take(nqn * sz);
+    l.aux = take(nqn * sz);
+    l.phase = take(nqn);
     l.cnt_below = take(nqn * 4);
     l.cnt_in = take(nqn * 4);
+    l.sub = take(nqn * 4 * kSubBins);
     l.resolved = take(nqn);
     l.cand = take(nqn * cap * sz);
     l.mom = take(static_cast<size_t>(max_slots) * 2 * nc * sizeof(double));
@@ -227,9 +230,9 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         BMC_LAUNCH_CHECK();
         predict_window_kernel<real><<<static_cast<unsigned>((nqn + 255) / 256), 256, 0, st>>>(
             n, p->nq, ws + lay.center, ws + lay.scale, d_zq, d_hw, ws + lay.win_lo, ws + lay.win_hi, ws + lay.brk_lo,
-            ws + lay.brk_hi, reinterpret_cast<unsigned int*>(ws + lay.brk_below),
+            ws + lay.brk_hi, ws + lay.pair_hi, ws + lay.aux, ws + lay.phase,
             reinterpret_cast<unsigned int*>(ws + lay.cnt_below), reinterpret_cast<unsigned int*>(ws + lay.cnt_in),
-            ws + lay.resolved);
+            reinterpret_cast<unsigned int*>(ws + lay.sub), ws + lay.resolved);
         BMC_LAUNCH_CHECK();
 
         PredictArgs a{};
@@ -251,6 +254,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         a.win_hi = ws + lay.win_hi;
         a.cnt_below = reinterpret_cast<unsigned int*>(ws + lay.cnt_below);
         a.cnt_in = reinterpret_cast<unsigned int*>(ws + lay.cnt_in);
+        a.sub_cnt = reinterpret_cast<unsigned int*>(ws + lay.sub);
         a.cand = ws + lay.cand;
         a.cand_cap = plan.cand_cap;
         a.first = 1;
@@ -274,9 +278,12 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         s.win_hi = a.win_hi;
         s.brk_lo = ws + lay.brk_lo;
         s.brk_hi = ws + lay.brk_hi;
-        s.brk_below = reinterpret_cast<unsigned int*>(ws + lay.brk_below);
+        s.pair_hi = ws + lay.pair_hi;
+        s.aux = ws + lay.aux;
+        s.phase = ws + lay.phase;
         s.cnt_below = a.cnt_below;
         s.cnt_in = a.cnt_in;
+        s.sub_cnt = a.sub_cnt;
         s.cand = a.cand;
         s.cand_cap = plan.cand_cap;
         s.resolved = ws + lay.resolved;

@@ -23,6 +23,7 @@
 #pragma once
 #include <cfloat>
 #include "rng.cuh"
+#include "select_logic.h"
 #include "tma.cuh"
 
 namespace bmc {
@@ -30,6 +31,7 @@ namespace bmc {
 constexpr int kPredTile = 256;        // posterior draws per staged tile
 constexpr int kPredWarps = 8;
 constexpr int kMaxQuant = 8;
+constexpr int kSubBins = kSelSlices;  // slices of a window counted for the overflow fallback
 
 struct PredictArgs {
     // per-nucleus inputs (this launch's chunk; index 0 is global nucleus point0)
@@ -53,6 +55,7 @@ struct PredictArgs {
     void* win_hi;             // real
     unsigned int* cnt_below;
     unsigned int* cnt_in;
+    unsigned int* sub_cnt;    // [n*nq][kSubBins] hits per equal-width slice of the window
     void* cand;               // [n*nq][cand_cap] real
     int cand_cap;
     // first-pass accumulators
@@ -230,8 +233,16 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
                             if (lane == leader) base = atomicAdd(a.cnt_in + idx, static_cast<unsigned int>(__popc(mask)));
                             base = __shfl_sync(0xffffffffu, base, leader);
                             const unsigned int pos = base + __popc(mask & ((1u << lane) - 1u));
-                            if (w && pos < static_cast<unsigned int>(a.cand_cap))
-                                static_cast<real*>(a.cand)[idx * a.cand_cap + pos] = x[q];
+                            if (w) {
+                                if (pos < static_cast<unsigned int>(a.cand_cap))
+                                    static_cast<real*>(a.cand)[idx * a.cand_cap + pos] = x[q];
+                                // which 1/32 slice of the window: lets an overflowing window be narrowed
+                                // with exact counts whatever the distribution (atoms, heavy tails)
+                                const real rel = (x[q] - wlo[q][j]) * (real(kSubBins) / (whi[q][j] - wlo[q][j]));
+                                int bin = static_cast<int>(rel);
+                                bin = bin < 0 ? 0 : (bin > kSubBins - 1 ? kSubBins - 1 : bin);
+                                atomicAdd(a.sub_cnt + idx * kSubBins + bin, 1u);
+                            }
                         }
                     }
                 }
@@ -285,9 +296,12 @@ struct SelectArgs {
     void* win_hi;
     void* brk_lo;              // hard bracket known to contain the target
     void* brk_hi;
-    unsigned int* brk_below;   // #(x < brk_lo)
+    void* pair_hi;             // split-mode state (select_logic.h)
+    void* aux;
+    unsigned char* phase;
     unsigned int* cnt_below;
     unsigned int* cnt_in;
+    unsigned int* sub_cnt;
     void* cand;
     int cand_cap;
     unsigned char* resolved;   // [n*nq]
@@ -314,19 +328,15 @@ struct SelectArgs {
     int* next_count;
 };
 
-template <typename real>
-__device__ __forceinline__ real next_up(real x);
-template <>
-__device__ __forceinline__ float next_up<float>(float x) { return nextafterf(x, FLT_MAX); }
-template <>
-__device__ __forceinline__ double next_up<double>(double x) { return nextafter(x, DBL_MAX); }
-
-// one warp per (nucleus, quantile); candidates are bitonic-sorted in shared memory
+// one warp per (nucleus, quantile): sort the window's candidates in shared memory when they fit,
+// then let sel_decide (select_logic.h) read the answer or choose the next window
 template <typename real>
 __global__ void __launch_bounds__(128) predict_select_kernel(const SelectArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    real* const buf = reinterpret_cast<real*>(smem_raw) + static_cast<size_t>(warp) * a.cand_cap;
+    int p2cap = 1;
+    while (p2cap < a.cand_cap) p2cap <<= 1;
+    real* const buf = reinterpret_cast<real*>(smem_raw) + static_cast<size_t>(warp) * p2cap;
     const long long item = static_cast<long long>(blockIdx.x) * 4 + warp;       // (quad slot, q, j)
     const long long per_quad = 4ll * a.nq;
     const long long qslot = item / per_quad;
@@ -355,20 +365,27 @@ __global__ void __launch_bounds__(128) predict_select_kernel(const SelectArgs a)
     }
     if (a.resolved[idx]) return;
 
-    real* const wlo = static_cast<real*>(a.win_lo) + idx;
-    real* const whi = static_cast<real*>(a.win_hi) + idx;
-    real* const blo = static_cast<real*>(a.brk_lo) + idx;
-    real* const bhi = static_cast<real*>(a.brk_hi) + idx;
+    SelState<real> st;
+    st.lo = static_cast<real*>(a.win_lo)[idx];
+    st.hi = static_cast<real*>(a.win_hi)[idx];
+    st.blo = static_cast<real*>(a.brk_lo)[idx];
+    st.bhi = static_cast<real*>(a.brk_hi)[idx];
+    st.pair_hi = static_cast<real*>(a.pair_hi)[idx];
+    st.aux = static_cast<real*>(a.aux)[idx];
+    st.phase = a.phase[idx];
     const long long r = a.rank[j];
-    const int need_hi = a.frac[j] > 0.0 ? 1 : 0;
+    const bool need_pair = a.frac[j] > 0.0;
     const long long cb = a.cnt_below[idx], cw = a.cnt_in[idx];
-    const bool inside = r >= cb && r + need_hi < cb + cw;
-    const real lo = *wlo, hi = *whi;
+    const long long t1 = st.phase == 2 ? r + 1 : r;
+    const long long t2 = t1 + ((st.phase == 0 && need_pair) ? 1 : 0);
+    const bool inside = t1 >= cb && t2 < cb + cw;
+    const real* src = static_cast<const real*>(a.cand) + idx * a.cand_cap;
 
+    bool stored_equal = false;
+    real stored_value = real(0);
     if (inside && cw <= a.cand_cap) {
         int p2 = 1;
         while (p2 < cw) p2 <<= 1;
-        const real* src = static_cast<const real*>(a.cand) + idx * a.cand_cap;
         for (int i = lane; i < p2; i += 32) buf[i] = i < cw ? src[i] : real(FLT_MAX);
         __syncwarp();
         for (int size = 2; size <= p2; size <<= 1)
@@ -385,75 +402,44 @@ __global__ void __launch_bounds__(128) predict_select_kernel(const SelectArgs a)
                 }
                 __syncwarp();
             }
-        if (lane == 0) {
-            const double v0 = static_cast<double>(buf[r - cb]);
-            const double v1 = need_hi ? static_cast<double>(buf[r - cb + 1]) : v0;
-            // numpy's linear interpolation: a + (b-a) t, taken from the upper end when t >= 1/2
-            const double t = a.frac[j], diff = v1 - v0;
-            double res = v0 + diff * t;
-            if (t >= 0.5) res = v1 - diff * (1.0 - t);
-            if (diff == 0.0) res = v0;
-            a.out_quant[static_cast<long long>(j) * a.ld_quant + a.out_offset + n] = (a.mu ? a.mu[n] : 0.0) + res;
-            a.resolved[idx] = 1;
-            // park the window so later passes over this quad collect nothing for it
-            *wlo = real(FLT_MAX);
-            *whi = real(FLT_MAX);
+    } else if (inside) {
+        real vmin = real(FLT_MAX), vmax = -real(FLT_MAX);
+        for (int i = lane; i < a.cand_cap; i += 32) {
+            vmin = fmin(vmin, src[i]);
+            vmax = fmax(vmax, src[i]);
         }
-        return;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+            vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        }
+        stored_equal = vmin == vmax;
+        stored_value = vmin;
     }
     if (lane != 0) return;
-    // not resolved: tighten the hard bracket, pick the next window, ask for another pass
-    real nlo, nhi;
-    const real width = hi - lo;
-    if (r < cb) {                                   // target lies below the window
-        *bhi = lo;
-        nhi = lo;
-        nlo = lo - real(4) * width;
-        if (nlo < *blo) nlo = *blo;
-    } else if (r + need_hi >= cb + cw && !(inside && cw > a.cand_cap)) {   // above (or straddling the top edge)
-        if (r >= cb + cw) {
-            *blo = hi;
-            a.brk_below[idx] = static_cast<unsigned int>(cb + cw);
-            nlo = hi;
-        } else {
-            nlo = lo;                               // straddle: keep the lower edge, grow upwards
-        }
-        nhi = hi + real(4) * width;
-        if (nhi > *bhi) nhi = *bhi;
-    } else {                                        // inside but too many candidates: shrink
-        *blo = lo;
-        *bhi = hi;
-        a.brk_below[idx] = static_cast<unsigned int>(cb);
-        const real next_lo = next_up<real>(lo);
-        if (!(next_lo < hi)) {
-            // the window holds a single representable value: every candidate equals lo
-            a.out_quant[static_cast<long long>(j) * a.ld_quant + a.out_offset + n] =
-                (a.mu ? a.mu[n] : 0.0) + static_cast<double>(lo);
-            a.resolved[idx] = 1;
-            *wlo = real(FLT_MAX);
-            *whi = real(FLT_MAX);
-            return;
-        }
-        const double f0 = static_cast<double>(r - cb) / static_cast<double>(cw);
-        const double f1 = static_cast<double>(r + need_hi - cb + 1) / static_cast<double>(cw);
-        const double margin = 0.25 * static_cast<double>(a.cand_cap) / static_cast<double>(cw);
-        nlo = lo + static_cast<real>((f0 - margin) * static_cast<double>(width));
-        nhi = lo + static_cast<real>((f1 + margin) * static_cast<double>(width));
-        if (nlo < lo) nlo = lo;
-        if (nhi > hi) nhi = hi;
-        if (!(nlo < nhi)) {                         // rounding collapsed it: bisect instead
-            nlo = lo;
-            nhi = lo + width * real(0.5);
-            if (!(nlo < nhi)) nhi = next_lo;
-        }
-        if (nlo == lo && nhi == hi) nhi = lo + width * real(0.5);
-        if (!(nhi > nlo)) nhi = next_up<real>(nlo);
+    unsigned int* sub = a.sub_cnt + idx * kSubBins;
+    double v0 = 0.0, v1 = 0.0;
+    const SelAction act = sel_decide<real>(st, r, need_pair, cb, cw, sub, a.cand_cap, buf, stored_equal,
+                                           stored_value, &v0, &v1);
+    if (act == kSelResolved) {
+        a.out_quant[static_cast<long long>(j) * a.ld_quant + a.out_offset + n] =
+            (a.mu ? a.mu[n] : 0.0) + sel_lerp(v0, v1, a.frac[j]);
+        a.resolved[idx] = 1;
+        // park the window so later passes over this quad collect nothing for it
+        static_cast<real*>(a.win_lo)[idx] = real(FLT_MAX);
+        static_cast<real*>(a.win_hi)[idx] = real(FLT_MAX);
+        return;
     }
-    if (!(nhi > nlo)) nhi = next_up<real>(nlo);
-    *wlo = nlo;
-    *whi = nhi;
+    static_cast<real*>(a.win_lo)[idx] = st.lo;
+    static_cast<real*>(a.win_hi)[idx] = st.hi;
+    static_cast<real*>(a.brk_lo)[idx] = st.blo;
+    static_cast<real*>(a.brk_hi)[idx] = st.bhi;
+    static_cast<real*>(a.pair_hi)[idx] = st.pair_hi;
+    static_cast<real*>(a.aux)[idx] = st.aux;
+    a.phase[idx] = static_cast<unsigned char>(st.phase);
     a.cnt_below[idx] = 0u;
     a.cnt_in[idx] = 0u;
+    for (int b = 0; b < kSubBins; ++b) sub[b] = 0u;
     if (atomicExch(a.quad_flag + quad, 1) == 0) {
         const int pos = atomicAdd(a.next_count, 1);
         a.next_list[pos] = quad;
@@ -488,8 +474,8 @@ __global__ void predict_guess_kernel(const void* u_, long long n, int k, const d
 template <typename real>
 __global__ void predict_window_kernel(long long n, int nq, const void* center_, const void* scale_,
                                       const double* zq, const double* hw, void* win_lo, void* win_hi,
-                                      void* brk_lo, void* brk_hi, unsigned int* brk_below, unsigned int* cnt_below,
-                                      unsigned int* cnt_in, unsigned char* resolved) {
+                                      void* brk_lo, void* brk_hi, void* pair_hi, void* aux, unsigned char* phase, unsigned int* cnt_below,
+                                      unsigned int* cnt_in, unsigned int* sub_cnt, unsigned char* resolved) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n * nq) return;
     const long long p = i / nq;
@@ -500,14 +486,17 @@ __global__ void predict_window_kernel(long long n, int nq, const void* center_, 
     if (!(s > tiny)) s = tiny;
     real lo = static_cast<real>(c + s * (zq[j] - hw[j]));
     real hi = static_cast<real>(c + s * (zq[j] + hw[j]));
-    if (!(hi > lo)) hi = next_up<real>(lo);
+    if (!(hi > lo)) hi = SelLimits<real>::up(lo);
     static_cast<real*>(win_lo)[i] = lo;
     static_cast<real*>(win_hi)[i] = hi;
     static_cast<real*>(brk_lo)[i] = -real(FLT_MAX);
     static_cast<real*>(brk_hi)[i] = real(FLT_MAX);
-    brk_below[i] = 0u;
+    static_cast<real*>(pair_hi)[i] = real(FLT_MAX);
+    static_cast<real*>(aux)[i] = real(0);
+    phase[i] = 0;
     cnt_below[i] = 0u;
     cnt_in[i] = 0u;
+    for (int b = 0; b < kSubBins; ++b) sub_cnt[i * kSubBins + b] = 0u;
     resolved[i] = 0;
 }
 

@@ -139,7 +139,7 @@ def test_conjugate_posterior_matches_reference_sampler_statistically():
     import pybmc_b200 as pb
     r = _ens()
     prior = [np.zeros(3), np.diag(r["S_hat"] ** 2), 1.0, 0.02]
-    T_ref, reps = 1500, 12
+    T_ref, reps = 1500, 40
     runs = _replicated_reference(lambda d: oc.gibbs_conjugate(r["y"], r["U_hat"], T_ref, prior, d), reps, 100)
     for dtype in ("float64", "float32"):
         res = pb.run_gibbs(r["y"], r["U_hat"], 400, prior, n_chains=2048, seed=1, dtype=dtype, keep_samples=False)
@@ -198,7 +198,7 @@ def test_simplex_posterior_matches_reference_sampler_statistically():
     """Slow-mixing chain: Monte-Carlo errors come from replicated reference chains, not a formula."""
     import pybmc_b200 as pb
     y, X, Vt, S = _simplex_case()
-    burn, T, reps = 400, 1500, 12
+    burn, T, reps = 400, 1500, 96
     runs = _replicated_reference(
         lambda d: oc.gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02, draws=d), reps, 300)
     for dtype in ("float64", "float32"):

@@ -110,7 +110,7 @@ def test_unmaterialised_equals_materialised_at_scale():
     full = prob.run(percentiles=q, seed=7, return_draws=True)
     lean = prob.run(percentiles=q, seed=7, return_draws=False)
     assert np.array_equal(full.percentiles, lean.percentiles)
-    assert np.array_equal(lean.percentiles, np.percentile(full.draws, q, axis=0))
+    np.testing.assert_allclose(lean.percentiles, np.percentile(full.draws, q, axis=0), rtol=1e-13, atol=0)
     c_lt, c_le = oc.order_counts(full.draws, truth)
     assert np.array_equal(lean.c_lt, c_lt) and np.array_equal(lean.c_le, c_le)
     np.testing.assert_allclose(lean.mean, full.draws.mean(axis=0), rtol=1e-12)
@@ -150,9 +150,9 @@ def test_rndm_m_random_calculator_dropin():
     theta = cases.posterior_like(13, 12000, 3)
     rndm_m, (lo, med, hi) = rndm_m_random_calculator(preds, theta, r["Vt_hat"], seed=11)
     assert rndm_m.shape == (10000, 7) and rndm_m.dtype == np.float64
-    assert np.array_equal(lo, np.percentile(rndm_m, 2.5, axis=0))
-    assert np.array_equal(med, np.percentile(rndm_m, 50, axis=0))
-    assert np.array_equal(hi, np.percentile(rndm_m, 97.5, axis=0))
+    np.testing.assert_allclose(lo, np.percentile(rndm_m, 2.5, axis=0), rtol=1e-13)
+    np.testing.assert_allclose(med, np.percentile(rndm_m, 50, axis=0), rtol=1e-13)
+    np.testing.assert_allclose(hi, np.percentile(rndm_m, 97.5, axis=0), rtol=1e-13)
     with pytest.raises(ValueError):                                  # < 10000 posterior rows (:57)
         rndm_m_random_calculator(preds, theta[:500], r["Vt_hat"])
     # distribution check against the reference path on NumPy's generator: 3 standard errors
