@@ -262,6 +262,12 @@ def run_native(args):
         barrier()
         return max_over_ranks(float(np.sum(ms))) / steps
 
+    if args.only == "predict":
+        out = extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ranks, barrier, flush, 6551.0,
+                     only_predict=True)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        return
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -324,6 +330,10 @@ def run_native(args):
                         "and lives in registers, so HBM is not the bound (SURVEY.md section 8d)"}}
 
     # ---- the rest of BASELINE.json's metric, measured the same way -------------------------------------
+    if args.only == "sampler":
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        return
     if rank == 0 or world > 1:
         line["extra"] = extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ranks, barrier,
                                flush, hbm_peak)
@@ -351,7 +361,8 @@ def load_dram_bytes():
         return None
 
 
-def extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ranks, barrier, flush, hbm_peak):
+def extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ranks, barrier, flush, hbm_peak,
+           only_predict=False):
     from pybmc_b200.inference_utils import SimplexSampler
     from pybmc_b200.sampling_utils import PredictiveProblem
     from pybmc_b200 import _lib
@@ -361,6 +372,15 @@ def extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ran
     chain0 = rank * CHAINS_PER_GPU
     thin = ITERATIONS // KEEP_PER_CHAIN
 
+    if not only_predict:
+        extras_samplers(out, timed, sampler, pb, dev, world, rank, steps)
+    return extras_predict(out, args, torch, dev, world, rank, timed, barrier, flush, hbm_peak, steps, only_predict)
+
+
+def extras_samplers(out, timed, sampler, pb, dev, world, rank, steps):
+    from pybmc_b200.inference_utils import SimplexSampler
+    chain0 = rank * CHAINS_PER_GPU
+    thin = ITERATIONS // KEEP_PER_CHAIN
     # conjugate sampler in fp64 (the reference's arithmetic type)
     ms = timed(lambda: sampler.run(ITERATIONS // 4, CHAINS_PER_GPU, SEED, "float64", thin, 0, True, "full", chain0),
                steps, 1)
@@ -379,6 +399,12 @@ def extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ran
     out["simplex_f32"] = {"value": chains * world * (burn + iters) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                           "config": "configs[1] surrogate: 377 x 15, K=3, 4096 chains/GPU x (10000 burn + 50000)"}
 
+
+
+def extras_predict(out, args, torch, dev, world, rank, timed, barrier, flush, hbm_peak, steps, only_predict):
+    from pybmc_b200.sampling_utils import PredictiveProblem
+    from pybmc_b200 import _lib
+    lib = _lib.load()
     # fused prediction, BASELINE configs[3]: 1e5 nuclei (sharded over ranks) x 1e5 draws x K=16
     n_total, n_draws = 100_000, 100_000
     per = -(-n_total // world) // 4 * 4 + (4 if (-(-n_total // world)) % 4 else 0)
@@ -401,7 +427,7 @@ def extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ran
     del prob, ws
 
     # an HBM-bound kernel of the path: order counts of a materialised matrix (coverage())
-    if rank == 0:
+    if rank == 0 and not only_predict:
         s_rows, n_cols = 10000, 65536
         mat = torch.randn((s_rows, n_cols), dtype=torch.float64, device=dev)
         tr = torch.zeros(n_cols, dtype=torch.float64, device=dev)
@@ -431,7 +457,7 @@ def cpu_baseline():
     os.environ["OMP_NUM_THREADS"] = "1"
     cores = os.cpu_count() or 1
     problem = cpu_problem()
-    iters = 4000
+    iters = 100000
     with mp.get_context("fork").Pool(cores) as pool:
         cpu_sampler_rate(100, pool, cores, problem)
         rate, dt = cpu_sampler_rate(iters, pool, cores, problem)
@@ -446,6 +472,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--only", default="all", choices=["all", "sampler", "predict"],
+                    help="profiling aid: restrict the run to one kernel family (no JSON contract)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
