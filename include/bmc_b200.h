@@ -150,15 +150,16 @@ int bmc_gibbs_simplex_run(int dtype, const bmc_simplex_problem* problem /*host*/
 
 typedef struct {
     int64_t n_points;          /* nuclei handled by this call                                      */
-    uint64_t point0;           /* global index of the first one (multiple of 4): noise is keyed on
-                                  the global index so results do not depend on the sharding        */
+    uint64_t point0;           /* global index of the first one: noise is keyed on the global index so
+                                  results do not depend on the sharding                            */
     int64_t n_draws;           /* S, posterior draws (reference: 10000, sampling_utils.py:57)      */
     int k;                     /* components (<= 16 in this version)                               */
     const void* u;             /* dev real [n_points][k]   preds Vt_hat'                           */
     const double* mu;          /* dev [n_points] mean over models (the 1/M term of :64), or NULL   */
     const double* truth;       /* dev [n_points] or NULL (no coverage counts)                      */
-    const void* theta_t;       /* dev real [k+1][n_draws] transposed draws, last row sigma (:60-61);
-                                  NULL = "matrix mode": the draws are `noise` itself               */
+    const void* theta;         /* dev real [n_draws][bmc_predict_theta_stride(k)] posterior draws, one row per
+                                  draw: beta in columns 0..k-1, sigma (:60-61) in column stride-4, zeros elsewhere;
+                                  NULL = "matrix mode": the draws are `noise` itself                  */
     int noise_mode;            /* BMC_NOISE_*                                                      */
     uint64_t seed;
     const void* noise;         /* dev real [n_draws][ld_noise] standard normals (external mode)    */
@@ -175,6 +176,7 @@ typedef struct {
  * = #(x < truth), #(x <= truth) (NULL without truth); draws_out [n_draws][ld_out] materialises
  * rndm_m = mu + x when not NULL.  Synchronises the stream (reads back the retry counter). */
 size_t bmc_predict_workspace_bytes(int dtype, int64_t n_points, int nq, int64_t n_draws);
+int bmc_predict_theta_stride(int k);
 int bmc_predict_fused(int dtype, const bmc_predict_problem* problem /*host*/, double* mean, double* var,
                       double* quant, int64_t* c_lt, int64_t* c_le, double* draws_out, int64_t ld_out,
                       void* workspace, size_t workspace_bytes, int* passes_out /*host, may be NULL*/, void* stream);

@@ -21,8 +21,8 @@ Stream layout (DESIGN.md "RNG contract"):
                block j < 0x10000   -> normals 4j .. 4j+3 of the K-vector draw
                block 0x10000 + t   -> Marsaglia-Tsang attempt t of the gamma draw
                block 0x20000       -> Metropolis uniform (simplex sampler only)
-     noise   : c0 = posterior-draw index s, c1 = nucleus >> 2, c2 = 0, c3 = tag
-               -> 4 normals for nuclei 4*(n>>2) .. 4*(n>>2)+3
+     noise   : c0 = posterior-draw index s >> 2, c1 = global nucleus index, c2 = 0, c3 = tag
+               -> 4 normals for draws 4*(s>>2) .. 4*(s>>2)+3 of that nucleus
   tag      : 1 conjugate Gibbs, 2 simplex sampler, 3 predictive noise
 """
 import math
@@ -124,6 +124,6 @@ def metropolis_uniform(it, chain, tag, key):
     return u01(philox4x32_10((it, BLOCK_UNIFORM, chain, tag), key)[0])
 
 
-def noise_block(s, nblock, key):
-    """Four N(0,1) for posterior draw ``s`` and nuclei 4*nblock .. 4*nblock+3."""
-    return normals4((s, nblock, 0, TAG_NOISE), key)
+def noise_block(sblock, nucleus, key):
+    """Four N(0,1) for posterior draws 4*sblock .. 4*sblock+3 of one (global) nucleus."""
+    return normals4((sblock, nucleus, 0, TAG_NOISE), key)

@@ -37,7 +37,7 @@ class SimplexProblem(C.Structure):
 
 class PredictProblem(C.Structure):
     _fields_ = [("n_points", _i64), ("point0", _u64), ("n_draws", _i64), ("k", _int), ("u", _p), ("mu", _p),
-                ("truth", _p), ("theta_t", _p), ("noise_mode", _int), ("seed", _u64), ("noise", _p),
+                ("truth", _p), ("theta", _p), ("noise_mode", _int), ("seed", _u64), ("noise", _p),
                 ("ld_noise", _i64), ("nq", _int), ("probs", C.POINTER(_dbl)), ("theta_mean", _p),
                 ("theta_cov", _p), ("center", _p), ("scale", _p)]
 
@@ -62,6 +62,7 @@ SIGNATURES = {
     "bmc_gibbs_literal_run": (_int, [_int, _p, _p, _i64, _int, _p, _p, _dbl, _dbl, _dbl, _u64, _u64, _i64, _i64,
                                      _p, _p]),
     "bmc_predict_workspace_bytes": (_sz, [_int, _i64, _int, _i64]),
+    "bmc_predict_theta_stride": (_int, [_int]),
     "bmc_predict_fused": (_int, [_int, C.POINTER(PredictProblem), _p, _p, _p, _p, _p, _p, _i64, _p, _sz,
                                  C.POINTER(_int), _p]),
     "bmc_coverage_counts": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),

@@ -41,7 +41,7 @@ struct QuantPlan {
     int nq;
     long long rank[kMaxQuant];
     double frac[kMaxQuant], zq[kMaxQuant], hw[kMaxQuant];
-    int cand_cap;
+    double max_expected;      // largest expected number of draws inside a first window
 };
 
 // np.percentile(..., method="linear"): virtual index v = q/100 (S-1), order statistics floor(v), floor(v)+1
@@ -49,7 +49,7 @@ struct QuantPlan {
 QuantPlan make_plan(const double* probs, int nq, long long s) {
     QuantPlan pl{};
     pl.nq = nq;
-    double max_expected = 16.0;
+    pl.max_expected = 16.0;
     for (int j = 0; j < nq; ++j) {
         const double v = (probs[j] / 100.0) * static_cast<double>(s - 1);
         long long r = static_cast<long long>(std::floor(v));
@@ -68,23 +68,52 @@ QuantPlan make_plan(const double* probs, int nq, long long s) {
         const double se = std::sqrt(p * (1.0 - p) / static_cast<double>(s)) / pdf;
         pl.zq[j] = z;
         pl.hw[j] = kWindowSigmas * se + kWindowSlack;
-        max_expected = std::max(max_expected, 2.0 * pl.hw[j] * pdf * static_cast<double>(s));
+        pl.max_expected = std::max(pl.max_expected, 2.0 * pl.hw[j] * pdf * static_cast<double>(s));
     }
-    long long cap = static_cast<long long>(1.5 * max_expected) + 32;
-    cap = (cap + 31) / 32 * 32;
-    pl.cand_cap = static_cast<int>(std::min<long long>(cap, 4096));
     return pl;
+}
+
+// room one sample split needs for its share of a window's draws (mean + 6 sigma of a Poisson share)
+int segment_len(double expected_total, int splits) {
+    const double e = expected_total / splits;
+    return static_cast<int>(1.5 * e + 6.0 * std::sqrt(e) + 8.0);
+}
+
+struct PassShape {
+    int s_splits, seg_len, cand_stride, sort_cap, retry_splits, retry_seg;
+};
+
+PassShape make_shape(long long n_points, long long n_draws, double expected) {
+    PassShape sh{};
+    const int tiles = static_cast<int>((n_draws + kPredTile - 1) / kPredTile);
+    const long long blocks_x = (n_points + kPredWarps * 32 - 1) / (kPredWarps * 32);
+    const int target = 444;                          // three resident blocks per SM
+    int s = 1;
+    if (blocks_x < target) s = static_cast<int>((target + blocks_x - 1) / blocks_x);
+    s = std::max(1, std::min(s, std::min(tiles, kMaxSlots)));
+    sh.s_splits = s;
+    sh.seg_len = segment_len(expected, s);
+    sh.cand_stride = (s * sh.seg_len + 3) / 4 * 4;
+    int p2 = 64;
+    while (p2 < sh.cand_stride && p2 < 4096) p2 <<= 1;
+    sh.sort_cap = p2;
+    // retry passes touch few nuclei: as many splits as the same buffer can host
+    int rs = std::min(16, std::min(tiles, kMaxSlots));
+    while (rs > 1 && rs * segment_len(expected, rs) > sh.cand_stride) rs >>= 1;
+    sh.retry_splits = std::max(1, rs);
+    sh.retry_seg = sh.cand_stride / sh.retry_splits;
+    return sh;
 }
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct Layout {
     // byte offsets inside the workspace for a chunk of nc nuclei
-    size_t center, scale, win_lo, win_hi, brk_lo, brk_hi, pair_hi, aux, phase, cnt_below, cnt_in, sub, resolved, cand, mom, c_lt,
-        c_le, flag, list_a, list_b, counter, plan, total;
+    size_t center, scale, win_lo, win_hi, brk_lo, brk_hi, pair_hi, aux, phase, cnt_below, cnt_slot, sub, resolved,
+        cand, mom, c_lt, c_le, flag, list_a, list_b, counter, plan, total;
 };
 
-Layout make_layout(long long nc, int nq, int cap, size_t sz, int max_slots) {
+Layout make_layout(long long nc, int nq, int cand_stride, size_t sz) {
     Layout l{};
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -93,7 +122,6 @@ Layout make_layout(long long nc, int nq, int cap, size_t sz, int max_slots) {
         return at;
     };
     const size_t nqn = static_cast<size_t>(nc) * nq;
-    const size_t quads = static_cast<size_t>((nc + 3) / 4);
     l.plan = take(kMaxQuant * (sizeof(long long) + 3 * sizeof(double)));
     l.counter = take(sizeof(int));
     l.center = take(nc * sz);
@@ -106,21 +134,21 @@ Layout make_layout(long long nc, int nq, int cap, size_t sz, int max_slots) {
     l.aux = take(nqn * sz);
     l.phase = take(nqn);
     l.cnt_below = take(nqn * 4);
-    l.cnt_in = take(nqn * 4);
+    l.cnt_slot = take(nqn * 4 * kMaxSlots);
     l.sub = take(nqn * 4 * kSubBins);
     l.resolved = take(nqn);
-    l.cand = take(nqn * cap * sz);
-    l.mom = take(static_cast<size_t>(max_slots) * 2 * nc * sizeof(double));
+    l.cand = take(nqn * cand_stride * sz);
+    l.mom = take(static_cast<size_t>(kMaxSlots) * 2 * nc * sizeof(double));
     l.c_lt = take(nc * 4);
     l.c_le = take(nc * 4);
-    l.flag = take(quads * 4);
-    l.list_a = take(quads * 4);
-    l.list_b = take(quads * 4);
+    l.flag = take(nc * 4);
+    l.list_a = take(nc * 4);
+    l.list_b = take(nc * 4);
     l.total = off;
     return l;
 }
 
-constexpr int kMaxSlots = 64;
+constexpr long long kChunkPoints = 32768;     // nuclei per chunk when the workspace allows
 
 template <typename real>
 __global__ void copy_guess_kernel(const double* c, const double* s, long long n, void* center, void* scale) {
@@ -132,9 +160,8 @@ __global__ void copy_guess_kernel(const double* c, const double* s, long long n,
 
 template <typename real, int KP, int NQ>
 int launch_pass(const PredictArgs& a, cudaStream_t st) {
-    const int qpb = kPredWarps / a.warps_per_quad;
-    dim3 grid((a.n_quads + qpb - 1) / qpb, a.s_splits);
-    const size_t smem = a.theta_t ? 2 * static_cast<size_t>(a.k + 1) * kPredTile * sizeof(real) : 16;
+    dim3 grid((a.n_active + kPredWarps * 32 - 1) / (kPredWarps * 32), a.s_splits);
+    const size_t smem = a.theta ? 2 * static_cast<size_t>(KP + 4) * kPredTile * sizeof(real) : 16;
     auto kern = predict_pass_kernel<real, KP, NQ>;
     if (smem > 48 * 1024) BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kPredWarps * 32, smem, st>>>(a);
@@ -156,36 +183,25 @@ int dispatch_pass(const PredictArgs& a, cudaStream_t st) {
     return dispatch_nq<real, 16>(a, st);
 }
 
-void pick_split(int n_quads, long long n_draws, int* wpq, int* splits) {
-    const int target = 296;                         // two blocks per SM
-    const int tiles = static_cast<int>((n_draws + kPredTile - 1) / kPredTile);
-    int w = 1;
-    while (w < 8 && (n_quads + (8 / w) - 1) / (8 / w) < target) w *= 2;
-    const int blocks = (n_quads + (8 / w) - 1) / (8 / w);
-    int s = 1;
-    if (blocks < target) s = std::min(std::max(1, (target + blocks - 1) / blocks), std::max(1, tiles));
-    s = std::min(s, kMaxSlots / w);
-    *wpq = w;
-    *splits = std::max(1, s);
-}
-
 template <typename real>
 int run_predict(const bmc_predict_problem* p, double* mean, double* var, double* quant, int64_t* c_lt,
                 int64_t* c_le, double* draws_out, int64_t ld_out, void* workspace, size_t workspace_bytes,
                 int* passes_out, cudaStream_t st) {
     const size_t sz = sizeof(real);
     const QuantPlan plan = make_plan(p->probs, p->nq, p->n_draws);
-    // largest chunk of nuclei the workspace can hold
-    long long nc = (p->n_points + 3) / 4 * 4;
-    while (nc > 4 && make_layout(nc, p->nq, plan.cand_cap, sz, kMaxSlots).total > workspace_bytes) {
-        const long long half = (nc / 2 + 3) / 4 * 4;
-        nc = half < nc ? half : nc - 4;
+    // largest chunk of nuclei the workspace can hold (the shape depends on the chunk size)
+    long long nc = std::min<long long>(p->n_points, kChunkPoints);
+    PassShape shape = make_shape(nc, p->n_draws, plan.max_expected);
+    while (nc > 32 && make_layout(nc, p->nq, shape.cand_stride, sz).total > workspace_bytes) {
+        nc = std::max<long long>(32, nc / 2);
+        shape = make_shape(nc, p->n_draws, plan.max_expected);
     }
-    if (make_layout(nc, p->nq, plan.cand_cap, sz, kMaxSlots).total > workspace_bytes) {
-        set_error("bmc_predict_fused: workspace of %zu bytes cannot hold even 4 nuclei", workspace_bytes);
+    if (make_layout(nc, p->nq, shape.cand_stride, sz).total > workspace_bytes) {
+        set_error("bmc_predict_fused: workspace of %zu bytes is too small (need %zu for %lld nuclei)",
+                  workspace_bytes, make_layout(nc, p->nq, shape.cand_stride, sz).total, nc);
         return BMC_ERR_WORKSPACE;
     }
-    const Layout lay = make_layout(nc, p->nq, plan.cand_cap, sz, kMaxSlots);
+    const Layout lay = make_layout(nc, p->nq, shape.cand_stride, sz);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
 
     // quantile plan to the device
@@ -199,22 +215,21 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
     BMC_CUDA(cudaMemcpyAsync(d_hw, plan.hw, sizeof(plan.hw), cudaMemcpyHostToDevice, st));
     BMC_CUDA(cudaStreamSynchronize(st));   // the plan lives on this stack frame
 
-    int pow2cap = 1;
-    while (pow2cap < plan.cand_cap) pow2cap <<= 1;
-    const size_t select_smem = 4 * static_cast<size_t>(pow2cap) * sz;
+    const size_t select_smem = 4 * static_cast<size_t>(shape.sort_cap) * sz;
     auto select_kern = predict_select_kernel<real>;
     if (select_smem > 48 * 1024)
         BMC_CUDA(cudaFuncSetAttribute(select_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem));
+    const int kp = p->k <= 4 ? 4 : (p->k <= 8 ? 8 : 16);
+    const int tiles = static_cast<int>((p->n_draws + kPredTile - 1) / kPredTile);
 
     int max_passes = 0;
     for (long long c0 = 0; c0 < p->n_points; c0 += nc) {
         const long long n = std::min<long long>(nc, p->n_points - c0);
-        const int n_quads = static_cast<int>((n + 3) / 4);
         const size_t nqn = static_cast<size_t>(n) * p->nq;
         int* d_counter = reinterpret_cast<int*>(ws + lay.counter);
         BMC_CUDA(cudaMemsetAsync(ws + lay.c_lt, 0, n * 4, st));
         BMC_CUDA(cudaMemsetAsync(ws + lay.c_le, 0, n * 4, st));
-        BMC_CUDA(cudaMemsetAsync(ws + lay.flag, 0, static_cast<size_t>(n_quads) * 4, st));
+        BMC_CUDA(cudaMemsetAsync(ws + lay.flag, 0, static_cast<size_t>(n) * 4, st));
         BMC_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
 
         const unsigned gb = static_cast<unsigned>((n + 255) / 256);
@@ -231,9 +246,14 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         predict_window_kernel<real><<<static_cast<unsigned>((nqn + 255) / 256), 256, 0, st>>>(
             n, p->nq, ws + lay.center, ws + lay.scale, d_zq, d_hw, ws + lay.win_lo, ws + lay.win_hi, ws + lay.brk_lo,
             ws + lay.brk_hi, ws + lay.pair_hi, ws + lay.aux, ws + lay.phase,
-            reinterpret_cast<unsigned int*>(ws + lay.cnt_below), reinterpret_cast<unsigned int*>(ws + lay.cnt_in),
-            reinterpret_cast<unsigned int*>(ws + lay.sub), ws + lay.resolved);
+            reinterpret_cast<unsigned int*>(ws + lay.cnt_below), reinterpret_cast<unsigned int*>(ws + lay.sub),
+            ws + lay.resolved);
         BMC_LAUNCH_CHECK();
+
+        // the first pass of a short last chunk may use more sample splits than the full-size chunk
+        PassShape cs = make_shape(n, p->n_draws, plan.max_expected);
+        if (cs.cand_stride > shape.cand_stride || cs.sort_cap > shape.sort_cap) cs = shape;
+        if (cs.s_splits * segment_len(plan.max_expected, cs.s_splits) > shape.cand_stride) cs = shape;
 
         PredictArgs a{};
         a.u = u_chunk;
@@ -241,7 +261,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         a.truth = p->truth ? p->truth + c0 : nullptr;
         a.n_points = n;
         a.point0 = p->point0 + static_cast<unsigned long long>(c0);
-        a.theta_t = p->theta_t;
+        a.theta = p->theta;
         a.n_draws = p->n_draws;
         a.k = p->k;
         a.noise_mode = p->noise_mode;
@@ -253,10 +273,12 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         a.win_lo = ws + lay.win_lo;
         a.win_hi = ws + lay.win_hi;
         a.cnt_below = reinterpret_cast<unsigned int*>(ws + lay.cnt_below);
-        a.cnt_in = reinterpret_cast<unsigned int*>(ws + lay.cnt_in);
+        a.cnt_slot = reinterpret_cast<unsigned int*>(ws + lay.cnt_slot);
         a.sub_cnt = reinterpret_cast<unsigned int*>(ws + lay.sub);
         a.cand = ws + lay.cand;
-        a.cand_cap = plan.cand_cap;
+        a.cand_stride = shape.cand_stride;
+        a.seg_len = shape.cand_stride / cs.s_splits;
+        a.count_slices = 0;
         a.first = 1;
         a.center = ws + lay.center;
         a.mom_part = reinterpret_cast<double*>(ws + lay.mom);
@@ -264,9 +286,9 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         a.c_le = reinterpret_cast<unsigned int*>(ws + lay.c_le);
         a.draws_out = draws_out ? draws_out + c0 : nullptr;
         a.ld_out = ld_out;
-        a.quad_list = nullptr;
-        a.n_quads = n_quads;
-        pick_split(n_quads, p->n_draws, &a.warps_per_quad, &a.s_splits);
+        a.point_list = nullptr;
+        a.n_active = static_cast<int>(n);
+        a.s_splits = cs.s_splits;
 
         SelectArgs s{};
         s.n_points = n;
@@ -282,10 +304,14 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         s.aux = ws + lay.aux;
         s.phase = ws + lay.phase;
         s.cnt_below = a.cnt_below;
-        s.cnt_in = a.cnt_in;
+        s.cnt_slot = a.cnt_slot;
         s.sub_cnt = a.sub_cnt;
+        s.slices_valid = 0;
         s.cand = a.cand;
-        s.cand_cap = plan.cand_cap;
+        s.cand_stride = a.cand_stride;
+        s.seg_len = a.seg_len;
+        s.n_slots = a.s_splits;
+        s.sort_cap = shape.sort_cap;
         s.resolved = ws + lay.resolved;
         s.mu = a.mu;
         s.out_quant = quant;
@@ -293,7 +319,6 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         s.out_offset = c0;
         s.first = 1;
         s.mom_part = a.mom_part;
-        s.n_slots = a.warps_per_quad * a.s_splits;
         s.center = a.center;
         s.out_mean = mean;
         s.out_var = var;
@@ -301,9 +326,9 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         s.c_le = a.c_le;
         s.out_c_lt = p->truth ? reinterpret_cast<long long*>(c_lt) : nullptr;
         s.out_c_le = p->truth ? reinterpret_cast<long long*>(c_le) : nullptr;
-        s.quad_list = nullptr;
-        s.n_quads = n_quads;
-        s.quad_flag = reinterpret_cast<int*>(ws + lay.flag);
+        s.point_list = nullptr;
+        s.n_active = static_cast<int>(n);
+        s.point_flag = reinterpret_cast<int*>(ws + lay.flag);
         int* list_cur = reinterpret_cast<int*>(ws + lay.list_a);
         int* list_next = reinterpret_cast<int*>(ws + lay.list_b);
         s.next_list = list_next;
@@ -312,9 +337,14 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         int pass = 0;
         for (;;) {
             ++pass;
-            const int rc = dispatch_pass<real>(a, st);
+            int rc = BMC_OK;
+            switch (kp) {
+                case 4: rc = dispatch_nq<real, 4>(a, st); break;
+                case 8: rc = dispatch_nq<real, 8>(a, st); break;
+                default: rc = dispatch_nq<real, 16>(a, st); break;
+            }
             if (rc != BMC_OK) return rc;
-            const long long items = 4ll * s.n_quads * p->nq;
+            const long long items = static_cast<long long>(s.n_active) * p->nq;
             select_kern<<<static_cast<unsigned>((items + 3) / 4), 128, select_smem, st>>>(s);
             BMC_LAUNCH_CHECK();
             int pending = 0;
@@ -322,24 +352,27 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
             BMC_CUDA(cudaStreamSynchronize(st));
             if (pending == 0) break;
             if (pass >= kMaxPasses) {
-                set_error("bmc_predict_fused: %d nuclei quads unresolved after %d passes", pending, pass);
+                set_error("bmc_predict_fused: %d nuclei unresolved after %d passes", pending, pass);
                 return BMC_ERR_CONVERGE;
             }
-            // next pass: only the quads that asked for it
+            // next pass: only the nuclei that asked for it, with slice counting on
             std::swap(list_cur, list_next);
-            BMC_CUDA(cudaMemsetAsync(ws + lay.flag, 0, static_cast<size_t>(n_quads) * 4, st));
+            BMC_CUDA(cudaMemsetAsync(ws + lay.flag, 0, static_cast<size_t>(n) * 4, st));
             BMC_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
             a.first = 0;
             a.draws_out = nullptr;
-            a.quad_list = list_cur;
-            a.n_quads = pending;
-            a.warps_per_quad = 8;
-            a.s_splits = std::min<int>(std::max(1, 296 / pending),
-                                       std::max<int>(1, static_cast<int>((p->n_draws + kPredTile - 1) / kPredTile)));
+            a.point_list = list_cur;
+            a.n_active = pending;
+            a.count_slices = 1;
+            a.s_splits = std::min(shape.retry_splits, tiles);
+            a.seg_len = shape.cand_stride / a.s_splits;
             s.first = 0;
-            s.quad_list = list_cur;
-            s.n_quads = pending;
+            s.point_list = list_cur;
+            s.n_active = pending;
             s.next_list = list_next;
+            s.slices_valid = 1;
+            s.n_slots = a.s_splits;
+            s.seg_len = a.seg_len;
         }
         max_passes = std::max(max_passes, pass);
     }
@@ -357,10 +390,13 @@ size_t bmc_predict_workspace_bytes(int dtype, int64_t n_points, int nq, int64_t 
     for (int j = 0; j < nq; ++j) probs[j] = 50.0;   // the median has the widest window
     const QuantPlan plan = make_plan(probs, nq, n_draws);
     const size_t sz = dtype == BMC_F32 ? 4 : 8;
-    // cap the recommendation: chunks of 32768 nuclei keep the candidate buffers in the hundreds of MB
-    const long long nc = std::min<long long>((n_points + 3) / 4 * 4, 32768);
-    return make_layout(nc, nq, plan.cand_cap, sz, kMaxSlots).total;
+    // chunks of 32768 nuclei keep the candidate buffers in the hundreds of MB
+    const long long nc = std::min<long long>(n_points, kChunkPoints);
+    const PassShape shape = make_shape(nc, n_draws, plan.max_expected);
+    return make_layout(nc, nq, shape.cand_stride, sz).total;
 }
+
+int bmc_predict_theta_stride(int k) { return (k <= 4 ? 4 : (k <= 8 ? 8 : 16)) + 4; }
 
 int bmc_predict_fused(int dtype, const bmc_predict_problem* p, double* mean, double* var, double* quant,
                       int64_t* c_lt, int64_t* c_le, double* draws_out, int64_t ld_out, void* workspace,
@@ -370,13 +406,12 @@ int bmc_predict_fused(int dtype, const bmc_predict_problem* p, double* mean, dou
     BMC_REQUIRE(p->n_points >= 1 && p->n_draws >= 1, "bmc_predict_fused: n_points=%lld n_draws=%lld",
                 (long long)p->n_points, (long long)p->n_draws);
     BMC_REQUIRE(p->n_draws < (1ll << 31), "bmc_predict_fused: n_draws must fit 31 bits");
-    BMC_REQUIRE((p->point0 & 3) == 0, "bmc_predict_fused: point0 must be a multiple of 4");
     BMC_REQUIRE(p->nq >= 1 && p->nq <= kMaxQuant && p->probs, "bmc_predict_fused: nq=%d", p->nq);
     for (int j = 0; j < p->nq; ++j)
         BMC_REQUIRE(p->probs[j] >= 0.0 && p->probs[j] <= 100.0, "Percentiles must be in the range [0, 100]");
     BMC_REQUIRE(mean && var && quant && workspace, "bmc_predict_fused: null output");
     BMC_REQUIRE(!p->truth || (c_lt && c_le), "bmc_predict_fused: truth given without count outputs");
-    if (p->theta_t) {
+    if (p->theta) {
         BMC_REQUIRE(p->k >= 0 && p->k <= 16, "bmc_predict_fused: k=%d outside 0..16", p->k);
         BMC_REQUIRE(p->k == 0 || p->u, "bmc_predict_fused: u is NULL");
         BMC_REQUIRE((p->theta_mean && p->theta_cov) || (p->center && p->scale),

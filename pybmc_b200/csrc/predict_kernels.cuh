@@ -29,8 +29,9 @@
 namespace bmc {
 
 constexpr int kPredTile = 256;        // posterior draws per staged tile
-constexpr int kPredWarps = 8;
+constexpr int kPredWarps = 8;         // 256 nuclei per block
 constexpr int kMaxQuant = 8;
+constexpr int kMaxSlots = 64;         // sample splits (gridDim.y) a launch may use
 constexpr int kSubBins = kSelSlices;  // slices of a window counted for the overflow fallback
 
 struct PredictArgs {
@@ -39,9 +40,9 @@ struct PredictArgs {
     const double* mu;         // [n] nullable (0)
     const double* truth;      // [n] nullable
     long long n_points;       // nuclei in this chunk
-    unsigned long long point0;  // global index of nucleus 0 (multiple of 4)
-    // posterior draws
-    const void* theta_t;      // [k+1][n_draws] real; nullable => x = z (matrix mode)
+    unsigned long long point0;  // global index of nucleus 0
+    // posterior draws: rows [beta_0 .. beta_{k-1}, 0 .., sigma at column KP, 0 ..], row stride KP + 4
+    const void* theta;        // [n_draws][KP + 4] real; nullable => x = z (matrix mode)
     long long n_draws;
     int k;
     // noise
@@ -49,61 +50,56 @@ struct PredictArgs {
     uint32_t key0, key1;
     const void* noise;        // [n_draws][ld_noise] real
     long long ld_noise;
-    // windows / results, all indexed [n * nq + j]
+    // windows / results, indexed [n * nq + j]
     int nq;
     void* win_lo;             // real
     void* win_hi;             // real
-    unsigned int* cnt_below;
-    unsigned int* cnt_in;
-    unsigned int* sub_cnt;    // [n*nq][kSubBins] hits per equal-width slice of the window
-    void* cand;               // [n*nq][cand_cap] real
-    int cand_cap;
+    unsigned int* cnt_below;  // += #(x < lo)
+    unsigned int* cnt_slot;   // [n*nq][kMaxSlots] in-window draws seen by each sample split
+    unsigned int* sub_cnt;    // [n*nq][kSubBins] hits per equal-width slice (retry passes only)
+    void* cand;               // [n*nq][cand_stride] real, split s owns [s*seg_len, (s+1)*seg_len)
+    int cand_stride, seg_len;
+    int count_slices;
     // first-pass accumulators
     int first;
     const void* center;       // [n] real: shift used for the moment sums
-    double* mom_part;         // [n_slots][2][n]
+    double* mom_part;         // [s_splits][2][n]
     unsigned int* c_lt;       // [n]
     unsigned int* c_le;       // [n]
     double* draws_out;        // [n_draws][ld_out] nullable (materialise rndm_m)
     long long ld_out;
-    // active list (retry passes)
-    const int* quad_list;     // nullable
-    int n_quads;              // quads to process
-    int warps_per_quad;       // 1, 2, 4 or 8
+    // active list (retry passes): nuclei to process
+    const int* point_list;    // nullable
+    int n_active;             // nuclei to process
     int s_splits;             // gridDim.y
 };
 
 // ----------------------------------------------------------------------------------------------
-// The pass kernel.  KP: compile-time bound on k (u kept in registers); NQ: bound on nq.
+// The pass kernel: lane <-> nucleus, four posterior draws per step (one Philox call = the four
+// normals of this nucleus for draws 4i .. 4i+3), the draws' rows broadcast from a TMA-staged tile.
+// Everything a lane accumulates is private to it, so the hot loop has no atomics, votes or branches.
 template <typename real, int KP, int NQ>
 __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const PredictArgs a) {
     using M = Math<real>;
+    constexpr int LDT = KP + 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // two stages of thetaT tile: [k+1][kPredTile]
     real* const tile0 = reinterpret_cast<real*>(smem_raw);
-    const int rows = a.k + 1;
-    real* const tile1 = tile0 + rows * kPredTile;
+    real* const tile1 = tile0 + kPredTile * LDT;
     __shared__ __align__(8) uint64_t bars[2];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpq = a.warps_per_quad;
-    const int qpb = kPredWarps / wpq;                       // quads per block
-    const int slice = warp % wpq;
-    const int qslot = blockIdx.x * qpb + warp / wpq;        // index into the active list
-    const bool has_quad = qslot < a.n_quads;
-    const int quad = has_quad ? (a.quad_list ? a.quad_list[qslot] : qslot) : 0;
-    const long long n0 = 4ll * quad;
+    const int slot = blockIdx.y;
+    const int pslot = blockIdx.x * (kPredWarps * 32) + threadIdx.x;   // index into the active list
+    const bool live = pslot < a.n_active;
+    const int n = live ? (a.point_list ? a.point_list[pslot] : pslot) : 0;
 
-    // sample range of this block
+    // sample range of this block: whole tiles, so every block's range starts on a multiple of 4
     const long long per = ((a.n_draws + a.s_splits - 1) / a.s_splits + kPredTile - 1) / kPredTile * kPredTile;
-    const long long s_begin = static_cast<long long>(blockIdx.y) * per;
+    const long long s_begin = static_cast<long long>(slot) * per;
     const long long s_end = min(a.n_draws, s_begin + per);
     const int n_tiles = s_end > s_begin ? static_cast<int>((s_end - s_begin + kPredTile - 1) / kPredTile) : 0;
-    const bool use_theta = a.theta_t != nullptr;
-    const real* theta_t = static_cast<const real*>(a.theta_t);
-    // TMA needs 16-byte aligned rows: n_draws % (16/sizeof(real)) == 0, else plain loads
-    const bool tma_ok = use_theta && (a.n_draws % (16 / sizeof(real)) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(theta_t) & 15) == 0);
+    const bool use_theta = a.theta != nullptr;
+    const real* theta = static_cast<const real*>(a.theta);
+    const bool tma_ok = use_theta && (reinterpret_cast<uintptr_t>(theta) & 15) == 0;
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
@@ -113,57 +109,44 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
     __syncthreads();
 
     auto issue_tile = [&](int t) {
-        // called by thread 0 (tma) or by all threads (fallback)
         real* dst = (t & 1) ? tile1 : tile0;
         const long long s0 = s_begin + static_cast<long long>(t) * kPredTile;
         const int cnt = static_cast<int>(min(static_cast<long long>(kPredTile), s_end - s0));
         if (tma_ok) {
             if (threadIdx.x == 0) {
-                const uint32_t bytes = static_cast<uint32_t>(((cnt * sizeof(real)) + 15) & ~15u);
-                mbar_expect_tx(&bars[t & 1], bytes * rows);
-                for (int r = 0; r < rows; ++r)
-                    tma_load_1d(dst + r * kPredTile, theta_t + r * a.n_draws + s0, bytes, &bars[t & 1]);
+                const uint32_t bytes = static_cast<uint32_t>(cnt * LDT * sizeof(real));   // LDT*sizeof % 16 == 0
+                mbar_expect_tx(&bars[t & 1], bytes);
+                tma_load_1d(dst, theta + s0 * LDT, bytes, &bars[t & 1]);
             }
         } else if (use_theta) {
-            for (int i = threadIdx.x; i < rows * kPredTile; i += blockDim.x) {
-                const int r = i / kPredTile, c = i % kPredTile;
-                dst[i] = c < cnt ? theta_t[r * a.n_draws + s0 + c] : real(0);
-            }
+            for (int i = threadIdx.x; i < cnt * LDT; i += blockDim.x) dst[i] = theta[s0 * LDT + i];
         }
     };
 
-    // per-warp constants
-    real u[4][KP];
-    real tc[4], ctr[4], muv[4];
-    bool live[4];
+    // per-lane constants
+    real u[KP];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const long long n = n0 + q;
-        live[q] = has_quad && n < a.n_points;
-        const long long nn = live[q] ? n : 0;
+    for (int k = 0; k < KP; ++k)
+        u[k] = (live && k < a.k) ? static_cast<const real*>(a.u)[static_cast<long long>(n) * a.k + k] : real(0);
+    const double mu_d = (live && a.mu) ? a.mu[n] : 0.0;
+    const real tc = (live && a.truth) ? static_cast<real>(a.truth[n] - mu_d) : real(0);
+    const real ctr = (live && a.center) ? static_cast<const real*>(a.center)[n] : real(0);
+    const int idx0 = n * a.nq;
+    real wlo[NQ], whi[NQ];
+    unsigned int below[NQ], inwin[NQ];
 #pragma unroll
-        for (int k = 0; k < KP; ++k)
-            u[q][k] = (live[q] && k < a.k) ? static_cast<const real*>(a.u)[nn * a.k + k] : real(0);
-        const double m = a.mu ? a.mu[nn] : 0.0;
-        muv[q] = static_cast<real>(m);
-        tc[q] = a.truth ? static_cast<real>(a.truth[nn] - m) : real(0);
-        ctr[q] = a.center ? static_cast<const real*>(a.center)[nn] : real(0);
+    for (int j = 0; j < NQ; ++j) {
+        const bool on = live && j < a.nq;
+        wlo[j] = on ? static_cast<const real*>(a.win_lo)[idx0 + j] : real(FLT_MAX);
+        whi[j] = on ? static_cast<const real*>(a.win_hi)[idx0 + j] : real(FLT_MAX);
+        below[j] = 0u;
+        inwin[j] = 0u;
     }
-    real wlo[4][NQ], whi[4][NQ];
-    unsigned int below[4][NQ];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int j = 0; j < NQ; ++j) {
-            const bool on = live[q] && j < a.nq;
-            const long long idx = (n0 + q) * a.nq + j;
-            wlo[q][j] = on ? static_cast<const real*>(a.win_lo)[idx] : real(FLT_MAX);
-            whi[q][j] = on ? static_cast<const real*>(a.win_hi)[idx] : real(FLT_MAX);
-            below[q][j] = 0u;
-        }
-    real sx[4] = {0, 0, 0, 0}, sxx[4] = {0, 0, 0, 0};
-    unsigned int nlt[4] = {0, 0, 0, 0}, nle[4] = {0, 0, 0, 0};
-    const uint32_t qglob = static_cast<uint32_t>((a.point0 >> 2) + static_cast<unsigned long long>(quad));
+    real sx = real(0), sxx = real(0);
+    unsigned int nlt = 0u, nle = 0u;
+    const uint32_t nglob = static_cast<uint32_t>(a.point0 + static_cast<unsigned long long>(n));
+    real* const cand = static_cast<real*>(a.cand);
+    const unsigned int seg = static_cast<unsigned int>(a.seg_len);
 
     if (n_tiles > 0) issue_tile(0);
     if (!tma_ok) __syncthreads();
@@ -172,77 +155,59 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
         if (tma_ok) mbar_wait(&bars[t & 1], (t >> 1) & 1);
         const real* tile = (t & 1) ? tile1 : tile0;
         const long long s0 = s_begin + static_cast<long long>(t) * kPredTile;
-        if (has_quad) {
-            for (int sub = slice; sub < kPredTile / 32; sub += wpq) {
-                const int sl = sub * 32 + lane;
-                const long long s = s0 + sl;
-                const bool valid = s < s_end;
-                real x[4] = {0, 0, 0, 0};
-                real sigma = real(1);
-                if (use_theta) {
+        const int cnt = static_cast<int>(min(static_cast<long long>(kPredTile), s_end - s0));
+        for (int g = 0; g < cnt; g += 4) {
+            real x[4] = {real(0), real(0), real(0), real(0)};
+            real sigma[4] = {real(1), real(1), real(1), real(1)};
+            if (use_theta) {
 #pragma unroll
-                    for (int k = 0; k < KP; ++k) {
-                        if (k < a.k) {
-                            const real b = tile[k * kPredTile + sl];
+                for (int r = 0; r < 4; ++r) {
+                    const real* row = tile + (g + r) * LDT;          // warp-uniform address: broadcast
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) x[q] = M::fma(u[q][k], b, x[q]);
-                        }
-                    }
-                    sigma = tile[a.k * kPredTile + sl];
+                    for (int k = 0; k < KP; ++k) x[r] = M::fma(u[k], row[k], x[r]);
+                    sigma[r] = row[KP];
                 }
-                if (a.noise_mode == 1) {
-                    real z[4];
-                    normals4<real>(static_cast<uint32_t>(s), qglob, 0u, kTagNoise, a.key0, a.key1, z);
+            }
+            const long long s = s0 + g;
+            if (a.noise_mode == 1) {
+                real z[4];
+                normals4<real>(static_cast<uint32_t>(s >> 2), nglob, 0u, kTagNoise, a.key0, a.key1, z);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) x[q] = M::fma(sigma, z[q], x[q]);
-                } else if (a.noise_mode == 2 && valid) {
-                    const real* zr = static_cast<const real*>(a.noise) + s * a.ld_noise + n0;
+                for (int r = 0; r < 4; ++r) x[r] = M::fma(sigma[r], z[r], x[r]);
+            } else if (a.noise_mode == 2 && live) {
+                const real* zc = static_cast<const real*>(a.noise) + n;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (live[q]) x[q] = M::fma(sigma, zr[q], x[q]);
-                }
+                for (int r = 0; r < 4; ++r)
+                    if (g + r < cnt) x[r] = M::fma(sigma[r], zc[(s + r) * a.ld_noise], x[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const bool valid = live && (g + r < cnt);
                 if (a.first) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const real dv = valid ? x[q] - ctr[q] : real(0);
-                        sx[q] += dv;
-                        sxx[q] = M::fma(dv, dv, sxx[q]);
-                        nlt[q] += (valid && x[q] < tc[q]) ? 1u : 0u;
-                        nle[q] += (valid && x[q] <= tc[q]) ? 1u : 0u;
-                    }
-                    if (a.draws_out && valid) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (live[q])
-                                a.draws_out[s * a.ld_out + n0 + q] =
-                                    static_cast<double>(x[q]) + (a.mu ? a.mu[n0 + q] : 0.0);
-                    }
+                    const real dv = valid ? x[r] - ctr : real(0);
+                    sx += dv;
+                    sxx = M::fma(dv, dv, sxx);
+                    nlt += (valid && x[r] < tc) ? 1u : 0u;
+                    nle += (valid && x[r] <= tc) ? 1u : 0u;
+                    if (a.draws_out && valid)
+                        a.draws_out[(s + r) * a.ld_out + n] = static_cast<double>(x[r]) + mu_d;
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                    for (int j = 0; j < NQ; ++j) {
-                        const bool b = valid && x[q] < wlo[q][j];
-                        const bool w = valid && !b && x[q] < whi[q][j];
-                        below[q][j] += b ? 1u : 0u;
-                        const unsigned int mask = __ballot_sync(0xffffffffu, w);
-                        if (mask) {
-                            const long long idx = (n0 + q) * a.nq + j;
-                            const int leader = __ffs(mask) - 1;
-                            unsigned int base = 0u;
-                            if (lane == leader) base = atomicAdd(a.cnt_in + idx, static_cast<unsigned int>(__popc(mask)));
-                            base = __shfl_sync(0xffffffffu, base, leader);
-                            const unsigned int pos = base + __popc(mask & ((1u << lane) - 1u));
-                            if (w) {
-                                if (pos < static_cast<unsigned int>(a.cand_cap))
-                                    static_cast<real*>(a.cand)[idx * a.cand_cap + pos] = x[q];
-                                // which 1/32 slice of the window: lets an overflowing window be narrowed
-                                // with exact counts whatever the distribution (atoms, heavy tails)
-                                const real rel = (x[q] - wlo[q][j]) * (real(kSubBins) / (whi[q][j] - wlo[q][j]));
-                                int bin = static_cast<int>(rel);
-                                bin = bin < 0 ? 0 : (bin > kSubBins - 1 ? kSubBins - 1 : bin);
-                                atomicAdd(a.sub_cnt + idx * kSubBins + bin, 1u);
-                            }
+                for (int j = 0; j < NQ; ++j) {
+                    const bool b = valid && x[r] < wlo[j];
+                    const bool w = valid && !b && x[r] < whi[j];
+                    below[j] += b ? 1u : 0u;
+                    if (w) {
+                        if (inwin[j] < seg)
+                            cand[static_cast<long long>(idx0 + j) * a.cand_stride + slot * seg + inwin[j]] = x[r];
+                        ++inwin[j];
+                        if (a.count_slices) {
+                            // which 1/32 slice of the window: lets an overflowing window be narrowed with
+                            // exact counts whatever the distribution (atoms, gaps, heavy tails)
+                            const real rel = (x[r] - wlo[j]) * (real(kSubBins) / (whi[j] - wlo[j]));
+                            int bin = static_cast<int>(rel);
+                            bin = bin < 0 ? 0 : (bin > kSubBins - 1 ? kSubBins - 1 : bin);
+                            atomicAdd(a.sub_cnt + static_cast<long long>(idx0 + j) * kSubBins + bin, 1u);
                         }
                     }
                 }
@@ -251,36 +216,20 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
         __syncthreads();                                   // everyone is done with this stage
     }
 
-    if (!has_quad) return;
-    // warp reduction, then one atomic (integers) or one partial slot (moments) per nucleus
+    if (!live) return;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int j = 0; j < NQ; ++j) {
-            unsigned int v = below[q][j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && live[q] && j < a.nq && v) atomicAdd(a.cnt_below + (n0 + q) * a.nq + j, v);
+    for (int j = 0; j < NQ; ++j) {
+        if (j < a.nq) {
+            if (below[j]) atomicAdd(a.cnt_below + idx0 + j, below[j]);
+            a.cnt_slot[static_cast<long long>(idx0 + j) * kMaxSlots + slot] = inwin[j];
         }
-        if (a.first) {
-            double s1 = static_cast<double>(sx[q]), s2 = static_cast<double>(sxx[q]);
-            unsigned int c1 = nlt[q], c2 = nle[q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-                c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-            }
-            if (lane == 0 && live[q]) {
-                const long long slot = static_cast<long long>(blockIdx.y) * wpq + slice;
-                a.mom_part[(slot * 2 + 0) * a.n_points + n0 + q] = s1;
-                a.mom_part[(slot * 2 + 1) * a.n_points + n0 + q] = s2;
-                if (a.truth) {
-                    atomicAdd(a.c_lt + n0 + q, c1);
-                    atomicAdd(a.c_le + n0 + q, c2);
-                }
-            }
+    }
+    if (a.first) {
+        a.mom_part[(static_cast<long long>(slot) * 2 + 0) * a.n_points + n] = static_cast<double>(sx);
+        a.mom_part[(static_cast<long long>(slot) * 2 + 1) * a.n_points + n] = static_cast<double>(sxx);
+        if (a.truth) {
+            atomicAdd(a.c_lt + n, nlt);
+            atomicAdd(a.c_le + n, nle);
         }
     }
 }
@@ -300,10 +249,11 @@ struct SelectArgs {
     void* aux;
     unsigned char* phase;
     unsigned int* cnt_below;
-    unsigned int* cnt_in;
+    unsigned int* cnt_slot;    // [n*nq][kMaxSlots]
     unsigned int* sub_cnt;
+    int slices_valid;          // the pass that just ran counted slices
     void* cand;
-    int cand_cap;
+    int cand_stride, seg_len, n_slots, sort_cap;
     unsigned char* resolved;   // [n*nq]
     const double* mu;          // nullable
     double* out_quant;         // [nq][ld_quant]
@@ -312,7 +262,6 @@ struct SelectArgs {
     // moments (first select only)
     int first;
     const double* mom_part;
-    int n_slots;
     const void* center;
     double* out_mean;
     double* out_var;
@@ -321,31 +270,27 @@ struct SelectArgs {
     long long* out_c_lt;
     long long* out_c_le;
     // retry bookkeeping
-    const int* quad_list;      // quads examined by this launch (nullable = all)
-    int n_quads;
-    int* quad_flag;            // [n_quads_total] set when the quad needs another pass
+    const int* point_list;     // nuclei examined by this launch (nullable = all)
+    int n_active;
+    int* point_flag;           // [n_points] set when the nucleus needs another pass
     int* next_list;
     int* next_count;
 };
 
-// one warp per (nucleus, quantile): sort the window's candidates in shared memory when they fit,
-// then let sel_decide (select_logic.h) read the answer or choose the next window
+// one warp per (nucleus, quantile): gather the window's candidates from the sample splits, sort them
+// in shared memory when they fit, then let sel_decide (select_logic.h) read the answer or choose the
+// next window
 template <typename real>
 __global__ void __launch_bounds__(128) predict_select_kernel(const SelectArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int p2cap = 1;
-    while (p2cap < a.cand_cap) p2cap <<= 1;
-    real* const buf = reinterpret_cast<real*>(smem_raw) + static_cast<size_t>(warp) * p2cap;
-    const long long item = static_cast<long long>(blockIdx.x) * 4 + warp;       // (quad slot, q, j)
-    const long long per_quad = 4ll * a.nq;
-    const long long qslot = item / per_quad;
-    if (qslot >= a.n_quads) return;
-    const int quad = a.quad_list ? a.quad_list[qslot] : static_cast<int>(qslot);
-    const int q = static_cast<int>((item % per_quad) / a.nq), j = static_cast<int>(item % a.nq);
-    const long long n = 4ll * quad + q;
-    if (n >= a.n_points) return;
-    const long long idx = n * a.nq + j;
+    real* const buf = reinterpret_cast<real*>(smem_raw) + static_cast<size_t>(warp) * a.sort_cap;
+    const long long item = static_cast<long long>(blockIdx.x) * 4 + warp;       // (active slot, j)
+    const long long pslot = item / a.nq;
+    if (pslot >= a.n_active) return;
+    const int n = a.point_list ? a.point_list[pslot] : static_cast<int>(pslot);
+    const int j = static_cast<int>(item % a.nq);
+    const long long idx = static_cast<long long>(n) * a.nq + j;
 
     if (a.first && j == 0 && lane == 0) {
         double s1 = 0.0, s2 = 0.0;
@@ -375,18 +320,35 @@ __global__ void __launch_bounds__(128) predict_select_kernel(const SelectArgs a)
     st.phase = a.phase[idx];
     const long long r = a.rank[j];
     const bool need_pair = a.frac[j] > 0.0;
-    const long long cb = a.cnt_below[idx], cw = a.cnt_in[idx];
+    const long long cb = a.cnt_below[idx];
+    const unsigned int* slot_cnt = a.cnt_slot + idx * kMaxSlots;
+    long long cw = 0;
+    bool storable = true;
+    int first_slot = -1;
+    for (int s = 0; s < a.n_slots; ++s) {
+        const unsigned int c = slot_cnt[s];
+        cw += c;
+        storable = storable && c <= static_cast<unsigned int>(a.seg_len);
+        if (first_slot < 0 && c > 0) first_slot = s;
+    }
     const long long t1 = st.phase == 2 ? r + 1 : r;
     const long long t2 = t1 + ((st.phase == 0 && need_pair) ? 1 : 0);
     const bool inside = t1 >= cb && t2 < cb + cw;
-    const real* src = static_cast<const real*>(a.cand) + idx * a.cand_cap;
+    const real* src = static_cast<const real*>(a.cand) + idx * a.cand_stride;
+    const int cap_eff = storable ? a.sort_cap : 0;
 
     bool stored_equal = false;
     real stored_value = real(0);
-    if (inside && cw <= a.cand_cap) {
+    if (inside && cw <= cap_eff) {
         int p2 = 1;
         while (p2 < cw) p2 <<= 1;
-        for (int i = lane; i < p2; i += 32) buf[i] = i < cw ? src[i] : real(FLT_MAX);
+        int off = 0;
+        for (int s = 0; s < a.n_slots; ++s) {
+            const int c = static_cast<int>(slot_cnt[s]);
+            for (int i = lane; i < c; i += 32) buf[off + i] = src[s * a.seg_len + i];
+            off += c;
+        }
+        for (int i = off + lane; i < p2; i += 32) buf[i] = real(FLT_MAX);
         __syncwarp();
         for (int size = 2; size <= p2; size <<= 1)
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -402,30 +364,32 @@ __global__ void __launch_bounds__(128) predict_select_kernel(const SelectArgs a)
                 }
                 __syncwarp();
             }
-    } else if (inside) {
+    } else if (inside && first_slot >= 0) {
+        const int c = min(static_cast<int>(slot_cnt[first_slot]), a.seg_len);
         real vmin = real(FLT_MAX), vmax = -real(FLT_MAX);
-        for (int i = lane; i < a.cand_cap; i += 32) {
-            vmin = fmin(vmin, src[i]);
-            vmax = fmax(vmax, src[i]);
+        for (int i = lane; i < c; i += 32) {
+            const real v = src[first_slot * a.seg_len + i];
+            vmin = fmin(vmin, v);
+            vmax = fmax(vmax, v);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
             vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         }
-        stored_equal = vmin == vmax;
+        stored_equal = c >= 8 && vmin == vmax;
         stored_value = vmin;
     }
     if (lane != 0) return;
     unsigned int* sub = a.sub_cnt + idx * kSubBins;
     double v0 = 0.0, v1 = 0.0;
-    const SelAction act = sel_decide<real>(st, r, need_pair, cb, cw, sub, a.cand_cap, buf, stored_equal,
-                                           stored_value, &v0, &v1);
+    const SelAction act = sel_decide<real>(st, r, need_pair, cb, cw, a.slices_valid ? sub : nullptr, cap_eff, buf,
+                                           stored_equal, stored_value, &v0, &v1);
     if (act == kSelResolved) {
         a.out_quant[static_cast<long long>(j) * a.ld_quant + a.out_offset + n] =
             (a.mu ? a.mu[n] : 0.0) + sel_lerp(v0, v1, a.frac[j]);
         a.resolved[idx] = 1;
-        // park the window so later passes over this quad collect nothing for it
+        // park the window so later passes over this nucleus collect nothing for it
         static_cast<real*>(a.win_lo)[idx] = real(FLT_MAX);
         static_cast<real*>(a.win_hi)[idx] = real(FLT_MAX);
         return;
@@ -438,11 +402,10 @@ __global__ void __launch_bounds__(128) predict_select_kernel(const SelectArgs a)
     static_cast<real*>(a.aux)[idx] = st.aux;
     a.phase[idx] = static_cast<unsigned char>(st.phase);
     a.cnt_below[idx] = 0u;
-    a.cnt_in[idx] = 0u;
     for (int b = 0; b < kSubBins; ++b) sub[b] = 0u;
-    if (atomicExch(a.quad_flag + quad, 1) == 0) {
+    if (atomicExch(a.point_flag + n, 1) == 0) {
         const int pos = atomicAdd(a.next_count, 1);
-        a.next_list[pos] = quad;
+        a.next_list[pos] = n;
     }
 }
 
@@ -475,7 +438,7 @@ template <typename real>
 __global__ void predict_window_kernel(long long n, int nq, const void* center_, const void* scale_,
                                       const double* zq, const double* hw, void* win_lo, void* win_hi,
                                       void* brk_lo, void* brk_hi, void* pair_hi, void* aux, unsigned char* phase, unsigned int* cnt_below,
-                                      unsigned int* cnt_in, unsigned int* sub_cnt, unsigned char* resolved) {
+                                      unsigned int* sub_cnt, unsigned char* resolved) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n * nq) return;
     const long long p = i / nq;
@@ -495,7 +458,6 @@ __global__ void predict_window_kernel(long long n, int nq, const void* center_, 
     static_cast<real*>(aux)[i] = real(0);
     phase[i] = 0;
     cnt_below[i] = 0u;
-    cnt_in[i] = 0u;
     for (int b = 0; b < kSubBins; ++b) sub_cnt[i * kSubBins + b] = 0u;
     resolved[i] = 0;
 }

@@ -58,6 +58,7 @@ struct SelState {
 enum SelAction { kSelResolved = 0, kSelAgain = 1 };
 
 // `sorted` holds the cw in-window draws in ascending order when cw <= cap (else unused);
+// `slices` may be null when the pass did not count them (the first pass does not: overflow is rare);
 // `stored_equal` / `stored_value`: all `cap` stored draws of an overflowing window are equal.
 template <typename real>
 BMC_HD SelAction sel_decide(SelState<real>& st, long long r, bool need_pair, long long cb, long long cw,
@@ -129,6 +130,7 @@ BMC_HD SelAction sel_decide(SelState<real>& st, long long r, bool need_pair, lon
             st.hi = L::up(stored_value);
             return kSelAgain;
         }
+        if (slices == nullptr) return kSelAgain;                  // same window again, slices counted
         long long cum = cb;
         int b0 = -1, b1 = -1;
         for (int b = 0; b < kSelSlices; ++b) {

@@ -116,12 +116,12 @@ def column_percentiles(matrix, percentiles, *, truth=None, device=None):
                                       D.stream_ptr(dev)), "bmc_column_moments")
     td = D.to_device(np.asarray(truth, dtype=np.float64), dev) if truth is not None else None
     return _launch_fused(dev, "float64", n_points=n_cols, point0=0, n_draws=s_rows, k=0, u=None, mu=None, truth=td,
-                         theta_t=None, noise_mode=_lib.NOISE_EXTERNAL, seed=0, noise=md, ld_noise=md.stride(0),
+                         theta=None, noise_mode=_lib.NOISE_EXTERNAL, seed=0, noise=md, ld_noise=md.stride(0),
                          percentiles=percentiles, theta_mean=None, theta_cov=None, center=center, scale=scale,
                          return_draws=False)
 
 
-def _launch_fused(dev, dtype, *, n_points, point0, n_draws, k, u, mu, truth, theta_t, noise_mode, seed, noise,
+def _launch_fused(dev, dtype, *, n_points, point0, n_draws, k, u, mu, truth, theta, noise_mode, seed, noise,
                   ld_noise, percentiles, theta_mean, theta_cov, center, scale, return_draws, as_numpy=True,
                   workspace=None):
     lib = _lib.load()
@@ -148,7 +148,7 @@ def _launch_fused(dev, dtype, *, n_points, point0, n_draws, k, u, mu, truth, the
             nbytes, dtype=torch.uint8, device=dev)
         prob = _lib.PredictProblem(
             n_points=n_points, point0=point0, n_draws=n_draws, k=k, u=D.ptr(u), mu=D.ptr(mu), truth=D.ptr(truth),
-            theta_t=D.ptr(theta_t), noise_mode=noise_mode, seed=int(seed) & (2 ** 64 - 1), noise=D.ptr(noise),
+            theta=D.ptr(theta), noise_mode=noise_mode, seed=int(seed) & (2 ** 64 - 1), noise=D.ptr(noise),
             ld_noise=ld_noise, nq=nq, probs=batch.ctypes.data_as(C.POINTER(C.c_double)),
             theta_mean=D.ptr(theta_mean), theta_cov=D.ptr(theta_cov), center=D.ptr(center), scale=D.ptr(scale))
         n_pass = C.c_int(0)
@@ -207,7 +207,12 @@ class PredictiveProblem:
         self.theta_mean = th.mean(dim=0).contiguous()
         cen = th - self.theta_mean
         self.theta_cov = (cen.t() @ cen / max(self.n_draws, 1)).contiguous()
-        self.theta_t = th.t().contiguous().to(tdt)
+        # rows padded for 16-byte broadcast loads: beta | zeros | sigma at column stride-4 | zeros
+        stride = _lib.load().bmc_predict_theta_stride(self.k)
+        padded = torch.zeros((self.n_draws, stride), dtype=tdt, device=self.dev)
+        padded[:, : self.k] = th[:, : self.k].to(tdt)
+        padded[:, stride - 4] = th[:, self.k].to(tdt)
+        self.theta = padded
 
     def run(self, percentiles=DEFAULT_PERCENTILES, noise="philox", seed=0, return_draws=False, as_numpy=True,
             workspace=None):
@@ -222,7 +227,7 @@ class PredictiveProblem:
             mode, ld = _lib.NOISE_EXTERNAL, noise_t.stride(0)
         return _launch_fused(self.dev, self.dtype, n_points=self.n_points, point0=self.point0,
                              n_draws=self.n_draws, k=self.k, u=self.u, mu=self.mu, truth=self.truth,
-                             theta_t=self.theta_t, noise_mode=mode, seed=seed, noise=noise_t, ld_noise=ld,
+                             theta=self.theta, noise_mode=mode, seed=seed, noise=noise_t, ld_noise=ld,
                              percentiles=percentiles, theta_mean=self.theta_mean, theta_cov=self.theta_cov,
                              center=None, scale=None, return_draws=return_draws, as_numpy=as_numpy,
                              workspace=workspace)
