@@ -80,7 +80,7 @@ int segment_len(double expected_total, int splits) {
 }
 
 struct PassShape {
-    int s_splits, seg_len, cand_stride, sort_cap, retry_splits, retry_seg;
+    int s_splits, seg_len, cand_stride, retry_splits, retry_seg;
 };
 
 PassShape make_shape(long long n_points, long long n_draws, double expected) {
@@ -94,9 +94,6 @@ PassShape make_shape(long long n_points, long long n_draws, double expected) {
     sh.s_splits = s;
     sh.seg_len = segment_len(expected, s);
     sh.cand_stride = (s * sh.seg_len + 3) / 4 * 4;
-    int p2 = 64;
-    while (p2 < sh.cand_stride && p2 < 4096) p2 <<= 1;
-    sh.sort_cap = p2;
     // retry passes touch few nuclei: as many splits as the same buffer can host
     int rs = std::min(16, std::min(tiles, kMaxSlots));
     while (rs > 1 && rs * segment_len(expected, rs) > sh.cand_stride) rs >>= 1;
@@ -215,10 +212,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
     BMC_CUDA(cudaMemcpyAsync(d_hw, plan.hw, sizeof(plan.hw), cudaMemcpyHostToDevice, st));
     BMC_CUDA(cudaStreamSynchronize(st));   // the plan lives on this stack frame
 
-    const size_t select_smem = 4 * static_cast<size_t>(shape.sort_cap) * sz;
     auto select_kern = predict_select_kernel<real>;
-    if (select_smem > 48 * 1024)
-        BMC_CUDA(cudaFuncSetAttribute(select_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem));
     const int kp = p->k <= 4 ? 4 : (p->k <= 8 ? 8 : 16);
     const int tiles = static_cast<int>((p->n_draws + kPredTile - 1) / kPredTile);
 
@@ -252,7 +246,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
 
         // the first pass of a short last chunk may use more sample splits than the full-size chunk
         PassShape cs = make_shape(n, p->n_draws, plan.max_expected);
-        if (cs.cand_stride > shape.cand_stride || cs.sort_cap > shape.sort_cap) cs = shape;
+        if (cs.cand_stride > shape.cand_stride) cs = shape;
         if (cs.s_splits * segment_len(plan.max_expected, cs.s_splits) > shape.cand_stride) cs = shape;
 
         PredictArgs a{};
@@ -311,7 +305,6 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         s.cand_stride = a.cand_stride;
         s.seg_len = a.seg_len;
         s.n_slots = a.s_splits;
-        s.sort_cap = shape.sort_cap;
         s.resolved = ws + lay.resolved;
         s.mu = a.mu;
         s.out_quant = quant;
@@ -345,7 +338,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
             }
             if (rc != BMC_OK) return rc;
             const long long items = static_cast<long long>(s.n_active) * p->nq;
-            select_kern<<<static_cast<unsigned>((items + 3) / 4), 128, select_smem, st>>>(s);
+            select_kern<<<static_cast<unsigned>((items + 7) / 8), 256, 0, st>>>(s);
             BMC_LAUNCH_CHECK();
             int pending = 0;
             BMC_CUDA(cudaMemcpyAsync(&pending, d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -180,36 +180,61 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
                 for (int r = 0; r < 4; ++r)
                     if (g + r < cnt) x[r] = M::fma(sigma[r], zc[(s + r) * a.ld_noise], x[r]);
             }
+            if (g + 4 > cnt) {
+                // ragged end of the draws: park the missing ones where no window or truth can see them
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const bool valid = live && (g + r < cnt);
-                if (a.first) {
+                for (int r = 0; r < 4; ++r)
+                    if (g + r >= cnt) x[r] = real(FLT_MAX);
+            }
+            if (a.first) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const bool valid = x[r] < real(FLT_MAX);
                     const real dv = valid ? x[r] - ctr : real(0);
                     sx += dv;
                     sxx = M::fma(dv, dv, sxx);
-                    nlt += (valid && x[r] < tc) ? 1u : 0u;
-                    nle += (valid && x[r] <= tc) ? 1u : 0u;
-                    if (a.draws_out && valid)
+                    nlt += x[r] < tc ? 1u : 0u;
+                    nle += x[r] <= tc ? 1u : 0u;
+                    if (a.draws_out && valid && live)
                         a.draws_out[(s + r) * a.ld_out + n] = static_cast<double>(x[r]) + mu_d;
                 }
+            }
+            // windows: two compares and a predicated add per (draw, window); hits only set a bit
+            unsigned int hits = 0u;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
 #pragma unroll
                 for (int j = 0; j < NQ; ++j) {
-                    const bool b = valid && x[r] < wlo[j];
-                    const bool w = valid && !b && x[r] < whi[j];
+                    const bool b = x[r] < wlo[j];
                     below[j] += b ? 1u : 0u;
-                    if (w) {
-                        if (inwin[j] < seg)
-                            cand[static_cast<long long>(idx0 + j) * a.cand_stride + slot * seg + inwin[j]] = x[r];
-                        ++inwin[j];
-                        if (a.count_slices) {
-                            // which 1/32 slice of the window: lets an overflowing window be narrowed with
-                            // exact counts whatever the distribution (atoms, gaps, heavy tails)
-                            const real rel = (x[r] - wlo[j]) * (real(kSubBins) / (whi[j] - wlo[j]));
-                            int bin = static_cast<int>(rel);
-                            bin = bin < 0 ? 0 : (bin > kSubBins - 1 ? kSubBins - 1 : bin);
-                            atomicAdd(a.sub_cnt + static_cast<long long>(idx0 + j) * kSubBins + bin, 1u);
-                        }
+                    if (!b && x[r] < whi[j]) hits |= 1u << (r * NQ + j);
+                }
+            }
+            while (hits) {                                  // rare per lane: store the draw, count it
+                const int bit = __ffs(hits) - 1;
+                hits &= hits - 1u;
+                const int r = bit / NQ, j = bit - r * NQ;
+                const real xv = r == 0 ? x[0] : (r == 1 ? x[1] : (r == 2 ? x[2] : x[3]));
+                unsigned int have = 0u;
+                real lo_j = real(0), hi_j = real(1);
+#pragma unroll
+                for (int jj = 0; jj < NQ; ++jj) {
+                    if (jj == j) {
+                        have = inwin[jj];
+                        inwin[jj] = have + 1u;
+                        lo_j = wlo[jj];
+                        hi_j = whi[jj];
                     }
+                }
+                if (have < seg)
+                    cand[static_cast<long long>(idx0 + j) * a.cand_stride + slot * seg + have] = xv;
+                if (a.count_slices) {
+                    // which 1/32 slice of the window: lets an overflowing window be narrowed with exact
+                    // counts whatever the distribution (atoms, gaps, heavy tails)
+                    const real rel = (xv - lo_j) * (real(kSubBins) / (hi_j - lo_j));
+                    int bin = static_cast<int>(rel);
+                    bin = bin < 0 ? 0 : (bin > kSubBins - 1 ? kSubBins - 1 : bin);
+                    atomicAdd(a.sub_cnt + static_cast<long long>(idx0 + j) * kSubBins + bin, 1u);
                 }
             }
         }
@@ -253,7 +278,7 @@ struct SelectArgs {
     unsigned int* sub_cnt;
     int slices_valid;          // the pass that just ran counted slices
     void* cand;
-    int cand_stride, seg_len, n_slots, sort_cap;
+    int cand_stride, seg_len, n_slots;
     unsigned char* resolved;   // [n*nq]
     const double* mu;          // nullable
     double* out_quant;         // [nq][ld_quant]
@@ -277,15 +302,131 @@ struct SelectArgs {
     int* next_count;
 };
 
-// one warp per (nucleus, quantile): gather the window's candidates from the sample splits, sort them
-// in shared memory when they fit, then let sel_decide (select_logic.h) read the answer or choose the
-// next window
+// order-preserving unsigned keys of floating-point values (for the radix select)
 template <typename real>
-__global__ void __launch_bounds__(128) predict_select_kernel(const SelectArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+struct RadixKey;
+template <>
+struct RadixKey<float> {
+    using type = uint32_t;
+    static constexpr int kBytes = 4;
+    static __device__ __forceinline__ type encode(float x) {
+        const uint32_t b = __float_as_uint(x);
+        return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+    }
+    static __device__ __forceinline__ float decode(type k) {
+        return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+    }
+};
+template <>
+struct RadixKey<double> {
+    using type = unsigned long long;
+    static constexpr int kBytes = 8;
+    static __device__ __forceinline__ type encode(double x) {
+        const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
+        return b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+    }
+    static __device__ __forceinline__ double decode(type k) {
+        return __longlong_as_double(static_cast<long long>(k ^ ((k >> 63) ? 0x8000000000000000ull : 0xffffffffffffffffull)));
+    }
+};
+
+// Warp-cooperative exact selection: the draws of ranks `want` and `want + 1` (0-based, ascending)
+// among the candidates one (nucleus, quantile) collected, spread over `n_slots` segments.  MSB-first
+// radix select on order-preserving keys: one 256-bin shared-memory histogram per byte, then one more
+// sweep for the successor.  Reads the candidates straight from global memory (L1/L2 resident).
+template <typename real>
+__device__ void warp_radix_select(const real* src, const unsigned int* slot_cnt, int n_slots, int seg_len,
+                                  long long want, unsigned int* hist, real* first, real* second) {
+    using RK = RadixKey<real>;
+    using key_t = typename RK::type;
+    const int lane = threadIdx.x & 31;
+    key_t prefix = 0;
+    long long k = want;
+    unsigned int n_equal = 0;
+    for (int byte = RK::kBytes - 1; byte >= 0; --byte) {
+        const int shift = 8 * byte;
+        for (int b = lane; b < 256; b += 32) hist[b] = 0u;
+        __syncwarp();
+        for (int sl = 0; sl < n_slots; ++sl) {
+            const int c = static_cast<int>(slot_cnt[sl]);
+            const real* seg = src + static_cast<long long>(sl) * seg_len;
+            for (int i = lane; i < c; i += 32) {
+                const key_t key = RK::encode(seg[i]);
+                const bool match = byte == RK::kBytes - 1 || (key >> (shift + 8)) == (prefix >> (shift + 8));
+                if (match) atomicAdd(hist + static_cast<unsigned int>((key >> shift) & 0xff), 1u);
+            }
+        }
+        __syncwarp();
+        // lane l owns bins 8l .. 8l+7; find the bin where the running count passes k
+        unsigned int mine[8], sum = 0u;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            mine[b] = hist[8 * lane + b];
+            sum += mine[b];
+        }
+        unsigned int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned int excl = incl - sum;
+        const bool owner = static_cast<long long>(excl) <= k && k < static_cast<long long>(incl);
+        const unsigned int who = __ballot_sync(0xffffffffu, owner);
+        const int src_lane = who ? __ffs(who) - 1 : 31;
+        int bin = 0;
+        unsigned int before = excl, in_bin = 0u;
+        if (lane == src_lane) {
+            unsigned int run = excl;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (static_cast<long long>(run) <= k && k < static_cast<long long>(run + mine[b])) {
+                    bin = 8 * lane + b;
+                    before = run;
+                    in_bin = mine[b];
+                }
+                run += mine[b];
+            }
+        }
+        bin = __shfl_sync(0xffffffffu, bin, src_lane);
+        before = __shfl_sync(0xffffffffu, before, src_lane);
+        in_bin = __shfl_sync(0xffffffffu, in_bin, src_lane);
+        prefix |= static_cast<key_t>(bin) << shift;
+        k -= before;
+        n_equal = in_bin;
+        __syncwarp();
+    }
+    *first = RK::decode(prefix);
+    // successor: the same value if more copies remain, else the smallest larger key
+    if (k + 1 < static_cast<long long>(n_equal)) {
+        *second = *first;
+        return;
+    }
+    key_t best = ~static_cast<key_t>(0);
+    for (int sl = 0; sl < n_slots; ++sl) {
+        const int c = static_cast<int>(slot_cnt[sl]);
+        const real* seg = src + static_cast<long long>(sl) * seg_len;
+        for (int i = lane; i < c; i += 32) {
+            const key_t key = RK::encode(seg[i]);
+            if (key > prefix && key < best) best = key;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const key_t other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    *second = RK::decode(best);
+}
+
+// one warp per (nucleus, quantile): exact selection among the window's candidates when they were
+// all stored, then sel_decide (select_logic.h) reads the answer or chooses the next window
+template <typename real>
+__global__ void __launch_bounds__(256) predict_select_kernel(const SelectArgs a) {
+    __shared__ unsigned int hist_all[8][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    real* const buf = reinterpret_cast<real*>(smem_raw) + static_cast<size_t>(warp) * a.sort_cap;
-    const long long item = static_cast<long long>(blockIdx.x) * 4 + warp;       // (active slot, j)
+    unsigned int* const hist = hist_all[warp];
+    const long long item = static_cast<long long>(blockIdx.x) * 8 + warp;       // (active slot, j)
     const long long pslot = item / a.nq;
     if (pslot >= a.n_active) return;
     const int n = a.point_list ? a.point_list[pslot] : static_cast<int>(pslot);
@@ -335,35 +476,13 @@ __global__ void __launch_bounds__(128) predict_select_kernel(const SelectArgs a)
     const long long t2 = t1 + ((st.phase == 0 && need_pair) ? 1 : 0);
     const bool inside = t1 >= cb && t2 < cb + cw;
     const real* src = static_cast<const real*>(a.cand) + idx * a.cand_stride;
-    const int cap_eff = storable ? a.sort_cap : 0;
+    // every in-window draw was stored <=> the answer can be read; otherwise it is an overflow
+    const int cap_eff = storable ? 0x7fffffff : 0;
 
     bool stored_equal = false;
-    real stored_value = real(0);
-    if (inside && cw <= cap_eff) {
-        int p2 = 1;
-        while (p2 < cw) p2 <<= 1;
-        int off = 0;
-        for (int s = 0; s < a.n_slots; ++s) {
-            const int c = static_cast<int>(slot_cnt[s]);
-            for (int i = lane; i < c; i += 32) buf[off + i] = src[s * a.seg_len + i];
-            off += c;
-        }
-        for (int i = off + lane; i < p2; i += 32) buf[i] = real(FLT_MAX);
-        __syncwarp();
-        for (int size = 2; size <= p2; size <<= 1)
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int i = lane; i < (p2 >> 1); i += 32) {
-                    const int lo_i = 2 * i - (i & (stride - 1));
-                    const int hi_i = lo_i + stride;
-                    const bool up = (lo_i & size) == 0;
-                    const real x0 = buf[lo_i], x1 = buf[hi_i];
-                    if ((x0 > x1) == up) {
-                        buf[lo_i] = x1;
-                        buf[hi_i] = x0;
-                    }
-                }
-                __syncwarp();
-            }
+    real stored_value = real(0), v_first = real(0), v_second = real(0);
+    if (inside && storable) {
+        warp_radix_select<real>(src, slot_cnt, a.n_slots, a.seg_len, t1 - cb, hist, &v_first, &v_second);
     } else if (inside && first_slot >= 0) {
         const int c = min(static_cast<int>(slot_cnt[first_slot]), a.seg_len);
         real vmin = real(FLT_MAX), vmax = -real(FLT_MAX);
@@ -383,8 +502,8 @@ __global__ void __launch_bounds__(128) predict_select_kernel(const SelectArgs a)
     if (lane != 0) return;
     unsigned int* sub = a.sub_cnt + idx * kSubBins;
     double v0 = 0.0, v1 = 0.0;
-    const SelAction act = sel_decide<real>(st, r, need_pair, cb, cw, a.slices_valid ? sub : nullptr, cap_eff, buf,
-                                           stored_equal, stored_value, &v0, &v1);
+    const SelAction act = sel_decide<real>(st, r, need_pair, cb, cw, a.slices_valid ? sub : nullptr, cap_eff, v_first,
+                                           v_second, stored_equal, stored_value, &v0, &v1);
     if (act == kSelResolved) {
         a.out_quant[static_cast<long long>(j) * a.ld_quant + a.out_offset + n] =
             (a.mu ? a.mu[n] : 0.0) + sel_lerp(v0, v1, a.frac[j]);

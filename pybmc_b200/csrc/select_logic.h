@@ -57,12 +57,13 @@ struct SelState {
 
 enum SelAction { kSelResolved = 0, kSelAgain = 1 };
 
-// `sorted` holds the cw in-window draws in ascending order when cw <= cap (else unused);
+// `first`, `second`: the in-window draws of ranks t1 - cb and t1 - cb + 1 (ascending order) when
+// cw <= cap; `second` is only meaningful when that rank exists (t1 - cb + 1 < cw);
 // `slices` may be null when the pass did not count them (the first pass does not: overflow is rare);
 // `stored_equal` / `stored_value`: all `cap` stored draws of an overflowing window are equal.
 template <typename real>
 BMC_HD SelAction sel_decide(SelState<real>& st, long long r, bool need_pair, long long cb, long long cw,
-                            const unsigned int* slices, int cap, const real* sorted, bool stored_equal,
+                            const unsigned int* slices, int cap, real first, real second, bool stored_equal,
                             real stored_value, double* v0, double* v1) {
     using L = SelLimits<real>;
     const real big = L::big();
@@ -75,10 +76,9 @@ BMC_HD SelAction sel_decide(SelState<real>& st, long long r, bool need_pair, lon
 
     if (!first_below && !last_above) {
         if (cw <= cap) {                                            // ---- read the answer
-            const real first = sorted[t1 - cb];
             if (st.phase == 0) {
                 *v0 = static_cast<double>(first);
-                *v1 = want2 ? static_cast<double>(sorted[t1 - cb + 1]) : *v0;
+                *v1 = want2 ? static_cast<double>(second) : *v0;
                 return kSelResolved;
             }
             if (st.phase == 2) {
@@ -88,7 +88,7 @@ BMC_HD SelAction sel_decide(SelState<real>& st, long long r, bool need_pair, lon
             }
             if (t1 - cb + 1 < cw) {                                 // phase 1 and the successor is here too
                 *v0 = static_cast<double>(first);
-                *v1 = static_cast<double>(sorted[t1 - cb + 1]);
+                *v1 = static_cast<double>(second);
                 return kSelResolved;
             }
             st.aux = first;                                         // successor lies at or above hi

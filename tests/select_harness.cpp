@@ -44,7 +44,13 @@ int run_column(const std::vector<real>& x, long long r, bool need_pair, int cap,
             std::sort(stored.begin(), stored.end());
         }
         double v0 = 0, v1 = 0;
-        if (sel_decide<real>(st, r, need_pair, cb, cw, slices, cap, stored.data(), eq, eqv, &v0, &v1) == kSelResolved) {
+        const long long t1 = st.phase == 2 ? r + 1 : r;
+        real first = 0, second = 0;
+        if (cw <= cap && t1 >= cb && t1 < cb + cw) {
+            first = stored[t1 - cb];
+            if (t1 - cb + 1 < cw) second = stored[t1 - cb + 1];
+        }
+        if (sel_decide<real>(st, r, need_pair, cb, cw, slices, cap, first, second, eq, eqv, &v0, &v1) == kSelResolved) {
             *passes_out = pass;
             return (v0 == want0 && v1 == want1) ? 0 : 1;
         }
