@@ -50,7 +50,7 @@ struct StatCount {
 };
 
 template <typename real, int KP, int MODE>
-__global__ void __launch_bounds__(128) gibbs_conjugate_kernel(const GibbsArgs a) {
+__global__ void __launch_bounds__(128, 4) gibbs_conjugate_kernel(const GibbsArgs a) {
     using M = Math<real>;
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (tid >= a.n_chains) return;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_kernel(const GibbsArgs a)
         const uint32_t it32 = static_cast<uint32_t>(it);
         const real inv_s2 = M::rcp(s2);
         real e[KP];
-        real rss = rss_min;
+        real rss0 = rss_min, rss1 = real(0);
 #pragma unroll
         for (int j = 0; j < (KP + 3) / 4; ++j) {
             real z[4];
@@ -94,13 +94,13 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_kernel(const GibbsArgs a)
                 if (k < KP) {
                     const real p = M::fma(d[k], inv_s2, real(1));
                     const real sd = M::rsqrt(p);
-                    const real v = sd * sd;
-                    e[k] = M::fma(sd, z[q], pull[k] * v);
-                    rss = M::fma(d[k] * e[k], e[k], rss);
+                    e[k] = sd * M::fma(pull[k], sd, z[q]);          // pull/p + z/sqrt(p)
+                    if (k & 1) rss1 = M::fma(d[k] * e[k], e[k], rss1);
+                    else rss0 = M::fma(d[k] * e[k], e[k], rss0);
                 }
             }
         }
-        const real scale = real(0.5) * (prior_scale + rss);
+        const real scale = real(0.5) * (prior_scale + (rss0 + rss1));
         const real gm = gamma_unit_scale<real>(gc, it32, chain, kTagGibbs, a.key0, a.key1);
         s2 = M::div(scale, gm);
         s2 = s2 > real(1e-6) ? s2 : real(1e-6);

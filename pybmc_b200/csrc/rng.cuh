@@ -53,16 +53,18 @@ struct Math<float> {
     static __device__ __forceinline__ float u01(uint32_t r) {
         return fmaf(__uint2float_rn(r), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     }
-    // Box-Muller on the MUFU pipe: lg2, sqrt, sin, cos.
+    // Box-Muller on the MUFU pipe: lg2, sqrt, sin, cos (all .approx.ftz: the arguments are never denormal).
     static __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& za, float& zb) {
-        const float l2 = __log2f(u01(ra));                         // <= 0
-        float rad;
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(l2 * -1.3862943611198906f));  // -2 ln2 * log2(u)
+        float l2, rad, sn, cs;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u01(ra)));                       // <= 0
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(l2 * -1.3862943611198906f));   // sqrt(-2 ln u)
         float t = u01(rb);
         t -= rintf(t);                                             // [-1/2, 1/2]: same angle mod 2 pi
         const float ang = t * 6.283185307179586f;
-        za = rad * __cosf(ang);
-        zb = rad * __sinf(ang);
+        asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+        asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+        za = rad * cs;
+        zb = rad * sn;
     }
     static __device__ __forceinline__ float log(float x) { return __logf(x); }
     static __device__ __forceinline__ float exp(float x) { return __expf(x); }
@@ -72,7 +74,11 @@ struct Math<float> {
         return r;
     }
     static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
-    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    static __device__ __forceinline__ float rcp(float x) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
     static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
     static __device__ __forceinline__ float pow(float a, float b) { return powf(a, b); }
     static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
@@ -133,27 +139,42 @@ __host__ __device__ inline GammaConst<real> make_gamma_const(double shape) {
     return g;
 }
 
+// One Marsaglia-Tsang attempt from Philox block kBlockGamma + t; returns true when accepted.
+template <typename real>
+__device__ __forceinline__ bool gamma_attempt(const GammaConst<real>& g, uint32_t it, uint32_t t, uint32_t chain,
+                                              uint32_t tag, uint32_t k0, uint32_t k1, real& v, Philox4& r) {
+    using M = Math<real>;
+    r = philox4x32_10(it, kBlockGamma + t, chain, tag, k0, k1);
+    real x, unused;
+    M::box_muller(r.x, r.y, x, unused);
+    v = M::fma(g.c, x, real(1));
+    if (v <= real(0)) {
+        v = real(1);
+        return false;
+    }
+    v = v * v * v;
+    const real u = M::u01(r.z);
+    const real x2 = x * x;
+    if (u < real(1) - real(0.0331) * x2 * x2) return true;                 // squeeze: almost always
+    return M::log(u) < real(0.5) * x2 + g.d * (real(1) - v + M::log(v));
+}
+
+template <typename real>
+__device__ __noinline__ void gamma_retry(const GammaConst<real>& g, uint32_t it, uint32_t chain, uint32_t tag,
+                                         uint32_t k0, uint32_t k1, real& v, Philox4& r) {
+    for (uint32_t t = 1; t < static_cast<uint32_t>(kGammaMaxAttempts); ++t)
+        if (gamma_attempt<real>(g, it, t, chain, tag, k0, k1, v, r)) return;
+}
+
+// Gamma(shape, 1).  The first attempt is inlined in the caller's instruction stream (it is accepted
+// with probability > 0.99 for the sampler's shapes); rejections take the out-of-line retry loop.
 template <typename real>
 __device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
                                                  uint32_t tag, uint32_t k0, uint32_t k1) {
     using M = Math<real>;
-    real v = real(1);
-    Philox4 r{0u, 0u, 0u, 0u};
-    for (int t = 0; t < kGammaMaxAttempts; ++t) {
-        r = philox4x32_10(it, kBlockGamma + static_cast<uint32_t>(t), chain, tag, k0, k1);
-        real x, unused;
-        M::box_muller(r.x, r.y, x, unused);
-        v = M::fma(g.c, x, real(1));
-        if (v <= real(0)) {
-            v = real(1);
-            continue;
-        }
-        v = v * v * v;
-        const real u = M::u01(r.z);
-        const real x2 = x * x;
-        if (u < real(1) - real(0.0331) * x2 * x2) break;
-        if (M::log(u) < real(0.5) * x2 + g.d * (real(1) - v + M::log(v))) break;
-    }
+    real v;
+    Philox4 r;
+    if (!gamma_attempt<real>(g, it, 0u, chain, tag, k0, k1, v, r)) gamma_retry<real>(g, it, chain, tag, k0, k1, v, r);
     real out = g.d * v;
     if (g.boost) out *= M::pow(M::u01(r.w), g.inv_shape);
     return out;
