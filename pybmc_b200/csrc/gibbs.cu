@@ -31,6 +31,8 @@ int launch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream
 
 template <typename real>
 int dispatch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream_t stream) {
+    // (a two-lanes-per-chain variant was measured in round 1: 46 % more instructions for 70 % instead of
+    //  61 % issue utilisation and register-limited to 16 warps/SM -- slower; see profiles/r1_notes.md)
     if (a.k <= 4) return launch_conjugate<real, 4>(a, stats_mode, threads, stream);
     if (a.k <= 8) return launch_conjugate<real, 8>(a, stats_mode, threads, stream);
     if (a.k <= 16) return launch_conjugate<real, 16>(a, stats_mode, threads, stream);

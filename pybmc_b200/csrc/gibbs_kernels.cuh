@@ -50,7 +50,7 @@ struct StatCount {
 };
 
 template <typename real, int KP, int MODE>
-__global__ void __launch_bounds__(128, 4) gibbs_conjugate_kernel(const GibbsArgs a) {
+__global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugate_kernel(const GibbsArgs a) {
     using M = Math<real>;
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (tid >= a.n_chains) return;

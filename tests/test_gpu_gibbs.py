@@ -41,13 +41,27 @@ CASES = {
 }
 
 
+def _wide(k, n=60, seed=5):
+    """Non-orthonormal design with k components, dense prior covariance, non-zero prior mean."""
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, k)) @ (np.eye(k) + 0.3 * rng.normal(size=(k, k)))
+    y = X @ rng.normal(size=k) + 0.3 * rng.normal(size=n)
+    a = rng.normal(size=(k, k))
+    return y, X, (0.1 * rng.normal(size=k), a @ a.T / k + np.eye(k), 1.5, 0.3)
+
+
+CASES["wide_k8"] = lambda: _wide(8)          # kernels compiled for 8 components
+CASES["wide_k11"] = lambda: _wide(11)        # padded to 16
+CASES["wide_k20"] = lambda: _wide(20, n=90)  # padded to 32
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_conjugate_chain_matches_oracle_fp64(name):
     from pybmc_b200.inference_utils import ConjugateSampler, _finish_samples
     y, X, prior = CASES[name]()
     X = np.asarray(X, dtype=float)
     sampler = ConjugateSampler(y, X, prior)
-    T, C, seed = 150, 3, 0xB200
+    T, C, seed = (150, 3, 0xB200) if X.shape[1] <= 8 else (40, 2, 0xB200)
     samples, _, _ = sampler.run(T, n_chains=C, seed=seed, dtype="float64", stats="none")
     got = _finish_samples(samples, True).reshape(C, T, -1)
     for c in range(C):
@@ -90,13 +104,19 @@ def test_thinning_and_discard_select_the_same_iterates():
 def test_device_moments_match_stored_samples(dtype, tol):
     """fp64 moment sums accumulated in the kernel == moments of the samples it wrote."""
     import pybmc_b200 as pb
-    y, X, prior = CASES["toy_dense_prior"]()
-    res = pb.run_gibbs(y, X, 300, prior, n_chains=64, seed=21, dtype=dtype, stats="full")
-    s = res.samples
-    np.testing.assert_allclose(res.mean, s.mean(axis=0), rtol=tol, atol=tol)
-    np.testing.assert_allclose(res.cov, np.cov(s.T, ddof=0), rtol=10 * tol, atol=tol)
-    per_chain = s.reshape(64, 300, 3).mean(axis=1)
-    np.testing.assert_allclose(res.chain_mean, per_chain, rtol=tol, atol=tol)
+    for name, stats in (("toy_dense_prior", "full"), ("wide_k8", "full"), ("wide_k11", "full"), ("wide_k20", "diag")):
+        y, X, prior = CASES[name]()
+        width = np.asarray(X).shape[1] + 1
+        res = pb.run_gibbs(y, X, 300, prior, n_chains=64, seed=21, dtype=dtype, stats=stats)
+        s = res.samples
+        scale = np.abs(s).max()
+        np.testing.assert_allclose(res.mean, s.mean(axis=0), rtol=tol, atol=tol * scale)
+        want = np.cov(s.T, ddof=0)
+        if stats == "diag":      # only the marginal variances are accumulated (in the rotated coordinates)
+            continue
+        np.testing.assert_allclose(res.cov, want, rtol=10 * tol, atol=10 * tol * np.abs(want).max())
+        per_chain = s.reshape(64, 300, width).mean(axis=1)
+        np.testing.assert_allclose(res.chain_mean, per_chain, rtol=tol, atol=tol * scale)
 
 
 def test_literal_kernel_matches_oracle_and_sufficient_statistic_law():
@@ -183,6 +203,23 @@ def test_simplex_chain_matches_oracle_fp64(capsys):
     ref = oc.gibbs_simplex(y, X, Vt, S, 100, [1.0, 1.0], burn=10, stepsize=0.01,
                            draws=oc.PhiloxDraws(6, 0, px.TAG_SIMPLEX, lambda cov: np.sqrt(cov)))
     np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-11)
+
+
+def test_simplex_chain_matches_oracle_k8_m16():
+    import pybmc_b200 as pb
+    rng = np.random.default_rng(12)
+    preds, truth = cases.ensemble(77, 120, 16)
+    r = oc.orthogonalize_arrays(preds, truth, 8)
+    burn, T, seed = 60, 120, 31
+    res = pb.run_gibbs_simplex(r["y"], r["U_hat"], r["Vt_hat"], r["S_hat"], T, [1.0, 0.02], burn=burn,
+                               stepsize=0.01, n_chains=2, seed=seed)
+    got = res.samples.reshape(2, T, 9)
+    for c in range(2):
+        ref, acc = oc.gibbs_simplex(r["y"], r["U_hat"], r["Vt_hat"], r["S_hat"], T, [1.0, 0.02], burn=burn,
+                                    stepsize=0.01, draws=oc.PhiloxDraws(seed, c, px.TAG_SIMPLEX, lambda cov: np.sqrt(cov)),
+                                    return_acceptance=True)
+        np.testing.assert_allclose(got[c], ref, rtol=1e-8, atol=1e-11)
+        assert round(res.acceptance[c] * T) == acc
 
 
 def test_simplex_validation_errors():
