@@ -153,7 +153,7 @@ typedef struct {
     uint64_t point0;           /* global index of the first one: noise is keyed on the global index so
                                   results do not depend on the sharding                            */
     int64_t n_draws;           /* S, posterior draws (reference: 10000, sampling_utils.py:57)      */
-    int k;                     /* components (<= 16 in this version)                               */
+    int k;                     /* components, <= BMC_MAX_COMPONENTS                                 */
     const void* u;             /* dev real [n_points][k]   preds Vt_hat'                           */
     const double* mu;          /* dev [n_points] mean over models (the 1/M term of :64), or NULL   */
     const double* truth;       /* dev [n_points] or NULL (no coverage counts)                      */

@@ -158,7 +158,7 @@ __global__ void copy_guess_kernel(const double* c, const double* s, long long n,
 template <typename real, int KP, int NQ>
 int launch_pass(const PredictArgs& a, cudaStream_t st) {
     dim3 grid((a.n_active + kPredWarps * 32 - 1) / (kPredWarps * 32), a.s_splits);
-    const size_t smem = a.theta ? 2 * static_cast<size_t>(KP + 4) * kPredTile * sizeof(real) : 16;
+    const size_t smem = a.theta ? 2 * static_cast<size_t>(KP + 4) * PredTile<real, KP>::value * sizeof(real) : 16;
     auto kern = predict_pass_kernel<real, KP, NQ>;
     if (smem > 48 * 1024) BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kPredWarps * 32, smem, st>>>(a);
@@ -173,12 +173,6 @@ int dispatch_nq(const PredictArgs& a, cudaStream_t st) {
     return launch_pass<real, KP, 8>(a, st);
 }
 
-template <typename real>
-int dispatch_pass(const PredictArgs& a, cudaStream_t st) {
-    if (a.k <= 4) return dispatch_nq<real, 4>(a, st);
-    if (a.k <= 8) return dispatch_nq<real, 8>(a, st);
-    return dispatch_nq<real, 16>(a, st);
-}
 
 template <typename real>
 int run_predict(const bmc_predict_problem* p, double* mean, double* var, double* quant, int64_t* c_lt,
@@ -213,7 +207,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
     BMC_CUDA(cudaStreamSynchronize(st));   // the plan lives on this stack frame
 
     auto select_kern = predict_select_kernel<real>;
-    const int kp = p->k <= 4 ? 4 : (p->k <= 8 ? 8 : 16);
+    const int kp = bmc_padded_components(p->k > 0 ? p->k : 1);
     const int tiles = static_cast<int>((p->n_draws + kPredTile - 1) / kPredTile);
 
     int max_passes = 0;
@@ -334,7 +328,9 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
             switch (kp) {
                 case 4: rc = dispatch_nq<real, 4>(a, st); break;
                 case 8: rc = dispatch_nq<real, 8>(a, st); break;
-                default: rc = dispatch_nq<real, 16>(a, st); break;
+                case 16: rc = dispatch_nq<real, 16>(a, st); break;
+                case 32: rc = dispatch_nq<real, 32>(a, st); break;
+                default: rc = dispatch_nq<real, 64>(a, st); break;
             }
             if (rc != BMC_OK) return rc;
             const long long items = static_cast<long long>(s.n_active) * p->nq;
@@ -389,7 +385,7 @@ size_t bmc_predict_workspace_bytes(int dtype, int64_t n_points, int nq, int64_t 
     return make_layout(nc, nq, shape.cand_stride, sz).total;
 }
 
-int bmc_predict_theta_stride(int k) { return (k <= 4 ? 4 : (k <= 8 ? 8 : 16)) + 4; }
+int bmc_predict_theta_stride(int k) { return bmc_padded_components(k > 0 ? k : 1) + 4; }
 
 int bmc_predict_fused(int dtype, const bmc_predict_problem* p, double* mean, double* var, double* quant,
                       int64_t* c_lt, int64_t* c_le, double* draws_out, int64_t ld_out, void* workspace,
@@ -405,7 +401,8 @@ int bmc_predict_fused(int dtype, const bmc_predict_problem* p, double* mean, dou
     BMC_REQUIRE(mean && var && quant && workspace, "bmc_predict_fused: null output");
     BMC_REQUIRE(!p->truth || (c_lt && c_le), "bmc_predict_fused: truth given without count outputs");
     if (p->theta) {
-        BMC_REQUIRE(p->k >= 0 && p->k <= 16, "bmc_predict_fused: k=%d outside 0..16", p->k);
+        BMC_REQUIRE(p->k >= 0 && p->k <= BMC_MAX_COMPONENTS, "bmc_predict_fused: k=%d outside 0..%d", p->k,
+                    BMC_MAX_COMPONENTS);
         BMC_REQUIRE(p->k == 0 || p->u, "bmc_predict_fused: u is NULL");
         BMC_REQUIRE((p->theta_mean && p->theta_cov) || (p->center && p->scale),
                     "bmc_predict_fused: need theta moments or a centre/scale guess");

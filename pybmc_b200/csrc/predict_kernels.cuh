@@ -28,11 +28,18 @@
 
 namespace bmc {
 
-constexpr int kPredTile = 256;        // posterior draws per staged tile
+constexpr int kPredTile = 256;        // posterior draws per staged tile (fewer for wide rows, see pred_tile)
 constexpr int kPredWarps = 8;         // 256 nuclei per block
 constexpr int kMaxQuant = 8;
 constexpr int kMaxSlots = 64;         // sample splits (gridDim.y) a launch may use
 constexpr int kSubBins = kSelSlices;  // slices of a window counted for the overflow fallback
+
+// draws per shared-memory tile: two stages must stay under ~100 KB so that two blocks fit an SM
+template <typename real, int KP>
+struct PredTile {
+    static constexpr int kRowBytes = (KP + 4) * static_cast<int>(sizeof(real));
+    static constexpr int value = 2 * 256 * kRowBytes <= 100 * 1024 ? 256 : (2 * 128 * kRowBytes <= 100 * 1024 ? 128 : 64);
+};
 
 struct PredictArgs {
     // per-nucleus inputs (this launch's chunk; index 0 is global nucleus point0)
@@ -82,9 +89,10 @@ template <typename real, int KP, int NQ>
 __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const PredictArgs a) {
     using M = Math<real>;
     constexpr int LDT = KP + 4;
+    constexpr int TILE = PredTile<real, KP>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     real* const tile0 = reinterpret_cast<real*>(smem_raw);
-    real* const tile1 = tile0 + kPredTile * LDT;
+    real* const tile1 = tile0 + TILE * LDT;
     __shared__ __align__(8) uint64_t bars[2];
 
     const int slot = blockIdx.y;
@@ -93,10 +101,10 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
     const int n = live ? (a.point_list ? a.point_list[pslot] : pslot) : 0;
 
     // sample range of this block: whole tiles, so every block's range starts on a multiple of 4
-    const long long per = ((a.n_draws + a.s_splits - 1) / a.s_splits + kPredTile - 1) / kPredTile * kPredTile;
+    const long long per = ((a.n_draws + a.s_splits - 1) / a.s_splits + TILE - 1) / TILE * TILE;
     const long long s_begin = static_cast<long long>(slot) * per;
     const long long s_end = min(a.n_draws, s_begin + per);
-    const int n_tiles = s_end > s_begin ? static_cast<int>((s_end - s_begin + kPredTile - 1) / kPredTile) : 0;
+    const int n_tiles = s_end > s_begin ? static_cast<int>((s_end - s_begin + TILE - 1) / TILE) : 0;
     const bool use_theta = a.theta != nullptr;
     const real* theta = static_cast<const real*>(a.theta);
     const bool tma_ok = use_theta && (reinterpret_cast<uintptr_t>(theta) & 15) == 0;
@@ -110,8 +118,8 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
 
     auto issue_tile = [&](int t) {
         real* dst = (t & 1) ? tile1 : tile0;
-        const long long s0 = s_begin + static_cast<long long>(t) * kPredTile;
-        const int cnt = static_cast<int>(min(static_cast<long long>(kPredTile), s_end - s0));
+        const long long s0 = s_begin + static_cast<long long>(t) * TILE;
+        const int cnt = static_cast<int>(min(static_cast<long long>(TILE), s_end - s0));
         if (tma_ok) {
             if (threadIdx.x == 0) {
                 const uint32_t bytes = static_cast<uint32_t>(cnt * LDT * sizeof(real));   // LDT*sizeof % 16 == 0
@@ -154,8 +162,8 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
         if (t + 1 < n_tiles) issue_tile(t + 1);           // the other stage was released by the barrier below
         if (tma_ok) mbar_wait(&bars[t & 1], (t >> 1) & 1);
         const real* tile = (t & 1) ? tile1 : tile0;
-        const long long s0 = s_begin + static_cast<long long>(t) * kPredTile;
-        const int cnt = static_cast<int>(min(static_cast<long long>(kPredTile), s_end - s0));
+        const long long s0 = s_begin + static_cast<long long>(t) * TILE;
+        const int cnt = static_cast<int>(min(static_cast<long long>(TILE), s_end - s0));
         for (int g = 0; g < cnt; g += 4) {
             real x[4] = {real(0), real(0), real(0), real(0)};
             real sigma[4] = {real(1), real(1), real(1), real(1)};

@@ -179,8 +179,8 @@ class PredictiveProblem:
         if preds.ndim != 2 or Vt_hat.ndim != 2 or preds.shape[1] != Vt_hat.shape[1]:
             raise ValueError(f"shapes do not align: predictions {preds.shape}, Vt_hat {Vt_hat.shape}")
         self.k, self.m = Vt_hat.shape
-        if self.k > 16:
-            raise ValueError("the fused predictive kernel supports up to 16 components in this version")
+        if self.k > _lib.MAX_COMPONENTS:
+            raise ValueError(f"at most {_lib.MAX_COMPONENTS} components are supported")
         self.n_points = preds.shape[0]
         self.point0 = int(point0)
         pd_ = D.to_device(preds, self.dev)
