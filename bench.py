@@ -363,18 +363,15 @@ def load_dram_bytes():
 
 def extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ranks, barrier, flush, hbm_peak,
            only_predict=False):
-    from pybmc_b200.inference_utils import SimplexSampler
-    from pybmc_b200.sampling_utils import PredictiveProblem
-    from pybmc_b200 import _lib
-    lib = _lib.load()
     out = {}
     steps = max(1, min(args.steps, 3))
-    chain0 = rank * CHAINS_PER_GPU
-    thin = ITERATIONS // KEEP_PER_CHAIN
-
     if not only_predict:
         extras_samplers(out, timed, sampler, pb, dev, world, rank, steps)
-    return extras_predict(out, args, torch, dev, world, rank, timed, barrier, flush, hbm_peak, steps, only_predict)
+    extras_predict(out, args, torch, dev, world, rank, timed, barrier, flush, hbm_peak, steps, only_predict)
+    if not only_predict:
+        extras_config5(out, torch, dev, world, rank, timed, pb, steps, hbm_peak)
+    barrier()
+    return out
 
 
 def extras_samplers(out, timed, sampler, pb, dev, world, rank, steps):
@@ -398,6 +395,29 @@ def extras_samplers(out, timed, sampler, pb, dev, world, rank, steps):
                steps, 1)
     out["simplex_f32"] = {"value": chains * world * (burn + iters) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                           "config": "configs[1] surrogate: 377 x 15, K=3, 4096 chains/GPU x (10000 burn + 50000)"}
+
+    # the literal one-chain-per-warp kernel (parity anchor): redoes the O(nK) residual every iteration
+    import torch
+    from pybmc_b200 import _lib
+    lib = _lib.load()
+    n, k = sampler.n, sampler.k
+    xt = sampler._Xd.t().contiguous().to(torch.float32)
+    yr = sampler._yd.to(torch.float32)
+    consts = torch.from_numpy(np.concatenate([sampler.lam.reshape(-1), sampler.lam @ sampler.b0])).to(dev)
+    lit_chains, lit_iters = 8192, 200
+    buf = torch.empty((lit_iters, k + 1, lit_chains), dtype=torch.float32, device=dev)
+
+    def lit_step():
+        _lib.check(lib.bmc_gibbs_literal_run(_lib.F32, xt.data_ptr(), yr.data_ptr(), n, k, consts.data_ptr(),
+                                             consts.data_ptr() + 8 * k * k, sampler.nu0, sampler.sigma20,
+                                             sampler.sigma2_init, SEED, rank * lit_chains, lit_chains, lit_iters,
+                                             buf.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    ms = timed(lit_step, steps, 1)
+    rate = lit_chains * world * lit_iters / (ms * 1e-3)
+    out["literal_f32"] = {"value": rate, "unit": UNIT, "ms_per_step": ms,
+                          "reference_equivalent_tflops": rate * (4 * n * k + 3 * n) / 1e12,
+                          "config": "same problem, one chain per warp, X in shared memory via TMA, residual over all "
+                                    "3000 rows each iteration; 8192 chains x 200 iterations per GPU"}
 
 
 
@@ -449,6 +469,48 @@ def extras_predict(out, args, torch, dev, world, rank, timed, barrier, flush, hb
         del mat
     barrier()
     return out
+
+
+def extras_config5(out, torch, dev, world, rank, timed, pb, steps, hbm_peak):
+    """BASELINE configs[4]: 256 models x 1e5 points, K = 64 (rows sharded over ranks for the projection)."""
+    from pybmc_b200 import _lib
+    lib = _lib.load()
+    n_total, m, k = 100_000, 256, 64
+    n = n_total // world
+    gen = torch.Generator(device=dev).manual_seed(1005 + rank)
+    latent = torch.randn((n, k), generator=gen, device=dev, dtype=torch.float64) * torch.logspace(
+        0, -3, k, device=dev, dtype=torch.float64)
+    mix = torch.randn((k, m), generator=torch.Generator(device=dev).manual_seed(7), device=dev, dtype=torch.float64)
+    preds = (torch.rand((n, 1), generator=gen, device=dev, dtype=torch.float64) * 1900 + 100
+             + 30 * latent @ mix + 0.05 * torch.randn((n, m), generator=gen, device=dev, dtype=torch.float64))
+    truth = preds.mean(dim=1)
+    mu = torch.empty(n, dtype=torch.float64, device=dev)
+    y = torch.empty(n, dtype=torch.float64, device=dev)
+    xc = torch.empty((n, m), dtype=torch.float64, device=dev)
+    gram = torch.empty((m, m), dtype=torch.float64, device=dev)
+    ws = torch.empty(int(lib.bmc_gram_workspace_bytes(n, m)), dtype=torch.uint8, device=dev)
+    vt = torch.randn((k, m), generator=torch.Generator(device=dev).manual_seed(8), device=dev, dtype=torch.float64)
+    u = torch.empty((n, k), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def center():
+        _lib.check(lib.bmc_center_rows(preds.data_ptr(), n, m, m, truth.data_ptr(), mu.data_ptr(), y.data_ptr(),
+                                       xc.data_ptr(), m, st))
+
+    def gram_step():
+        _lib.check(lib.bmc_gram(xc.data_ptr(), n, m, m, None, None, gram.data_ptr(), ws.data_ptr(), ws.numel(), st))
+
+    def project():
+        _lib.check(lib.bmc_project_rows(xc.data_ptr(), n, m, m, None, vt.data_ptr(), k, u.data_ptr(), k, st))
+    res = {}
+    for name, fn, bytes_, flops in (("center_rows", center, 8 * n * m * 2, 0),
+                                    ("gram", gram_step, 8 * n * m, 2.0 * n * m * m),
+                                    ("project_rows", project, 8 * n * (m + k), 2.0 * n * m * k)):
+        ms = timed(fn, steps, 1)
+        res[name] = {"ms": ms, "GB/s": bytes_ / (ms * 1e-3) / 1e9, "frac_of_hbm": bytes_ / (ms * 1e-3) / 1e9 / hbm_peak,
+                     "fp64_TFLOP/s": flops / (ms * 1e-3) / 1e12}
+    out["config5_orthogonalize_f64"] = {"config": f"configs[4]: {n} x 256 fp64 rows per GPU, K=64", **res}
+    del preds, xc
 
 
 def cpu_baseline():

@@ -347,4 +347,221 @@ __global__ void __launch_bounds__(128) gibbs_simplex_kernel(const SimplexArgs a)
     if (a.accepted) a.accepted[tid] = n_acc;
 }
 
+// --------------------------------------------------------------------------------------
+// Simplex sampler, eight lanes per chain: the layout for few chains (BASELINE configs[1]: 4096 chains
+// are 128 warps if a thread owns a chain -- under one warp per SM -- and the loop is a chain of
+// dependent fixed-latency instructions).  The random variates of an iteration do not depend on the
+// chain's state, so each group first generates those of 32 consecutive iterations in parallel (lane g
+// draws the normals, the Metropolis uniform and the Gamma variate of iterations base + g + 8t:
+// perfectly uniform SIMT code), parks them in shared memory, and then walks the 32 state updates in
+// order with the state spread over the group: lane g owns component g (dc_g, (G dc)_g) and evaluates
+// the weights of models g, g + 8, ...; reductions are three shuffle steps inside the group.
+// Four chains per warp, everything predicated (no divergence between the four).
+constexpr int kSimplexGroup = 8;
+
+template <typename real, int KP, int MODE>
+__global__ void __launch_bounds__(128) gibbs_simplex_group_kernel(const SimplexArgs a) {
+    using M = Math<real>;
+    static_assert(KP <= kSimplexGroup, "one lane per component");
+    constexpr int G = kSimplexGroup;
+    constexpr int D = KP + 1;
+    constexpr int WPB = 4, CPW = 32 / G;                                  // warps per block, chains per warp
+    constexpr int ROW = KP + 2;                                           // z[KP], uniform, gamma
+    constexpr int RREG = 2;                                               // model passes kept in registers
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int mg = (a.m + G - 1) / G * G;
+    real* const vt_s = reinterpret_cast<real*>(smem_raw);                 // [KP][mg], zero padded
+    real* const draws_s = vt_s + KP * mg;                                 // [WPB][CPW][32][ROW]
+    for (int i = threadIdx.x; i < KP * mg; i += blockDim.x) {
+        const int k = i / mg, m = i % mg;
+        vt_s[i] = (k < a.k && m < a.m) ? static_cast<real>(a.vt[k * a.m + m]) : real(0);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane & (G - 1), grp = lane / G;
+    const long long cid_raw = (static_cast<long long>(blockIdx.x) * WPB + warp) * CPW + grp;
+    const bool chain_ok = cid_raw < a.n_chains;
+    if (!__any_sync(0xffffffffu, chain_ok)) return;                       // whole warp beyond the last chain
+    const long long cid = chain_ok ? cid_raw : a.n_chains - 1;            // idle groups shadow a real chain
+    const uint32_t chain = static_cast<uint32_t>(a.chain0 + static_cast<unsigned long long>(cid));
+    real* const mine = draws_s + (static_cast<size_t>(warp) * CPW + grp) * 32 * ROW;
+
+    // lane g: constants and state of component g
+    const bool comp = g < a.k;
+    const real step = comp ? static_cast<real>(a.step[g]) : real(0);
+    const real b_ols = comp ? static_cast<real>(a.b_ols[g]) : real(0);
+    real grow[KP];                                                        // row g of G
+#pragma unroll
+    for (int c = 0; c < KP; ++c) grow[c] = (comp && c < a.k) ? static_cast<real>(a.gram[g * a.k + c]) : real(0);
+    const real bias0 = static_cast<real>(1.0 / static_cast<double>(a.m));  // :78
+    const real prior_scale = static_cast<real>(a.prior_scale);
+    const real sig_ref = static_cast<real>(a.sigma_ref);
+    const GammaConst<real> gc = make_gamma_const<real>(a.shape);
+    // models g, g + 8 in registers; more (m > 16) are read from shared memory
+    const int n_pass = mg / G;
+    real vcol[RREG][KP];
+    bool vok[RREG];
+#pragma unroll
+    for (int r = 0; r < RREG; ++r) {
+        vok[r] = g + G * r < a.m;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) vcol[r][k] = g + G * r < mg ? vt_s[k * mg + g + G * r] : real(0);
+    }
+
+    real dc = -b_ols;                                                     // b starts at 0 (:82)
+    real gdc = real(0);
+#pragma unroll
+    for (int c = 0; c < KP; ++c) gdc = M::fma(grow[c], __shfl_sync(0xffffffffu, dc, c, G), gdc);
+    real rss = comp ? gdc * dc : real(0);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) rss += __shfl_xor_sync(0xffffffffu, rss, o, G);
+    rss += static_cast<real>(a.rss_min);
+    real s2 = static_cast<real>(a.sigma2_init);                           // :86
+
+    // moment sums of lane g: dc_g, dc_g * dc_c (c = 0..KP-1), dc_g * es, and (used from lane 0) es, es^2
+    real acc1 = real(0), accs = real(0), acce = real(0), accee = real(0);
+    real acc2[KP];
+#pragma unroll
+    for (int c = 0; c < KP; ++c) acc2[c] = real(0);
+    int n_acc = 0;
+    real* const out = static_cast<real*>(a.samples);
+
+    // one state update (:98-117 / :121-140)
+    auto update = [&](const real* row, bool count_accept) {
+        const real z = g < KP ? row[g] : real(0);
+        const real u = row[KP];
+        const real gm = row[KP + 1];
+        const real delta = step * z;                                      // :98 / :121
+        const real prop = (b_ols + dc) + delta;
+        real pk[KP], dk[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            pk[k] = __shfl_sync(0xffffffffu, prop, k, G);
+            dk[k] = __shfl_sync(0xffffffffu, delta, k, G);
+        }
+        // weights of the proposal (:99); only the minimum matters (:102)
+        real wmin = real(1);
+#pragma unroll
+        for (int r = 0; r < RREG; ++r) {
+            real w = bias0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) w = M::fma(pk[k], vcol[r][k], w);
+            wmin = vok[r] ? fmin(wmin, w) : wmin;
+        }
+        for (int r = RREG; r < n_pass; ++r) {
+            real w = bias0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) w = M::fma(pk[k], vt_s[k * mg + g + G * r], w);
+            if (g + G * r < a.m) wmin = fmin(wmin, w);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o, G));
+        real gdelta = real(0);
+#pragma unroll
+        for (int c = 0; c < KP; ++c) gdelta = M::fma(grow[c], dk[c], gdelta);
+        real diff = delta * M::fma(real(2), gdc, gdelta);                 // RSS' - RSS = delta'G(2 dc + delta)
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o, G);
+        const real alpha = M::exp(M::div(-diff, s2));                     // no factor 1/2 (:108 / :130)
+        const bool accept = !(wmin < real(0)) && u < fmin(real(1), alpha);   // :102, :110
+        dc = accept ? dc + delta : dc;
+        gdc = accept ? gdc + gdelta : gdc;
+        rss = accept ? rss + diff : rss;
+        n_acc += (accept && count_accept) ? 1 : 0;
+        s2 = M::div(real(0.5) * (prior_scale + rss), gm);                 // :116-117, no floor
+    };
+
+    const int burn = static_cast<int>(a.burn), total = static_cast<int>(a.burn + a.iterations);
+    int next_store = a.samples ? burn : -1;
+    int slot = 0;
+    for (int base = 0; base < total; base += 32) {
+        // ---- phase 1: the variates of iterations base .. base+31 of this group's chain
+#pragma unroll 1
+        for (int t = 0; t < 32 / G; ++t) {
+            const int j = g + G * t;
+            const uint32_t it32 = static_cast<uint32_t>(base + j);
+            real* row = mine + j * ROW;
+#pragma unroll
+            for (int b = 0; b < (KP + 3) / 4; ++b) {
+                real z[4];
+                normals4<real>(it32, static_cast<uint32_t>(b), chain, kTagSimplex, a.key0, a.key1, z);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (4 * b + q < KP) row[4 * b + q] = z[q];
+            }
+            row[KP] = M::u01(philox4x32_10(it32, kBlockUniform, chain, kTagSimplex, a.key0, a.key1).x);
+            row[KP + 1] = gamma_unit_scale<real>(gc, it32, chain, kTagSimplex, a.key0, a.key1);
+        }
+        __syncwarp();
+        // ---- phase 2: the state updates, in order
+        const int n_here = min(32, total - base);
+        if (base + n_here <= burn) {
+            for (int j = 0; j < n_here; ++j) update(mine + j * ROW, false);   // burn-in: nothing recorded
+        } else {
+            for (int j = 0; j < n_here; ++j) {
+                const int it = base + j;
+                update(mine + j * ROW, it >= burn);
+                if (it < burn) continue;
+                const real sig = M::sqrt(s2);
+                if (MODE != 0) {
+                    const real es = sig - sig_ref;
+                    acc1 += dc;
+                    accs = M::fma(dc, es, accs);
+                    acce += es;
+                    accee = M::fma(es, es, accee);
+                    if (MODE == 1) {
+                        acc2[0] = M::fma(dc, dc, acc2[0]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < KP; ++c)
+                            acc2[c] = M::fma(dc, __shfl_sync(0xffffffffu, dc, c, G), acc2[c]);
+                    }
+                    const int done = it - burn + 1;
+                    if ((done % kFlushEvery) == 0 || it + 1 == total) {
+                        auto row2 = [&](int r, int c) { return D + r * D - r * (r - 1) / 2 + (c - r); };
+                        auto flush = [&](int row_out, real& v) {
+                            if (chain_ok) {
+                                double* p = a.chain_stats + static_cast<long long>(row_out) * a.n_chains + cid;
+                                *p += static_cast<double>(v);
+                            }
+                            v = real(0);
+                        };
+                        if (g < KP) {
+                            flush(g, acc1);
+                            if (MODE == 1) {
+                                flush(D + g, acc2[0]);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < KP; ++c) {
+                                    if (c >= g) flush(row2(g, c), acc2[c]);
+                                    else acc2[c] = real(0);
+                                }
+                                flush(row2(g, KP), accs);
+                            }
+                        }
+                        if (g == 0) {
+                            flush(KP, acce);
+                            flush(MODE == 1 ? D + KP : row2(KP, KP), accee);
+                        }
+                        acc1 = accs = acce = accee = real(0);
+#pragma unroll
+                        for (int c = 0; c < KP; ++c) acc2[c] = real(0);
+                    }
+                }
+                if (it == next_store) {
+                    if (chain_ok) {
+                        real* dst = out + static_cast<long long>(slot) * (a.k + 1) * a.n_chains + cid;
+                        if (g < a.k) dst[static_cast<long long>(g) * a.n_chains] = b_ols + dc;
+                        if (g == 0) dst[static_cast<long long>(a.k) * a.n_chains] = sig;
+                    }
+                    ++slot;
+                    next_store += static_cast<int>(a.thin);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (a.accepted && g == 0 && chain_ok) a.accepted[cid] = n_acc;
+}
+
 }  // namespace bmc

@@ -43,8 +43,39 @@ int launch_simplex(const SimplexArgs& a, int stats_mode, int threads, cudaStream
     return BMC_OK;
 }
 
+template <typename real, int KP>
+int launch_simplex_group(const SimplexArgs& a, int stats_mode, cudaStream_t stream) {
+    const int wpb = 4, cpw = 32 / kSimplexGroup;
+    const unsigned blocks = static_cast<unsigned>((a.n_chains + wpb * cpw - 1) / (wpb * cpw));
+    const int mg = (a.m + kSimplexGroup - 1) / kSimplexGroup * kSimplexGroup;
+    const size_t smem = sizeof(real) * (static_cast<size_t>(KP) * mg + static_cast<size_t>(wpb) * cpw * 32 * (KP + 2));
+    if (smem > 200 * 1024) return 1;                       // caller falls back to one chain per thread
+#define BMC_SIMPLEX_GROUP(MODE)                                                                               \
+    do {                                                                                                      \
+        auto kern = gibbs_simplex_group_kernel<real, KP, MODE>;                                               \
+        if (smem > 48 * 1024)                                                                                 \
+            BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        kern<<<blocks, wpb * 32, smem, stream>>>(a);                                                          \
+    } while (0)
+    if (stats_mode == BMC_STATS_NONE) BMC_SIMPLEX_GROUP(0);
+    else if (stats_mode == BMC_STATS_DIAG) BMC_SIMPLEX_GROUP(1);
+    else BMC_SIMPLEX_GROUP(2);
+#undef BMC_SIMPLEX_GROUP
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+// below this many chains a thread-per-chain launch cannot fill the machine (148 SMs x 4 schedulers x
+// a few warps each): give every chain eight lanes instead
+constexpr long long kGroupPerChainBelow = 131072;
+
 template <typename real>
 int dispatch_simplex(const SimplexArgs& a, int stats_mode, int threads, cudaStream_t stream) {
+    if (a.n_chains < kGroupPerChainBelow && a.k <= 8) {
+        const int rc = a.k <= 4 ? launch_simplex_group<real, 4>(a, stats_mode, stream)
+                                : launch_simplex_group<real, 8>(a, stats_mode, stream);
+        if (rc <= 0) return rc;
+    }
     if (a.k <= 4) return launch_simplex<real, 4>(a, stats_mode, threads, stream);
     if (a.k <= 8) return launch_simplex<real, 8>(a, stats_mode, threads, stream);
     if (a.k <= 16) return launch_simplex<real, 16>(a, stats_mode, threads, stream);

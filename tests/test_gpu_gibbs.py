@@ -222,6 +222,36 @@ def test_simplex_chain_matches_oracle_k8_m16():
         assert round(res.acceptance[c] * T) == acc
 
 
+def test_simplex_layouts_agree_with_oracle_and_each_other():
+    """Few chains run eight lanes per chain, many chains one chain per thread: same stream, same law.
+    Chain ids are global, so chain 5 of a 131072-chain launch is the oracle's chain 5."""
+    import pybmc_b200 as pb
+    y, X, Vt, S = _simplex_case()
+    burn, T, seed = 40, 60, 77
+    many = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02, n_chains=131072, seed=seed,
+                                stats="full")
+    few = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02, n_chains=8, seed=seed,
+                               stats="full")
+    got_many = many.samples.reshape(131072, T, 4)
+    got_few = few.samples.reshape(8, T, 4)
+    np.testing.assert_allclose(got_many[:8], got_few, rtol=1e-9, atol=1e-12)
+    for c in (0, 5):
+        ref, acc = oc.gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02,
+                                    draws=oc.PhiloxDraws(seed, c, px.TAG_SIMPLEX, lambda cov: np.sqrt(cov)),
+                                    return_acceptance=True)
+        np.testing.assert_allclose(got_many[c], ref, rtol=1e-8, atol=1e-11)
+        assert round(many.acceptance[c] * T) == acc == round(few.acceptance[c] * T)
+    # device moment sums of both layouts against the samples they wrote
+    for res in (few, many):
+        smp = res.samples
+        np.testing.assert_allclose(res.mean, smp.mean(axis=0), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(res.cov, np.cov(smp.T, ddof=0), rtol=1e-7, atol=1e-12)
+    diag = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02, n_chains=8, seed=seed,
+                                stats="diag")
+    np.testing.assert_allclose(np.diag(diag.cov), np.diag(few.cov), rtol=1e-10)
+    np.testing.assert_allclose(diag.mean, few.mean, rtol=1e-12)
+
+
 def test_simplex_validation_errors():
     import pybmc_b200 as pb
     y, X, Vt, S = cases.toy_simplex()
