@@ -29,10 +29,34 @@ int launch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream
     return BMC_OK;
 }
 
+template <typename real, int KP>
+int launch_group(const GibbsArgs& a, int stats_mode, cudaStream_t stream) {
+    const int wpb = 4, cpw = 32 / kConjGroup;
+    const unsigned blocks = static_cast<unsigned>((a.n_chains + wpb * cpw - 1) / (wpb * cpw));
+    switch (stats_mode) {
+        case BMC_STATS_NONE:
+            gibbs_conjugate_group_kernel<real, KP, 0><<<blocks, wpb * 32, 0, stream>>>(a);
+            break;
+        case BMC_STATS_DIAG:
+            gibbs_conjugate_group_kernel<real, KP, 1><<<blocks, wpb * 32, 0, stream>>>(a);
+            break;
+        default:
+            gibbs_conjugate_group_kernel<real, KP, 2><<<blocks, wpb * 32, 0, stream>>>(a);
+    }
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+// with fewer chains than this a thread-per-chain launch leaves schedulers idle; eight lanes per chain
+// cost ~50 % more instructions per chain-iteration but bring eight times the warps
+constexpr long long kConjGroupBelow = 16384;
+
 template <typename real>
 int dispatch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream_t stream) {
     // (a two-lanes-per-chain variant was measured in round 1: 46 % more instructions for 70 % instead of
     //  61 % issue utilisation and register-limited to 16 warps/SM -- slower; see profiles/r1_notes.md)
+    if (a.n_chains < kConjGroupBelow && a.k <= 8)
+        return a.k <= 4 ? launch_group<real, 4>(a, stats_mode, stream) : launch_group<real, 8>(a, stats_mode, stream);
     if (a.k <= 4) return launch_conjugate<real, 4>(a, stats_mode, threads, stream);
     if (a.k <= 8) return launch_conjugate<real, 8>(a, stats_mode, threads, stream);
     if (a.k <= 16) return launch_conjugate<real, 16>(a, stats_mode, threads, stream);

@@ -166,6 +166,156 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
 }
 
 // --------------------------------------------------------------------------------------
+// Conjugate sampler, eight lanes per chain: the layout for few chains (the reference's own use is ONE
+// chain of 50,000 iterations, which a single thread would walk through alone).  As in the simplex
+// group kernel below, the state-independent variates of 32 consecutive iterations are generated in
+// parallel by the group (lane g: iterations base + g + 8t) and parked in shared memory; the 32 state
+// updates then run in order with lane g owning component g and RSS summed by three shuffles.
+constexpr int kConjGroup = 8;
+
+template <typename real, int KP, int MODE>
+__global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsArgs a) {
+    using M = Math<real>;
+    static_assert(KP <= kConjGroup, "one lane per component");
+    constexpr int G = kConjGroup;
+    constexpr int D = KP + 1;
+    constexpr int WPB = 4, CPW = 32 / G;
+    constexpr int ROW = KP + 1;                                           // z[KP], gamma
+    __shared__ real draws_s[WPB * CPW * 32 * ROW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane & (G - 1), grp = lane / G;
+    const long long cid_raw = (static_cast<long long>(blockIdx.x) * WPB + warp) * CPW + grp;
+    const bool chain_ok = cid_raw < a.n_chains;
+    if (!__any_sync(0xffffffffu, chain_ok)) return;
+    const long long cid = chain_ok ? cid_raw : a.n_chains - 1;            // idle groups shadow a real chain
+    const uint32_t chain = static_cast<uint32_t>(a.chain0 + static_cast<unsigned long long>(cid));
+    real* const mine = draws_s + (static_cast<size_t>(warp) * CPW + grp) * 32 * ROW;
+
+    const bool comp = g < a.k;
+    const real d = comp ? static_cast<real>(a.d[g]) : real(0);
+    const real pull = comp ? static_cast<real>(a.pull[g]) : real(0);
+    const real g_ols = comp ? static_cast<real>(a.g_ols[g]) : real(0);
+    const real rss_min = static_cast<real>(a.rss_min);
+    const real prior_scale = static_cast<real>(a.prior_scale);
+    const real sig_ref = static_cast<real>(a.sigma_ref);
+    const GammaConst<real> gc = make_gamma_const<real>(a.shape);
+
+    real acc1 = real(0), accs = real(0), acce = real(0), accee = real(0);
+    real acc2[KP];
+#pragma unroll
+    for (int c = 0; c < KP; ++c) acc2[c] = real(0);
+    real s2 = static_cast<real>(a.sigma2_init);
+    real* const out = static_cast<real*>(a.samples);
+    const int total = static_cast<int>(a.iterations);
+    int next_store = a.samples ? static_cast<int>(a.store_from) : -1;
+    int slot = 0;
+
+    for (int base = 0; base < total; base += 32) {
+        // ---- phase 1: the variates of iterations base .. base+31 of this group's chain
+#pragma unroll 1
+        for (int t = 0; t < 32 / G; ++t) {
+            const int j = g + G * t;
+            const uint32_t it32 = static_cast<uint32_t>(base + j);
+            real* row = mine + j * ROW;
+#pragma unroll
+            for (int b = 0; b < (KP + 3) / 4; ++b) {
+                real z[4];
+                normals4<real>(it32, static_cast<uint32_t>(b), chain, kTagGibbs, a.key0, a.key1, z);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (4 * b + q < KP) row[4 * b + q] = z[q];
+            }
+            row[KP] = gamma_unit_scale<real>(gc, it32, chain, kTagGibbs, a.key0, a.key1);
+        }
+        __syncwarp();
+        // ---- phase 2: the state updates, in order (:41-52)
+        const int n_here = min(32, total - base);
+        for (int j = 0; j < n_here; ++j) {
+            const int it = base + j;
+            const real* row = mine + j * ROW;
+            const real z = g < KP ? row[g] : real(0);
+            const real gm = row[KP];
+            const real inv_s2 = M::rcp(s2);
+            const real p = M::fma(d, inv_s2, real(1));
+            const real sd = M::rsqrt(p);
+            const real e = sd * M::fma(pull, sd, z);                      // pull/p + z/sqrt(p)
+            real rss = (d * e) * e;
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) rss += __shfl_xor_sync(0xffffffffu, rss, o, G);
+            s2 = M::div(real(0.5) * (prior_scale + (rss_min + rss)), gm);
+            s2 = s2 > real(1e-6) ? s2 : real(1e-6);
+            const real sig = M::sqrt(s2);
+            if (MODE != 0) {
+                const real es = sig - sig_ref;
+                acc1 += e;
+                accs = M::fma(e, es, accs);
+                acce += es;
+                accee = M::fma(es, es, accee);
+                if (MODE == 1) {
+                    acc2[0] = M::fma(e, e, acc2[0]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < KP; ++c) acc2[c] = M::fma(e, __shfl_sync(0xffffffffu, e, c, G), acc2[c]);
+                }
+                if (((it + 1) % kFlushEvery) == 0 || it + 1 == total) {
+                    auto row2 = [&](int r, int c) { return D + r * D - r * (r - 1) / 2 + (c - r); };
+                    auto flush = [&](int row_out, real& v) {
+                        if (chain_ok) {
+                            double* q = a.chain_stats + static_cast<long long>(row_out) * a.n_chains + cid;
+                            *q += static_cast<double>(v);
+                        }
+                        v = real(0);
+                    };
+                    if (g < KP) {
+                        flush(g, acc1);
+                        if (MODE == 1) {
+                            flush(D + g, acc2[0]);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < KP; ++c) {
+                                if (c >= g) flush(row2(g, c), acc2[c]);
+                                else acc2[c] = real(0);
+                            }
+                            flush(row2(g, KP), accs);
+                        }
+                    }
+                    if (g == 0) {
+                        flush(KP, acce);
+                        flush(MODE == 1 ? D + KP : row2(KP, KP), accee);
+                    }
+                    acc1 = accs = acce = accee = real(0);
+#pragma unroll
+                    for (int c = 0; c < KP; ++c) acc2[c] = real(0);
+                }
+            }
+            if (it == next_store) {
+                // b = W (g_ols + e): lane r gathers the group's coordinates for its row of W
+                const real gam = g_ols + e;
+                real b;
+                if (a.dense_w) {
+                    b = real(0);
+#pragma unroll
+                    for (int c = 0; c < KP; ++c) {
+                        const real gc_ = __shfl_sync(0xffffffffu, gam, c, G);
+                        if (comp && c < a.k) b = M::fma(static_cast<real>(a.w[g * a.k + c]), gc_, b);
+                    }
+                } else {
+                    b = comp ? static_cast<real>(a.w[g]) * gam : real(0);
+                }
+                if (chain_ok) {
+                    real* dst = out + static_cast<long long>(slot) * (a.k + 1) * a.n_chains + cid;
+                    if (comp) dst[static_cast<long long>(g) * a.n_chains] = b;
+                    if (g == 0) dst[static_cast<long long>(a.k) * a.n_chains] = sig;
+                }
+                ++slot;
+                next_store += static_cast<int>(a.thin);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------------------------------
 struct SimplexArgs {
     const double* gram;     // [k*k]
     const double* b_ols;    // [k]   any least-squares solution
