@@ -192,7 +192,20 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
                   workspace_bytes, make_layout(nc, p->nq, shape.cand_stride, sz).total, nc);
         return BMC_ERR_WORKSPACE;
     }
+    // equal chunks (a short last chunk would run at a fraction of the machine)
+    {
+        const long long n_chunks = (p->n_points + nc - 1) / nc;
+        const long long even = ((p->n_points + n_chunks - 1) / n_chunks + 255) / 256 * 256;
+        if (even < nc) {
+            nc = even;
+            shape = make_shape(nc, p->n_draws, plan.max_expected);
+        }
+    }
     const Layout lay = make_layout(nc, p->nq, shape.cand_stride, sz);
+    if (lay.total > workspace_bytes) {
+        set_error("bmc_predict_fused: workspace of %zu bytes is too small (need %zu)", workspace_bytes, lay.total);
+        return BMC_ERR_WORKSPACE;
+    }
     unsigned char* ws = static_cast<unsigned char*>(workspace);
 
     // quantile plan to the device
