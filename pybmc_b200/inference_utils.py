@@ -221,16 +221,19 @@ class ConjugateSampler:
         mean = base + jac @ mean_e
         cov = jac @ cov_e @ jac.T
         comp = list(range(k)) + [kp]
-        per_chain = D.to_host(cstats[comp, :]).T / float(iterations)
-        chain_mean = base[None, :] + per_chain @ jac.T
+        jac_d = torch.from_numpy(jac).to(cstats.device)
+        base_d = torch.from_numpy(base).to(cstats.device)
+        chain_mean = D.to_host(base_d[None, :] + (cstats[comp, :].t() / float(iterations)) @ jac_d.t())
         return mean, cov, chain_mean
 
 
 def _finish_samples(samples, as_numpy):
+    """[kept, K+1, chains] on the device -> the reference's row layout [chains*kept, K+1] (chain-major).
+    The array keeps the arithmetic type of the run: float64 by default, float32 when asked for."""
     if samples is None:
         return None
     n_kept, width, n_chains = samples.shape
-    rows = samples.permute(2, 0, 1).reshape(n_chains * n_kept, width).to(torch.float64)
+    rows = samples.permute(2, 0, 1).reshape(n_chains * n_kept, width)
     return D.to_host(rows) if as_numpy else rows
 
 
@@ -261,8 +264,9 @@ def gibbs_sampler(y, X, iterations, prior_info, *, n_chains=1, seed=None, dtype=
             fp64 chain from a fresh seed, like upstream.
 
     Returns:
-        ``[n_chains * kept, K+1]`` float64 array of ``[beta, sigma]`` rows (``[iterations, K+1]``
-        by default), no burn-in, first iterate kept -- as upstream.
+        ``[n_chains * kept, K+1]`` array of ``[beta, sigma]`` rows (``[iterations, K+1]`` float64 by
+        default; float32 if ``dtype="float32"`` was asked for), no burn-in, first iterate kept -- as
+        upstream.
     """
     return run_gibbs(y, X, iterations, prior_info, n_chains=n_chains, seed=seed, dtype=dtype, thin=thin,
                      discard=discard, stats="none", device=device).samples
