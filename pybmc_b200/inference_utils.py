@@ -47,6 +47,7 @@ class GibbsResult:
     dtype: str
     acceptance: np.ndarray = None
     info: dict = field(default_factory=dict)
+    rhat: np.ndarray = None   # [K+1] Gelman-Rubin potential scale reduction (needs >= 2 chains, full stats)
 
 
 def USVt_hat_extraction(U, S, Vt, components_kept):
@@ -223,8 +224,31 @@ class ConjugateSampler:
         comp = list(range(k)) + [kp]
         jac_d = torch.from_numpy(jac).to(cstats.device)
         base_d = torch.from_numpy(base).to(cstats.device)
-        chain_mean = D.to_host(base_d[None, :] + (cstats[comp, :].t() / float(iterations)) @ jac_d.t())
-        return mean, cov, chain_mean
+        chain_mean_d = base_d[None, :] + (cstats[comp, :].t() / float(iterations)) @ jac_d.t()
+        self.last_rhat = _rhat(cstats, comp, _stat_layout(k, kp, mode)[2], jac_d, chain_mean_d, iterations)
+        return mean, cov, D.to_host(chain_mean_d)
+
+
+def _rhat(cstats, comp, second, jac_d, chain_mean_d, iterations):
+    """Gelman-Rubin R-hat per coordinate of [b, sigma] from the per-chain moment sums (device, fp64):
+    sqrt(((n-1)/n W + B/n) / W) with W the mean within-chain variance and B/n the variance of the
+    chain means.  None when there is a single chain or only diagonal moments of rotated coordinates."""
+    n_chains = cstats.shape[1]
+    if n_chains < 2 or iterations < 2:
+        return None
+    d = len(comp)
+    idx = [[second.get((min(a, b), max(a, b))) for b in comp] for a in comp]
+    if any(i is None for row in idx for i in row):
+        return None
+    flat = torch.tensor([i for row in idx for i in row], device=cstats.device)
+    m2 = cstats[flat, :].t().reshape(n_chains, d, d) / float(iterations)          # E[e e'] per chain
+    m1 = cstats[comp, :].t() / float(iterations)
+    cov_e = m2 - m1[:, :, None] * m1[:, None, :]
+    var_b = torch.einsum("ra,cab,rb->cr", jac_d, cov_e, jac_d) * (iterations / (iterations - 1.0))
+    w = var_b.mean(dim=0)
+    b_over_n = chain_mean_d.var(dim=0, unbiased=True)
+    rhat = torch.sqrt(((iterations - 1.0) / iterations * w + b_over_n) / w)
+    return rhat.cpu().numpy()
 
 
 def _finish_samples(samples, as_numpy):
@@ -248,7 +272,8 @@ def run_gibbs(y, X, iterations, prior_info, *, n_chains=1, seed=None, dtype="flo
     return GibbsResult(samples=_finish_samples(samples, as_numpy), mean=mean, cov=cov, chain_mean=chain_mean,
                        n_chains=int(n_chains), iterations=int(iterations), n_kept=meta["n_kept"], seed=seed,
                        dtype=str(dtype), info=dict(rss_min=sampler.rss_min, b_ols=sampler.b_ols,
-                                                   sigma2_init=sampler.sigma2_init))
+                                                   sigma2_init=sampler.sigma2_init),
+                       rhat=getattr(sampler, "last_rhat", None))
 
 
 def gibbs_sampler(y, X, iterations, prior_info, *, n_chains=1, seed=None, dtype="float64", thin=1, discard=0,
@@ -332,8 +357,11 @@ class SimplexSampler:
         sig_ref = np.sqrt(self.rss_zero / self.n) if self.rss_zero > 0 else 1.0
         base = np.concatenate([self.b_ols, [sig_ref]])
         comp = list(range(k)) + [kp]
-        chain_mean = base[None, :] + D.to_host(cstats[comp, :]).T / float(iterations)
-        return base + mean_e, cov_e, chain_mean
+        base_d = torch.from_numpy(base).to(cstats.device)
+        chain_mean_d = base_d[None, :] + cstats[comp, :].t() / float(iterations)
+        eye = torch.eye(k + 1, dtype=torch.float64, device=cstats.device)
+        self.last_rhat = _rhat(cstats, comp, _stat_layout(k, kp, mode)[2], eye, chain_mean_d, iterations)
+        return base + mean_e, cov_e, D.to_host(chain_mean_d)
 
 
 def run_gibbs_simplex(y, X, Vt_hat, S_hat, iterations, prior_info, burn=10000, stepsize=0.001, *, n_chains=1,
@@ -353,7 +381,8 @@ def run_gibbs_simplex(y, X, Vt_hat, S_hat, iterations, prior_info, burn=10000, s
     acc = D.to_host(accepted).astype(np.float64) / max(int(iterations), 1)
     return GibbsResult(samples=_finish_samples(samples, as_numpy), mean=mean, cov=cov, chain_mean=chain_mean,
                        n_chains=int(n_chains), iterations=int(iterations), n_kept=meta["n_kept"], seed=seed,
-                       dtype=str(dtype), acceptance=acc, info=dict(rss_min=sampler.rss_min, b_ols=sampler.b_ols))
+                       dtype=str(dtype), acceptance=acc, info=dict(rss_min=sampler.rss_min, b_ols=sampler.b_ols),
+                       rhat=getattr(sampler, "last_rhat", None))
 
 
 def gibbs_sampler_simplex(y, X, Vt_hat, S_hat, iterations, prior_info, burn=10000, stepsize=0.001, *,
