@@ -160,7 +160,7 @@ int launch_pass(const PredictArgs& a, cudaStream_t st) {
     dim3 grid((a.n_active + kPredWarps * 32 - 1) / (kPredWarps * 32), a.s_splits);
     const size_t smem = a.theta ? 2 * static_cast<size_t>(KP + 4) * PredTile<real, KP>::value * sizeof(real) : 16;
     auto kern = predict_pass_kernel<real, KP, NQ>;
-    if (smem > 48 * 1024) BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kPredWarps * 32, smem, st>>>(a);
     BMC_LAUNCH_CHECK();
     return BMC_OK;

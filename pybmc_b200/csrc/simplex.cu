@@ -19,7 +19,7 @@ int launch_simplex(const SimplexArgs& a, int stats_mode, int threads, cudaStream
 #define BMC_SIMPLEX_LAUNCH(MODE)                                                                              \
     do {                                                                                                      \
         auto kern = gibbs_simplex_kernel<real, KP, MODE>;                                                     \
-        if (smem > 48 * 1024)                                                                                 \
+        if (smem > 32 * 1024)                                                                                 \
             BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
         kern<<<blocks, threads, smem, stream>>>(a);                                                           \
     } while (0)
@@ -53,7 +53,7 @@ int launch_simplex_group(const SimplexArgs& a, int stats_mode, cudaStream_t stre
 #define BMC_SIMPLEX_GROUP(MODE)                                                                               \
     do {                                                                                                      \
         auto kern = gibbs_simplex_group_kernel<real, KP, MODE>;                                               \
-        if (smem > 48 * 1024)                                                                                 \
+        if (smem > 32 * 1024)                                                                                 \
             BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
         kern<<<blocks, wpb * 32, smem, stream>>>(a);                                                          \
     } while (0)

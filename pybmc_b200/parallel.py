@@ -87,3 +87,61 @@ def posterior_from_sums(sums, count, k):
             cov[r, c] = cov[c, r] = sums[idx] / count - mean[r] * mean[c]
             idx += 1
     return mean, cov
+
+
+# ------------------------------------------------------------------------------------------------
+# the two sharded entry points (one process per GPU; call them from every rank)
+# ------------------------------------------------------------------------------------------------
+def sharded_gibbs(y, X, iterations, prior_info, n_chains_total, *, seed, dtype="float32", thin=1, discard=0,
+                  keep_samples=False, group=None, device=None):
+    """Run this rank's share of ``n_chains_total`` conjugate chains and all-reduce the moment sums.
+
+    Every rank returns the same posterior mean / covariance of [b, sigma] (what a single GPU running
+    all chains would report) plus its own ``GibbsResult`` (samples of its chains, if kept)."""
+    from .inference_utils import ConjugateSampler, GibbsResult, _finish_samples, _moments_from_stats
+    rank, world = _world(group)
+    lo, hi = chain_range(n_chains_total, rank, world)
+    sampler = ConjugateSampler(y, X, prior_info, device)
+    samples, cstats, meta = sampler.run(iterations, hi - lo, seed, dtype, thin, discard, keep_samples, "full", lo)
+    total, count = merge_moment_sums(cstats.sum(dim=1), float(iterations) * (hi - lo), group)
+    k, kp = sampler.k, meta["kp"]
+    mean_e, cov_e = _moments_from_stats(total.cpu().numpy(), k, kp, meta["mode"], count)
+    jac = np.zeros((k + 1, k + 1))
+    jac[:k, :k] = sampler.w
+    jac[k, k] = 1.0
+    base = np.concatenate([sampler.w @ sampler.g_ols, [np.sqrt(sampler.sigma2_init)]])
+    local = GibbsResult(samples=_finish_samples(samples, True), mean=None, cov=None, chain_mean=None,
+                        n_chains=hi - lo, iterations=int(iterations), n_kept=meta["n_kept"], seed=int(seed),
+                        dtype=str(dtype), info=dict(chain_range=(lo, hi)))
+    return base + jac @ mean_e, jac @ cov_e @ jac.T, local
+
+
+def sharded_predictive_summary(preds, theta, Vt_hat, *, truth=None, percentiles=(2.5, 50.0, 97.5), seed=0,
+                               dtype="float32", group=None, device=None):
+    """Fused prediction with the nuclei split over ranks; every rank returns the full-length outputs
+    (all-gather).  ``theta`` are the posterior rows to use (already selected), identical on all ranks."""
+    from .sampling_utils import PredictiveProblem, PredictiveResult
+    rank, world = _world(group)
+    n = int(np.asarray(preds).shape[0])
+    lo, hi = point_range(n, rank, world)
+    if hi > lo:
+        prob = PredictiveProblem(np.asarray(preds)[lo:hi], theta, Vt_hat,
+                                 truth=None if truth is None else np.asarray(truth)[lo:hi], dtype=dtype,
+                                 device=device, point0=lo)
+        res = prob.run(percentiles=percentiles, seed=seed, as_numpy=False)
+        dev = res.mean.device
+        parts = dict(mean=res.mean, var=res.var, percentiles=res.percentiles, c_lt=res.c_lt, c_le=res.c_le)
+        passes = res.passes
+    else:   # more ranks than 4-aligned blocks of nuclei
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nq = len(tuple(percentiles))
+        parts = dict(mean=torch.zeros(0, dtype=torch.float64, device=dev),
+                     var=torch.zeros(0, dtype=torch.float64, device=dev),
+                     percentiles=torch.zeros((nq, 0), dtype=torch.float64, device=dev),
+                     c_lt=None if truth is None else torch.zeros(0, dtype=torch.int64, device=dev),
+                     c_le=None if truth is None else torch.zeros(0, dtype=torch.int64, device=dev))
+        passes = 0
+    out = {k: (None if v is None else gather_points(v, n, group).cpu().numpy()) for k, v in parts.items()}
+    return PredictiveResult(mean=out["mean"], var=out["var"], percentiles=out["percentiles"], c_lt=out["c_lt"],
+                            c_le=out["c_le"], draws=None, n_draws=int(np.asarray(theta).shape[0]), passes=passes,
+                            seed=int(seed))

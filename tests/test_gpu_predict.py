@@ -158,3 +158,25 @@ def test_rndm_m_random_calculator_dropin():
     assert np.all(np.abs(med - rmed) < 3 * 1.2533 * sd / np.sqrt(10000) * np.sqrt(2))
     assert np.all(np.abs(rndm_m.mean(axis=0) - ref_m.mean(axis=0)) < 3 * sd * np.sqrt(2 / 10000))
     assert np.all(np.abs(lo - rlo) < 3 * 2.7 * sd / np.sqrt(10000) * np.sqrt(2))
+
+
+@pytest.mark.parametrize("k", [1, 5, 8, 12, 33])
+def test_component_counts_and_precisions(k):
+    """Every compiled component count (4, 8, 16, 32, 64) in both precisions; fp64 with 8 components
+    needs exactly 48 KB of dynamic shared memory on top of the static barriers (opt-in path)."""
+    from pybmc_b200.sampling_utils import PredictiveProblem
+    rng = np.random.default_rng(100 + k)
+    n, m, s = 37, k + 3, 1500
+    preds = 500 + rng.normal(0, 2, size=(n, m))
+    vt = rng.normal(size=(k, m)) * 0.05
+    theta = np.column_stack([rng.normal(size=(s, k)) * 0.2 + rng.normal(size=k), np.abs(rng.normal(0.2, 0.02, s))])
+    truth = preds.mean(axis=1) + rng.normal(0, 0.3, n)
+    for dtype, tol in (("float64", 1e-12), ("float32", 1e-5)):
+        prob = PredictiveProblem(preds, theta, vt, truth=truth, dtype=dtype)
+        res = prob.run(percentiles=[2.5, 50, 97.5], seed=3, return_draws=True)
+        np.testing.assert_allclose(res.percentiles, np.percentile(res.draws, [2.5, 50, 97.5], axis=0), rtol=1e-13)
+        noiseless = prob.run(noise="none", return_draws=True)
+        want = (theta[:, :k] @ vt + 1.0 / m) @ preds.T             # sampling_utils.py:64-72
+        np.testing.assert_allclose(noiseless.draws, want, rtol=tol if dtype == "float64" else 1e-5)
+        c_lt, c_le = oc.order_counts(res.draws, truth)
+        assert np.array_equal(res.c_lt, c_lt) and np.array_equal(res.c_le, c_le)
