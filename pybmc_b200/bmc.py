@@ -74,168 +74,171 @@ def orthogonalize_arrays(preds, truth, components_kept, method="auto", device=No
                 Vt_hat=D.to_host(vt_hat), Vt_hat_normalized=D.to_host(vt_norm), method=used)
 
 
+# training options in the order upstream announces them (bmc.py:160-171); each default may depend on
+# the instance (number of components, singular values)
+_TRAIN_OPTIONS = (
+    ("iterations", lambda self: 50000),
+    ("sampler", lambda self: "gibbs_sampling"),
+    ("burn", lambda self: 10000),
+    ("stepsize", lambda self: 0.001),
+    ("b_mean_prior", lambda self: np.zeros(self.U_hat.shape[1])),
+    ("b_mean_cov", lambda self: np.diag(self.S_hat ** 2)),
+    ("nu0_chosen", lambda self: 1.0),
+    ("sigma20_chosen", lambda self: 0.02),
+)
+# GPU controls: optional, silent, defaults reproduce upstream's single fp64 chain
+_GPU_OPTIONS = {"n_chains": 1, "seed": None, "dtype": "float64", "thin": 1}
+_BANDS = (("Predicted_Lower", 0), ("Predicted_Median", 1), ("Predicted_Upper", 2))
+
+
+def _filter_rows(df, domain_filter):
+    """Row selection rules of ``evaluate`` (bmc.py:352-364): per column a callable on the column, a
+    (low, high) tuple, a list of admissible values or a single value; the key "multi" with a callable
+    is applied row-wise."""
+    for column, rule in (domain_filter or {}).items():
+        if callable(rule):
+            mask = df.apply(rule, axis=1) if column == "multi" else rule(df[column])
+        elif isinstance(rule, tuple) and len(rule) == 2:
+            mask = df[column].between(*rule)
+        elif isinstance(rule, list):
+            mask = df[column].isin(rule)
+        else:
+            mask = df[column] == rule
+        df = df[mask]
+    return df
+
+
 class BayesianModelCombination:
-    """Bayesian model combination of several models' predictions.
+    """Bayesian model combination of several models' predictions (drop-in for ``pybmc.bmc``).
 
     Args:
         models_list (list[str]): model (column) names to combine.
         data_dict (dict[str, pandas.DataFrame]): one DataFrame per property.
         truth_column_name (str): column holding the ground truth.
-        weights (list[float], optional): initial weights (kept for compatibility; unused upstream too).
+        weights (list[float], optional): kept for compatibility (unused upstream as well).
 
-    Attributes set by ``orthogonalize``: ``centered_experiment_train``, ``U_hat``, ``Vt_hat`` (right
-    singular vectors divided by the singular values), ``S_hat``, ``Vt_hat_normalized``,
-    ``_predictions_mean_train``, ``current_property``; by ``train``: ``samples``.
+    ``orthogonalize`` sets ``centered_experiment_train``, ``U_hat``, ``Vt_hat`` (right singular vectors
+    divided by their singular values), ``S_hat``, ``Vt_hat_normalized``, ``_predictions_mean_train``,
+    ``current_property``; ``train`` sets ``samples``.
     """
 
     def __init__(self, models_list, data_dict, truth_column_name, weights=None):
-        if not isinstance(models_list, list) or not all(isinstance(m, str) for m in models_list):
+        names_ok = isinstance(models_list, list) and all(isinstance(m, str) for m in models_list)
+        if not names_ok:
             raise ValueError("The 'models' should be a list of model names (strings) for Bayesian Combination.")
-        if not isinstance(data_dict, dict) or not all(isinstance(df, pd.DataFrame) for df in data_dict.values()):
+        frames_ok = isinstance(data_dict, dict) and all(isinstance(v, pd.DataFrame) for v in data_dict.values())
+        if not frames_ok:
             raise ValueError("The 'data_dict' should be a dictionary of pandas DataFrames, one per property.")
-        self.data_dict = data_dict
         self.models_list = models_list
-        # only the literal name "truth" is dropped (bmc.py:75); a truth column with another name
-        # that is listed in models_list is used as a model, as upstream
-        self.models = [m for m in models_list if m != "truth"]
-        self.weights = weights if weights is not None else None
+        self.data_dict = data_dict
         self.truth_column_name = truth_column_name
+        self.weights = weights
+        # only the literal name "truth" is dropped (bmc.py:75): a truth column with another name that is
+        # listed in models_list is used as a model, exactly as upstream
+        self.models = [name for name in models_list if name != "truth"]
 
-    # -- orthogonalize ------------------------------------------------------------------------
+    # -- orthogonalize ------------------------------------------------------------------------------
     def orthogonalize(self, property, train_df, components_kept, *, method="auto", device=None):
-        """SVD-orthogonalise the centred training predictions (bmc.py:79-130)."""
+        """SVD-orthogonalise the centred training predictions on the GPU (bmc.py:79-130)."""
         self.current_property = property
         self.selected_models_dataset = self.data_dict[property].copy()
-        preds = train_df[self.models].values
-        truth = train_df[self.truth_column_name].values
-        r = orthogonalize_arrays(preds, truth, components_kept, method=method, device=device)
-        self.centered_experiment_train = r["y"]
-        self.U_hat = r["U_hat"]
-        self.Vt_hat = r["Vt_hat"]
-        self.S_hat = r["S_hat"]
-        self.Vt_hat_normalized = r["Vt_hat_normalized"]
-        self._predictions_mean_train = r["mu"]
-        self._svd_method = r["method"]
+        result = orthogonalize_arrays(train_df[self.models].values, train_df[self.truth_column_name].values,
+                                      components_kept, method=method, device=device)
+        self._svd_method = result["method"]
+        for attribute, key in (("centered_experiment_train", "y"), ("U_hat", "U_hat"), ("Vt_hat", "Vt_hat"),
+                               ("S_hat", "S_hat"), ("Vt_hat_normalized", "Vt_hat_normalized"),
+                               ("_predictions_mean_train", "mu")):
+            setattr(self, attribute, result[key])
 
-    # -- train ------------------------------------------------------------------------------------
+    # -- train ----------------------------------------------------------------------------------------
     def train(self, training_options=None):
         """Sample the posterior of the combination coefficients (bmc.py:132-193).
 
-        ``training_options`` keys as upstream (iterations, sampler, burn, stepsize, b_mean_prior,
-        b_mean_cov, nu0_chosen, sigma20_chosen), each announced with an ``[INFO]`` line when
-        defaulted; optional GPU keys ``n_chains``, ``seed``, ``dtype``, ``thin`` are silent.
-        """
-        if training_options is None:
-            training_options = {}
-
-        def get_option(key, default):
-            if key not in training_options:
-                print(f"[INFO] Using default value for '{key}': {default}")
-            return training_options.get(key, default)
-
-        iterations = get_option("iterations", 50000)
-        sampler = get_option("sampler", "gibbs_sampling")
-        burn = get_option("burn", 10000)
-        stepsize = get_option("stepsize", 0.001)
-        num_components = self.U_hat.shape[1]
-        b_mean_prior = get_option("b_mean_prior", np.zeros(num_components))
-        b_mean_cov = get_option("b_mean_cov", np.diag(self.S_hat ** 2))
-        nu0_chosen = get_option("nu0_chosen", 1.0)
-        sigma20_chosen = get_option("sigma20_chosen", 0.02)
-        extra = dict(n_chains=training_options.get("n_chains", 1), seed=training_options.get("seed"),
-                     dtype=training_options.get("dtype", "float64"), thin=training_options.get("thin", 1))
-        if sampler == "simplex":
+        ``training_options`` takes upstream's keys (iterations, sampler, burn, stepsize, b_mean_prior,
+        b_mean_cov, nu0_chosen, sigma20_chosen); every key left out is announced with upstream's
+        ``[INFO]`` line.  Extra keys ``n_chains``, ``seed``, ``dtype``, ``thin`` steer the GPU run."""
+        given = dict(training_options or {})
+        opt = {}
+        for key, default in _TRAIN_OPTIONS:
+            if key in given:
+                opt[key] = given[key]
+            else:
+                opt[key] = default(self)
+                print(f"[INFO] Using default value for '{key}': {opt[key]}")
+        gpu = {key: given.get(key, default) for key, default in _GPU_OPTIONS.items()}
+        variance_prior = [opt["nu0_chosen"], opt["sigma20_chosen"]]
+        if opt["sampler"] == "simplex":
             self.samples = gibbs_sampler_simplex(self.centered_experiment_train, self.U_hat, self.Vt_hat, self.S_hat,
-                                                 iterations, [nu0_chosen, sigma20_chosen], burn=burn,
-                                                 stepsize=stepsize, **extra)
-        else:  # any other string selects the conjugate sampler, as upstream (bmc.py:187)
-            self.samples = gibbs_sampler(self.centered_experiment_train, self.U_hat, iterations,
-                                         [b_mean_prior, b_mean_cov, nu0_chosen, sigma20_chosen], **extra)
+                                                 opt["iterations"], variance_prior, burn=opt["burn"],
+                                                 stepsize=opt["stepsize"], **gpu)
+        else:   # any other name selects the conjugate sampler, as upstream (bmc.py:187)
+            self.samples = gibbs_sampler(self.centered_experiment_train, self.U_hat, opt["iterations"],
+                                         [opt["b_mean_prior"], opt["b_mean_cov"], *variance_prior], **gpu)
 
-    # -- predict ----------------------------------------------------------------------------------
-    def _require_trained(self):
+    # -- predict --------------------------------------------------------------------------------------
+    def _predict_frames(self, model_preds, vt_hat, domain_df, **kwargs):
+        """Shared tail of ``predict`` / ``predict2``: draws + the three band frames (bmc.py:226-242)."""
+        rndm_m, bands = rndm_m_random_calculator(model_preds, self.samples, vt_hat, **kwargs)
+        domain_df = domain_df.reset_index(drop=True)
+        frames = []
+        for column, which in _BANDS:
+            frame = domain_df.copy()
+            frame[column] = bands[which]
+            frames.append(frame)
+        return (rndm_m, *frames)
+
+    def _check_trained(self):
         if getattr(self, "samples", None) is None or getattr(self, "Vt_hat", None) is None:
             raise ValueError("Must call `orthogonalize()` and `train()` before predicting.")
-
-    @staticmethod
-    def _frames(domain_df, lower, median, upper):
-        lower_df = domain_df.copy()
-        lower_df["Predicted_Lower"] = lower
-        median_df = domain_df.copy()
-        median_df["Predicted_Median"] = median
-        upper_df = domain_df.copy()
-        upper_df["Predicted_Upper"] = upper
-        return lower_df, median_df, upper_df
 
     def predict(self, X, *, n_draws=DEFAULT_DRAWS, seed=None, dtype="float64", return_draws=True):
         """Posterior predictive draws and 2.5/50/97.5 % bands for the rows of ``X`` (bmc.py:195-242).
 
         Returns ``(rndm_m, lower_df, median_df, upper_df)``; ``return_draws=False`` skips building the
-        ``[n_draws, N]`` matrix (``rndm_m`` is then None).
-        """
-        self._require_trained()
+        ``[n_draws, N]`` matrix (``rndm_m`` is then None)."""
+        self._check_trained()
         if not isinstance(X, pd.DataFrame):
             raise ValueError("X must be a pandas DataFrame containing model predictions and domain info.")
-        domain_keys = [c for c in X.columns if c not in self.models]
-        rndm_m, (lower, median, upper) = rndm_m_random_calculator(
-            X[self.models].values, self.samples, self.Vt_hat, n_draws=n_draws, seed=seed, dtype=dtype,
-            return_draws=return_draws)
-        domain_df = X[domain_keys].reset_index(drop=True)
-        return (rndm_m, *self._frames(domain_df, lower, median, upper))
+        domain = X[[c for c in X.columns if c not in self.models]]
+        return self._predict_frames(X[self.models].values, self.Vt_hat, domain, n_draws=n_draws, seed=seed,
+                                    dtype=dtype, return_draws=return_draws)
 
     def predict2(self, property, *, n_draws=DEFAULT_DRAWS, seed=None, dtype="float64", return_draws=True):
-        """Same as ``predict`` for a whole property table, tolerating missing models (bmc.py:244-337)."""
-        self._require_trained()
+        """``predict`` for a whole property table; models absent from that table are tolerated with a
+        warning, unknown ones are an error (bmc.py:244-337)."""
+        self._check_trained()
         if property not in self.data_dict:
             raise KeyError(f"Property '{property}' not found in data_dict.")
-        df = self.data_dict[property].copy()
-        domain_keys = [c for c in df.columns if c not in self.models and c != self.truth_column_name]
-        available_models = [m for m in df.columns if m in self.models]
-        trained_models_set = set(self.models)
-        available_models_set = set(available_models)
-        missing_models = trained_models_set - available_models_set
-        extra_models = available_models_set - trained_models_set
+        table = self.data_dict[property].copy()
+        present = [c for c in table.columns if c in self.models]
+        trained_models_set, available_models_set = set(self.models), set(present)
         print(f"Available models: {available_models_set}")
         print(f"Trained models: {trained_models_set}")
-        if len(extra_models) > 0:
+        unknown = available_models_set - trained_models_set
+        if unknown:
             raise ValueError(
                 f"ERROR: Property '{property}' contains extra models not present during training: "
-                f"{list(extra_models)}. You must retrain if using a larger model space.")
-        if len(missing_models) > 0:
-            print(f"WARNING: Predicting on property '{property}' with missing models: {list(missing_models)}")
+                f"{list(unknown)}. You must retrain if using a larger model space.")
+        absent = trained_models_set - available_models_set
+        if absent:
+            print(f"WARNING: Predicting on property '{property}' with missing models: {list(absent)}")
             print("         The trained model weights include these models — prediction will proceed, "
                   "but results may not be statistically accurate.")
-        if len(available_models) == 0:
+        if not present:
             raise ValueError("No available trained models are present in prediction DataFrame.")
-        model_indices = [self.models.index(m) for m in available_models]
-        vt_reduced = self.Vt_hat[:, model_indices]
-        rndm_m, (lower, median, upper) = rndm_m_random_calculator(
-            df[available_models].values, self.samples, vt_reduced, n_draws=n_draws, seed=seed, dtype=dtype,
-            return_draws=return_draws)
-        domain_df = df[domain_keys].reset_index(drop=True)
-        return (rndm_m, *self._frames(domain_df, lower, median, upper))
+        columns = [self.models.index(name) for name in present]
+        domain = table[[c for c in table.columns if c not in self.models and c != self.truth_column_name]]
+        return self._predict_frames(table[present].values, self.Vt_hat[:, columns], domain, n_draws=n_draws,
+                                    seed=seed, dtype=dtype, return_draws=return_draws)
 
-    # -- evaluate ---------------------------------------------------------------------------------
+    # -- evaluate -------------------------------------------------------------------------------------
     def evaluate(self, domain_filter=None, *, n_draws=DEFAULT_DRAWS, seed=None, dtype="float64"):
         """Coverage of the 0, 5, ..., 100 % credible intervals over the current property's table,
-        optionally filtered (bmc.py:339-376).  The predictive matrix is never materialised: the
-        fused kernel returns the two order counts per point that decide every level."""
-        df = self.data_dict[self.current_property]
-        if domain_filter:
-            for col, cond in domain_filter.items():
-                if col == "multi" and callable(cond):
-                    df = df[df.apply(cond, axis=1)]
-                elif callable(cond):
-                    df = df[cond(df[col])]
-                elif isinstance(cond, tuple) and len(cond) == 2:
-                    df = df[df[col].between(*cond)]
-                elif isinstance(cond, list):
-                    df = df[df[col].isin(cond)]
-                else:
-                    df = df[df[col] == cond]
-        preds = df[self.models].to_numpy()
-        truth = np.asarray(df[self.truth_column_name].tolist(), dtype=np.float64)
+        optionally filtered (bmc.py:339-376).  The predictive matrix is never materialised: the fused
+        kernel returns the two order counts per point that decide every level."""
+        table = _filter_rows(self.data_dict[self.current_property], domain_filter)
+        truth = np.asarray(table[self.truth_column_name].tolist(), dtype=np.float64)
         np.random.seed(142858)   # side effect of rndm_m_random_calculator upstream (sampling_utils.py:54)
-        res = predictive_summary(preds, self.samples, self.Vt_hat, truth=truth, n_draws=n_draws, seed=seed,
-                                 dtype=dtype, return_draws=False)
-        return coverage_from_counts(np.arange(0, 101, 5), res.n_draws, res.c_lt, res.c_le)
+        summary = predictive_summary(table[self.models].to_numpy(), self.samples, self.Vt_hat, truth=truth,
+                                     n_draws=n_draws, seed=seed, dtype=dtype, return_draws=False)
+        return coverage_from_counts(np.arange(0, 101, 5), summary.n_draws, summary.c_lt, summary.c_le)
