@@ -24,3 +24,16 @@ __all__ = [
     "coverage",
     "rndm_m_random_calculator",
 ]
+
+
+def __getattr__(name):
+    """``Dataset`` (HDF5/CSV loading and splitting, pybmc/data.py) is outside the accelerated path: it is
+    re-exported from an installed upstream ``pybmc`` when there is one."""
+    if name == "Dataset":
+        try:
+            from pybmc.data import Dataset
+        except ImportError as exc:
+            raise AttributeError("pybmc_b200 accelerates the inference path only; install pybmc for its "
+                                 "Dataset loader (or build the data_dict of DataFrames yourself)") from exc
+        return Dataset
+    raise AttributeError(f"module 'pybmc_b200' has no attribute {name!r}")

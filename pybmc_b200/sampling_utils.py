@@ -49,6 +49,8 @@ def coverage_from_counts(percentiles, n_draws, c_lt, c_le, device=None):
     c_lt = c_lt if isinstance(c_lt, torch.Tensor) else torch.from_numpy(np.asarray(c_lt, dtype=np.int64)).to(dev)
     c_le = c_le if isinstance(c_le, torch.Tensor) else torch.from_numpy(np.asarray(c_le, dtype=np.int64)).to(dev)
     n = int(c_lt.numel())
+    if n == 0:
+        raise ZeroDivisionError("division by zero")     # upstream divides by the number of points (:35)
     lo_d = torch.tensor(lo, dtype=torch.int64, device=dev)
     hi_d = torch.tensor(hi, dtype=torch.int64, device=dev)
     out = torch.empty(len(lo), dtype=torch.int64, device=dev)
@@ -132,6 +134,13 @@ def _launch_fused(dev, dtype, *, n_points, point0, n_draws, k, u, mu, truth, the
         raise ValueError("at least one percentile is required")
     if np.any(probs < 0) or np.any(probs > 100):
         raise ValueError("Percentiles must be in the range [0, 100]")
+    if n_points == 0:      # nothing to predict: empty outputs of the right shapes, as NumPy would give
+        empty = np.zeros(0)
+        return PredictiveResult(mean=empty, var=empty, percentiles=np.zeros((nq_total, 0)),
+                                c_lt=None if truth is None else np.zeros(0, dtype=np.int64),
+                                c_le=None if truth is None else np.zeros(0, dtype=np.int64),
+                                draws=np.zeros((n_draws, 0)) if return_draws else None, n_draws=n_draws, passes=0,
+                                seed=int(seed))
     mean = torch.empty(n_points, dtype=torch.float64, device=dev)
     var = torch.empty(n_points, dtype=torch.float64, device=dev)
     quant = torch.empty((nq_total, n_points), dtype=torch.float64, device=dev)
@@ -183,6 +192,12 @@ class PredictiveProblem:
             raise ValueError(f"at most {_lib.MAX_COMPONENTS} components are supported")
         self.n_points = preds.shape[0]
         self.point0 = int(point0)
+        if self.n_points == 0:
+            self.mu = torch.zeros(0, dtype=torch.float64, device=self.dev)
+            self.u = torch.zeros((0, self.k), dtype=tdt, device=self.dev)
+            self.truth = None if truth is None else torch.zeros(0, dtype=torch.float64, device=self.dev)
+            self.set_draws(theta)
+            return
         pd_ = D.to_device(preds, self.dev)
         vd = D.to_device(Vt_hat, self.dev)
         # mu = mean over models: the 1/M default weights of :64;  u = preds Vt_hat' (:64-72 in K-space)

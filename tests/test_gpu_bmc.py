@@ -139,3 +139,24 @@ def test_pipeline_against_reference_golden_run(golden):
     # 40 points: one point changing sides moves a level by 2.5 %
     assert np.max(np.abs(cov - g["coverage"])) <= 5.0
     assert cov[0] == g["coverage"][0] == 0.0
+
+
+def test_edge_cases_empty_and_single_point(toy):
+    import pybmc_b200 as pb
+    from pybmc_b200.sampling_utils import rndm_m_random_calculator
+    bmc, df, train = toy
+    bmc.orthogonalize("target", train, 2)
+    bmc.train({"iterations": 10000, "dtype": "float32", "seed": 1})
+    assert bmc.samples.dtype == np.float32 and bmc.samples.shape == (10000, 3)
+    one = df.iloc[[2]][["x", "model1", "model2", "model3"]]
+    rndm_m, lo, med, hi = bmc.predict(one, seed=2)                         # a single point
+    assert rndm_m.shape == (10000, 1) and len(lo) == len(med) == len(hi) == 1
+    none = df.iloc[:0][["x", "model1", "model2", "model3"]]
+    rndm_m, lo, med, hi = bmc.predict(none)                                # no points at all
+    assert rndm_m.shape == (10000, 0) and lo.empty and list(lo.columns) == ["x", "Predicted_Lower"]
+    with pytest.raises(ZeroDivisionError):                                 # upstream divides by the point count
+        bmc.evaluate({"x": (100, 200)})
+    empty = pb.gibbs_sampler(np.array([1.0, 2.0, 3.0]), np.eye(3)[:, :2], 0, (np.zeros(2), np.eye(2), 1.0, 1.0))
+    assert empty.shape == (0, 3)
+    with pytest.raises(np.linalg.LinAlgError):                             # singular X'X, as np.linalg.inv upstream
+        pb.gibbs_sampler(np.ones(3), np.ones((3, 2)), 5, (np.zeros(2), np.eye(2), 1.0, 1.0))
