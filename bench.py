@@ -348,6 +348,7 @@ def run_native(args):
                                flush, hbm_peak)
     if rank == 0 and world == 1:
         line["cpu_baseline"] = cpu_baseline()
+        line["extra"]["predict_cpu_baseline"] = cpu_predict_baseline()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -522,6 +523,32 @@ def extras_config5(out, torch, dev, world, rank, timed, pb, steps, hbm_peak):
                      "fp64_TFLOP/s": flops / (ms * 1e-3) / 1e12}
     out["config5_orthogonalize_f64"] = {"config": f"configs[4]: {n} x 256 fp64 rows per GPU, K=64", **res}
     del preds, xc
+
+
+def _cpu_predict(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    preds, theta, vt, truth, seed = args
+    from oracle import bmc_oracle as oc
+    rndm_m, _ = oc.predictive_draws(preds, theta, vt, np.random.default_rng(seed))
+    # the reference re-sorts every column for each of the 21 levels (pybmc/sampling_utils.py:24-28); the
+    # port sorts once, so this baseline is faster than the reference itself
+    oc.coverage_levels(np.arange(0, 101, 5), rndm_m, truth)
+    return rndm_m.shape[0] * rndm_m.shape[1]
+
+
+def cpu_predict_baseline():
+    """rndm_m_random_calculator + coverage (oracle port) at the reference's S = 10^4 on all host cores."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    preds, vt, theta, truth = config4_inputs(629, 12000)
+    jobs = [(preds, theta, vt, truth, 50 + c) for c in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        units = sum(pool.map(_cpu_predict, jobs))
+        dt = time.perf_counter() - t0
+    return {"value": units / dt, "unit": "samples*points/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} x (629 points x 10000 draws x K=16: predictive matrix, 3 percentiles, 21 coverage "
+                      f"levels), one process per core, {dt:.1f} s"}
 
 
 def cpu_baseline():
