@@ -35,12 +35,6 @@ ITERATIONS = 10000
 KEEP_PER_CHAIN = 10
 SEED = 0xB200 + 3
 
-# warp-level instructions the conjugate kernel issues per chain-iteration and warp (fp32, K=8, full
-# cross moments), from profiles/ (ncu smsp__inst_executed.sum / (chains/32 * iterations)); the
-# roofline "achieved" below is this constant x measured chain-iterations/s
-INST_PER_CHAIN_ITER = {"f32": None}
-
-
 # ------------------------------------------------------------------------------------------------
 # synthetic inputs
 # ------------------------------------------------------------------------------------------------
@@ -204,8 +198,7 @@ def run_native(args):
     import torch.distributed as dist
     import pybmc_b200 as pb
     from pybmc_b200 import _lib
-    from pybmc_b200.inference_utils import ConjugateSampler, SimplexSampler
-    from pybmc_b200.sampling_utils import PredictiveProblem
+    from pybmc_b200.inference_utils import ConjugateSampler
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

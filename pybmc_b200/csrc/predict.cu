@@ -80,7 +80,7 @@ int segment_len(double expected_total, int splits) {
 }
 
 struct PassShape {
-    int s_splits, seg_len, cand_stride, retry_splits, retry_seg;
+    int s_splits, seg_len, cand_stride, retry_splits;
 };
 
 PassShape make_shape(long long n_points, long long n_draws, double expected) {
@@ -98,7 +98,6 @@ PassShape make_shape(long long n_points, long long n_draws, double expected) {
     int rs = std::min(16, std::min(tiles, kMaxSlots));
     while (rs > 1 && rs * segment_len(expected, rs) > sh.cand_stride) rs >>= 1;
     sh.retry_splits = std::max(1, rs);
-    sh.retry_seg = sh.cand_stride / sh.retry_splits;
     return sh;
 }
 
