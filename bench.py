@@ -316,14 +316,19 @@ def run_native(args):
     alg_bytes = CHAINS_PER_GPU * (KEEP_PER_CHAIN * 9 * 4 + 54 * 8 * 2 * (ITERATIONS // 64))
     kernel_s = ms_step * 1e-3
     inst = load_inst_per_iter()
-    issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9                    # warp-instructions / ns -> Ginst/s
+    nominal_issue = 148 * 4 * sm_mhz * 1e6 / 1e9                 # 148 SMs x 4 schedulers x clock, Gwarp-inst/s
+    pipe_peaks = measure_pipe_peaks(torch, dev)
+    issue_peak = max(pipe_peaks["issue"]["Gwarp_inst_per_s"], pipe_peaks["ffma"]["Gwarp_inst_per_s"])
     line["roofline"] = {
         "kernel": "gibbs_conjugate_kernel<float,8,2>",
         "bound": "issue", "unit": "Gwarp-inst/s",
         "achieved": (inst * per_gpu_rate / 32 / 1e9) if inst else None,
         "peak": issue_peak, "frac": (inst * per_gpu_rate / 32 / 1e9 / issue_peak) if inst else None,
-        "peak_source": "148 SMs x 4 schedulers x 1 warp-inst/clk x SM clock sampled during the run",
+        "peak_source": "measured in this run by bmc_probe (independent FFMA + LOP3 streams, all SMs); nominal "
+                       "148 SMs x 4 schedulers x sampled SM clock = %.0f" % nominal_issue,
+        "pipe_peaks_measured": pipe_peaks,
         "warp_inst_per_chain_iter": inst,
+        "fma_pipe": fma_pipe_view(per_gpu_rate, sm_mhz),
         "traffic": load_dram_bytes(),
         "hbm": {"bound": "hbm", "achieved": alg_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / kernel_s / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs"
@@ -346,6 +351,45 @@ def run_native(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_pipe_peaks(torch, dev):
+    """FP32 FMA, MUFU, Philox-mix and dual-issue peaks of this GPU, measured now (bmc_probe)."""
+    from pybmc_b200 import _lib
+    lib = _lib.load()
+    sink = torch.zeros(1, dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    blocks, threads, iters = 148 * 8, 256, 20000
+    out = {}
+    for kind, name in ((0, "ffma"), (1, "mufu"), (2, "philox_mix"), (3, "issue"), (4, "imad_wide_plus_iadd"),
+                       (5, "imad_hi"), (6, "imad"), (7, "lop3")):
+        ops = lib.bmc_probe_ops_per_iteration(kind)
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.bmc_probe(kind, iters, blocks, threads, sink.data_ptr(), st))
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        thread_ops = float(blocks) * threads * iters * ops
+        out[name] = {"Gwarp_inst_per_s": thread_ops / 32 / (best * 1e-3) / 1e9, "ms": best}
+    out["ffma"]["TFLOP_per_s"] = out["ffma"]["Gwarp_inst_per_s"] * 32 * 2 / 1e3
+    return out
+
+
+def fma_pipe_view(rate_per_gpu, sm_mhz):
+    """The busiest pipe of the sampler is the FMA pipe: Philox's 32x32->64 multiplies issue at a quarter
+    of the FFMA rate on B200 (bmc_probe: IMAD.WIDE 0.23, IMAD 0.50, LOP3 0.50, MUFU 0.125 of one
+    warp-instruction per clock and scheduler).  Fraction = pipe cycles the opcode mix needs / cycles spent."""
+    try:
+        need = float(json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))[
+            "gibbs_conjugate_f32_k8_full"]["fma_pipe_cycles_per_warp_iter"])
+    except (OSError, KeyError, ValueError):
+        return None
+    spent = 148 * 4 * sm_mhz * 1e6 / (rate_per_gpu / 32)        # scheduler-cycles per warp-iteration
+    return {"cycles_needed_per_warp_iter": need, "cycles_spent_per_warp_iter": spent, "frac": need / spent}
 
 
 def load_inst_per_iter():

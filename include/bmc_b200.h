@@ -196,6 +196,13 @@ int bmc_column_moments(const double* matrix, int64_t s_rows, int64_t n_cols, int
 int bmc_coverage_levels(const int64_t* c_lt, const int64_t* c_le, int64_t n_points, const int64_t* lo_idx,
                         const int64_t* hi_idx, int n_levels, int64_t* covered, void* stream);
 
+/* ---- peak probes for the pipe rooflines: register-only kernels measuring what the
+ *      box sustains on the FP32 FMA pipe (kind 0), the MUFU pipe (1), the Philox integer mix (2) and
+ *      dual-pipe issue (3).  `iters` loop iterations per thread, each issuing
+ *      bmc_probe_ops_per_iteration(kind) thread-level operations; `sink` is a dev float[1]. */
+int bmc_probe_ops_per_iteration(int kind);
+int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

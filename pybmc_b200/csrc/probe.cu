@@ -1,0 +1,152 @@
+// Peak probes for the non-HBM rooflines.  SURVEY.md section 8(d): the sampler and predictive kernels
+// are bound by the FP32 FMA pipe, the MUFU (XU) pipe and integer issue, and MEASURED_PEAKS.json only
+// holds the HBM and bf16 tensor peaks -- so bench.py measures the pipe peaks it divides by with these
+// kernels, on the same box and at the clocks of the same run.  Each probe is a grid of warps running
+// `iters` iterations of independent register-only chains; the result is written so nothing is elided.
+#include "common.h"
+
+namespace {
+
+constexpr int kChains = 8;
+
+__global__ void probe_ffma(long long iters, float* sink) {
+    float a[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) a[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+    const float m = 0.999999f, c = 1e-7f;
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) a[i] = fmaf(a[i], m, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i];
+    if (s == 123.456f) sink[0] = s;
+}
+
+__global__ void probe_mufu(long long iters, float* sink) {
+    float a[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) a[i] = 0.5f + 1e-3f * (threadIdx.x + i);
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i];
+    if (s == 123.456f) sink[0] = s;
+}
+
+// the sampler's integer mix: 32x32->64 multiply (fma pipe) + three-input logic (alu pipe), as in Philox
+__global__ void probe_philox_mix(long long iters, float* sink) {
+    unsigned int a[kChains], b[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        a[i] = threadIdx.x * 2654435761u + i;
+        b[i] = a[i] ^ 0x9E3779B9u;
+    }
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+            const unsigned long long p = static_cast<unsigned long long>(0xD2511F53u) * a[i];
+            a[i] = static_cast<unsigned int>(p >> 32) ^ b[i] ^ 0xBB67AE85u;
+            b[i] = static_cast<unsigned int>(p);
+        }
+    }
+    unsigned int s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i] ^ b[i];
+    if (s == 0x12345678u) sink[0] = static_cast<float>(s);
+}
+
+// issue peak: independent FFMA (fma pipe) and LOP3 (alu pipe) streams side by side
+__global__ void probe_issue(long long iters, float* sink) {
+    float a[kChains];
+    unsigned int b[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        a[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+        b[i] = threadIdx.x * 2654435761u + i;
+    }
+    const float m = 0.999999f, c = 1e-7f;
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+            a[i] = fmaf(a[i], m, c);
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(b[(i + 1) % kChains]), "r"(0x9E3779B9u));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i] + static_cast<float>(b[i] & 1u);
+    if (s == 123.456f) sink[0] = s;
+}
+
+// single-instruction streams, to price the pieces of Philox
+template <int KIND>
+__global__ void probe_single(long long iters, float* sink) {
+    unsigned int a[kChains], b[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        a[i] = threadIdx.x * 2654435761u + i;
+        b[i] = a[i] ^ 0x9E3779B9u;
+    }
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+            if (KIND == 0) {            // IMAD.WIDE.U32
+                const unsigned long long p = static_cast<unsigned long long>(0xD2511F53u) * a[i];
+                a[i] = static_cast<unsigned int>(p >> 32) + static_cast<unsigned int>(p);
+            } else if (KIND == 1) {     // IMAD.HI.U32
+                a[i] = __umulhi(a[i], 0xD2511F53u);
+            } else if (KIND == 2) {     // IMAD (32-bit multiply-add)
+                a[i] = a[i] * 0xD2511F53u + b[i];
+            } else {                    // LOP3
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(0x9E3779B9u));
+            }
+        }
+    }
+    unsigned int s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i] ^ b[i];
+    if (s == 0x12345678u) sink[0] = static_cast<float>(s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bmc_probe_ops_per_iteration(int kind) {
+    // thread-level operations one loop iteration issues (bench.py turns time into a rate)
+    switch (kind) {
+        case 0: return kChains;          // FFMA
+        case 1: return 2 * kChains;      // MUFU (ex2 + lg2)
+        case 2: return 2 * kChains;      // IMAD.WIDE + LOP3
+        case 3: return 2 * kChains;      // FFMA + LOP3
+        case 4: case 5: case 6: case 7: return kChains;   // IMAD.WIDE(+IADD) / IMAD.HI / IMAD / LOP3 alone
+        default: return 0;
+    }
+}
+
+int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, void* stream) {
+    BMC_REQUIRE(kind >= 0 && kind <= 7 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink,
+                "bmc_probe: bad arguments");
+    cudaStream_t st = bmc::as_stream(stream);
+    switch (kind) {
+        case 0: probe_ffma<<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 1: probe_mufu<<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 2: probe_philox_mix<<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 3: probe_issue<<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 4: probe_single<0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 5: probe_single<1><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 6: probe_single<2><<<blocks, threads, 0, st>>>(iters, sink); break;
+        default: probe_single<3><<<blocks, threads, 0, st>>>(iters, sink); break;
+    }
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+}  // extern "C"
