@@ -16,3 +16,12 @@ for rep in range(3):
     t_perm, rows = T(lambda: samples.permute(2, 0, 1).reshape(-1, 9).to(torch.float64))
     t_d2h, _ = T(lambda: rows.cpu())
     print(f"setup {t_setup:.2f} run {t_run:.2f} summarise {t_sum:.2f} finish {t_fin:.2f} (permute {t_perm:.2f} d2h {t_d2h:.2f}) ms")
+
+import cProfile, pstats
+for rep in range(2):
+    t, res = T(lambda: pb.run_gibbs(y, X, 10000, prior, n_chains=65536, seed=1, dtype="float32", thin=1000, stats="full"))
+    print(f"run_gibbs total {t:.2f} ms")
+pr = cProfile.Profile(); pr.enable()
+pb.run_gibbs(y, X, 10000, prior, n_chains=65536, seed=1, dtype="float32", thin=1000, stats="full")
+torch.cuda.synchronize(); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(14)

@@ -53,8 +53,9 @@ def to_device(a, dev, dtype=torch.float64):
 
 
 def to_host(t):
-    """Device tensor -> NumPy array.  Large results go through page-locked memory (PyTorch caches the
-    pinned blocks), which is ~10x faster than a pageable copy; the array keeps the pinned block alive."""
+    """Device tensor -> NumPy array.  Large results land in page-locked memory taken from PyTorch's
+    caching host allocator (a fresh cudaHostAlloc costs ~1 ms per MB, a cached block nothing), ~10x
+    faster than a pageable copy; the returned array owns the block until it is garbage-collected."""
     t = t.detach()
     if t.device.type != "cuda" or t.numel() * t.element_size() < (1 << 20):
         return t.cpu().numpy()
