@@ -48,7 +48,8 @@ int launch_group(const GibbsArgs& a, int stats_mode, cudaStream_t stream) {
 }
 
 // with fewer chains than this a thread-per-chain launch leaves schedulers idle; eight lanes per chain
-// cost ~50 % more instructions per chain-iteration but bring eight times the warps
+// cost ~50 % more instructions per chain-iteration but bring eight times the warps.  Measured crossover
+// on B200 (profiles/layout_sweep.py): 16,384 chains (1.23 vs 1.18 ms); 32,768: 1.8 vs 2.3; 4096: 1.2 vs 0.5.
 constexpr long long kConjGroupBelow = 16384;
 
 template <typename real>

@@ -66,8 +66,9 @@ int launch_simplex_group(const SimplexArgs& a, int stats_mode, cudaStream_t stre
 }
 
 // below this many chains a thread-per-chain launch cannot fill the machine (148 SMs x 4 schedulers x
-// a few warps each): give every chain eight lanes instead
-constexpr long long kGroupPerChainBelow = 131072;
+// a few warps each): give every chain eight lanes instead.  Measured crossover on B200
+// (profiles/layout_sweep.py): 16,384 chains (4.08 vs 4.03 ms); 32,768: 4.8 vs 7.8 ms; 4096: 4.1 vs 1.7 ms.
+constexpr long long kGroupPerChainBelow = 16384;
 
 template <typename real>
 int dispatch_simplex(const SimplexArgs& a, int stats_mode, int threads, cudaStream_t stream) {

@@ -262,15 +262,15 @@ def test_simplex_chain_matches_oracle_k8_m16():
 
 def test_simplex_layouts_agree_with_oracle_and_each_other():
     """Few chains run eight lanes per chain, many chains one chain per thread: same stream, same law.
-    Chain ids are global, so chain 5 of a 131072-chain launch is the oracle's chain 5."""
+    Chain ids are global, so chain 5 of a 16384-chain launch is the oracle's chain 5."""
     import pybmc_b200 as pb
     y, X, Vt, S = _simplex_case()
     burn, T, seed = 40, 60, 77
-    many = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02, n_chains=131072, seed=seed,
+    many = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02, n_chains=16384, seed=seed,
                                 stats="full")
     few = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02, n_chains=8, seed=seed,
                                stats="full")
-    got_many = many.samples.reshape(131072, T, 4)
+    got_many = many.samples.reshape(16384, T, 4)
     got_few = few.samples.reshape(8, T, 4)
     np.testing.assert_allclose(got_many[:8], got_few, rtol=1e-9, atol=1e-12)
     for c in (0, 5):
