@@ -209,6 +209,12 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if not os.path.exists(_lib.LIB_PATH):       # snapshot without the built library: compile it (rank 0), never fall back
+        if rank == 0:
+            from pybmc_b200.build import build_library
+            build_library(force=True)
+        if world > 1:
+            dist.barrier()
     lib = _lib.load()
 
     def barrier():
