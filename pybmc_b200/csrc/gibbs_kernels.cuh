@@ -75,13 +75,13 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     for (int j = 0; j < (NS > 0 ? NS : 1); ++j) acc[j] = real(0);
 
     real s2 = static_cast<real>(a.sigma2_init);
+    real sig = M::sqrt(s2);
     real* const out = static_cast<real*>(a.samples);
     long long next_store = a.samples ? a.store_from : -1;
     long long slot = 0;
 
     for (long long it = 0; it < a.iterations; ++it) {
         const uint32_t it32 = static_cast<uint32_t>(it);
-        const real inv_s2 = M::rcp(s2);
         real e[KP];
         real rss0 = rss_min, rss1 = real(0);
 #pragma unroll
@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
             for (int q = 0; q < 4; ++q) {
                 const int k = 4 * j + q;
                 if (k < KP) {
-                    const real p = M::fma(d[k], inv_s2, real(1));
-                    const real sd = M::rsqrt(p);
+                    // 1/sqrt(p_k) = sigma / sqrt(d_k + s2): one MUFU on the s2 -> e -> RSS -> s2 dependency
+                    const real sd = sig * M::rsqrt(d[k] + s2);
                     e[k] = sd * M::fma(pull[k], sd, z[q]);          // pull/p + z/sqrt(p)
                     if (k & 1) rss1 = M::fma(d[k] * e[k], e[k], rss1);
                     else rss0 = M::fma(d[k] * e[k], e[k], rss0);
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         const real gm = gamma_unit_scale<real>(gc, it32, chain, kTagGibbs, a.key0, a.key1);
         s2 = M::div(scale, gm);
         s2 = s2 > real(1e-6) ? s2 : real(1e-6);
-        const real sig = M::sqrt(s2);
+        sig = M::sqrt(s2);
 
         if (MODE != 0) {
             const real es = sig - sig_ref;
@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
 #pragma unroll
     for (int c = 0; c < KP; ++c) acc2[c] = real(0);
     real s2 = static_cast<real>(a.sigma2_init);
+    real sig = M::sqrt(s2);
     real* const out = static_cast<real*>(a.samples);
     const int total = static_cast<int>(a.iterations);
     int next_store = a.samples ? static_cast<int>(a.store_from) : -1;
@@ -234,17 +235,15 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
             const int it = base + j;
             const real* row = mine + j * ROW;
             const real z = g < KP ? row[g] : real(0);
-            const real gm = row[KP];
-            const real inv_s2 = M::rcp(s2);
-            const real p = M::fma(d, inv_s2, real(1));
-            const real sd = M::rsqrt(p);
+            const real inv_gm = M::rcp(row[KP]);                         // off the dependency chain
+            const real sd = sig * M::rsqrt(d + s2);                      // 1/sqrt(d/s2 + 1)
             const real e = sd * M::fma(pull, sd, z);                      // pull/p + z/sqrt(p)
             real rss = (d * e) * e;
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) rss += __shfl_xor_sync(0xffffffffu, rss, o, G);
-            s2 = M::div(real(0.5) * (prior_scale + (rss_min + rss)), gm);
+            s2 = (real(0.5) * (prior_scale + (rss_min + rss))) * inv_gm;
             s2 = s2 > real(1e-6) ? s2 : real(1e-6);
-            const real sig = M::sqrt(s2);
+            sig = M::sqrt(s2);
             if (MODE != 0) {
                 const real es = sig - sig_ref;
                 acc1 += e;
