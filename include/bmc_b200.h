@@ -196,6 +196,12 @@ int bmc_column_moments(const double* matrix, int64_t s_rows, int64_t n_cols, int
 int bmc_coverage_levels(const int64_t* c_lt, const int64_t* c_le, int64_t n_points, const int64_t* lo_idx,
                         const int64_t* hi_idx, int n_levels, int64_t* covered, void* stream);
 
+/* ---- data split by distance: Dataset.separate_points_distance_allSets, pybmc/data.py:194-245 ---------
+ * cls[i] = 0 if a reference point lies within d1 of point i (Euclidean, <=), 1 if one lies within d2 but
+ * none within d1, 2 otherwise.  points dev [n][dim], refs dev [r][dim] (fp64), cls dev int32 [n]. */
+int bmc_nearest_class(const double* points, int64_t n, const double* refs, int64_t r, int dim, double d1,
+                      double d2, int32_t* cls, void* stream);
+
 /* ---- peak probes for the pipe rooflines: register-only kernels measuring what the
  *      box sustains on the FP32 FMA pipe (kind 0), the MUFU pipe (1), the Philox integer mix (2) and
  *      dual-pipe issue (3).  `iters` loop iterations per thread, each issuing

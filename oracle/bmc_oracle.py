@@ -272,6 +272,26 @@ def coverage_from_counts(percentiles, n_draws, c_lt, c_le):
 
 
 # --------------------------------------------------------------------------- #
+# data split by distance                                                       #
+# --------------------------------------------------------------------------- #
+def distance_classes(points, refs, distance1, distance2):
+    """data.py:194-245: indices of ``points`` whose nearest reference point is within ``distance1``,
+    within ``distance2`` only, or farther.  One norm per pair, `<=`, as the reference's double loop."""
+    points = np.asarray(points, dtype=float)
+    refs = np.asarray(refs, dtype=float)
+    near, mid, far = [], [], []
+    for i, p in enumerate(points):
+        dist = np.array([np.linalg.norm(p - q) for q in refs])           # :218-221, :228-231
+        if np.any(dist <= distance1):
+            near.append(i)                                               # :223-225
+        elif np.any(dist <= distance2):
+            mid.append(i)                                                # :233-235
+        else:
+            far.append(i)                                                # :237-238
+    return near, mid, far
+
+
+# --------------------------------------------------------------------------- #
 # sufficient-statistic identities used by the device kernels (checked in tests)  #
 # --------------------------------------------------------------------------- #
 def simultaneous_diagonalisation(gram, lam):

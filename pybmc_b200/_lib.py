@@ -68,6 +68,7 @@ SIGNATURES = {
     "bmc_coverage_counts": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "bmc_column_moments": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
     "bmc_coverage_levels": (_int, [_p, _p, _i64, _p, _p, _int, _p, _p]),
+    "bmc_nearest_class": (_int, [_p, _i64, _p, _i64, _int, _dbl, _dbl, _p, _p]),
     "bmc_probe_ops_per_iteration": (_int, [_int]),
     "bmc_probe": (_int, [_int, _i64, _int, _int, _p, _p]),
 }

@@ -116,4 +116,17 @@ int bmc_residual_ss(const double* x, int64_t n, int k, int64_t ld, const double*
     return BMC_OK;
 }
 
+int bmc_nearest_class(const double* points, int64_t n, const double* refs, int64_t r, int dim, double d1,
+                      double d2, int32_t* cls, void* stream) {
+    BMC_REQUIRE(points && refs && cls, "bmc_nearest_class: null pointer");
+    BMC_REQUIRE(n >= 1 && r >= 1 && dim >= 1 && dim <= 1024, "bmc_nearest_class: bad shape n=%lld r=%lld dim=%d",
+                (long long)n, (long long)r, dim);
+    const int tile_refs = 1024 / dim > 0 ? 1024 / dim : 1;
+    const size_t smem = sizeof(double) * tile_refs * dim;
+    nearest_class_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, smem, as_stream(stream)>>>(
+        points, n, refs, r, dim, d1, d2, cls);
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
 }  // extern "C"

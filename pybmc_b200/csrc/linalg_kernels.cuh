@@ -179,4 +179,36 @@ __global__ void __launch_bounds__(256) rss_partial_kernel(const double* __restri
     }
 }
 
+// class[i] = 0 if some reference point lies within d1 of point i, 1 if within d2 (but none within d1),
+// 2 otherwise: Dataset.separate_points_distance_allSets, pybmc/data.py:194-245 (the O(N R) Python double
+// loop with one np.linalg.norm per pair).  Distances are sqrt(sum of squares) in fp64, compared with <=
+// exactly as the reference does.  Reference points are staged through shared memory in tiles.
+__global__ void __launch_bounds__(256) nearest_class_kernel(const double* __restrict__ pts, long long n,
+                                                            const double* __restrict__ refs, long long r, int dim,
+                                                            double d1, double d2, int* __restrict__ cls) {
+    extern __shared__ double tile[];                         // [tile_refs][dim]
+    const int tile_refs = 1024 / dim > 0 ? 1024 / dim : 1;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool in1 = false, in2 = false;
+    for (long long r0 = 0; r0 < r; r0 += tile_refs) {
+        const int cnt = static_cast<int>(min(static_cast<long long>(tile_refs), r - r0));
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt * dim; t += blockDim.x) tile[t] = refs[r0 * dim + t];
+        __syncthreads();
+        if (i < n && !in1) {
+            for (int j = 0; j < cnt; ++j) {
+                double s = 0.0;
+                for (int c = 0; c < dim; ++c) {
+                    const double diff = pts[i * dim + c] - tile[j * dim + c];
+                    s += diff * diff;
+                }
+                const double dist = sqrt(s);
+                in1 = in1 || dist <= d1;
+                in2 = in2 || dist <= d2;
+            }
+        }
+    }
+    if (i < n) cls[i] = in1 ? 0 : (in2 ? 1 : 2);
+}
+
 }  // namespace bmc

@@ -120,6 +120,15 @@ def main():
     cov_odd = coverage([1, 33, 68, 95, 99], mat[:137], pd.DataFrame({"t": tr}), "t")
     save("coverage_ties", matrix=mat, truth=tr, coverage=np.array(cov_ties), coverage_odd=np.array(cov_odd))
 
+    # -- inside_to_outside split (data.py:194-245) -------------------------------------------------
+    from pybmc.data import Dataset
+    g2 = np.random.default_rng(31)
+    pts = [tuple(map(float, p)) for p in g2.integers(0, 40, size=(300, 2))]
+    stable = [tuple(map(float, p)) for p in g2.integers(10, 30, size=(12, 2))]
+    tr, va, te = Dataset().separate_points_distance_allSets(pts, stable, 3.0, 7.5)
+    save("split_distance", points=np.array(pts), stable=np.array(stable), train=np.array(tr), val=np.array(va),
+         test=np.array(te))
+
     # -- whole class pipeline (bmc.py:79-376) -----------------------------------------------
     pipe = BayesianModelCombination(models, {"BE": frame}, "truth")
     pipe.orthogonalize("BE", train, 3)

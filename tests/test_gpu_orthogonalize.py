@@ -85,3 +85,22 @@ def test_device_sufficient_statistics():
     for s2 in (1e-6, 0.02, 3.7):                                   # the reference's covariance, :41
         ref = np.linalg.inv(X.T @ X / s2 + lam + np.eye(5) * 1e-6)
         np.testing.assert_allclose((s.w / (s.d / s2 + 1.0)) @ s.w.T, ref, rtol=1e-10)
+
+
+def test_distance_split_matches_reference(golden):
+    """Dataset.separate_points_distance_allSets (pybmc/data.py:194-245) on the device: same three index
+    lists as the reference produced, and as the oracle gives on non-integer coordinates in 3-D."""
+    import pandas as pd
+    from pybmc_b200.data_utils import separate_points_distance_allSets, split_inside_to_outside
+    g = golden("split_distance")
+    pts = [tuple(p) for p in g["points"]]
+    stable = [tuple(p) for p in g["stable"]]
+    tr, va, te = separate_points_distance_allSets(pts, stable, 3.0, 7.5)
+    assert tr == list(g["train"]) and va == list(g["val"]) and te == list(g["test"])
+    rng = np.random.default_rng(4)
+    p3, r3 = rng.normal(size=(5000, 3)) * 4, rng.normal(size=(1500, 3))
+    assert separate_points_distance_allSets(p3, r3, 0.8, 2.5) == tuple(oc.distance_classes(p3, r3, 0.8, 2.5))
+    assert separate_points_distance_allSets([], stable, 1.0, 2.0) == ([], [], [])
+    frame = pd.DataFrame(g["points"], columns=["N", "Z"])
+    a, b, c = split_inside_to_outside(frame, stable, 3.0, 7.5)
+    assert list(a.index) == list(g["train"]) and list(b.index) == list(g["val"]) and list(c.index) == list(g["test"])

@@ -133,3 +133,10 @@ def test_simultaneous_diagonalisation_matches_reference_covariance():
         ref = np.linalg.inv(gram / s2 + lam + np.eye(4) * oc.RIDGE)   # inference_utils.py:41
         mine = (w / (d / s2 + 1.0)) @ w.T
         assert np.allclose(mine, ref, rtol=1e-11, atol=0)
+
+
+def test_distance_split(golden):
+    g = golden("split_distance")
+    tr, va, te = oc.distance_classes(g["points"], g["stable"], 3.0, 7.5)
+    assert tr == list(g["train"]) and va == list(g["val"]) and te == list(g["test"])
+    assert len(tr) and len(va) and len(te) and sorted(tr + va + te) == list(range(300))
