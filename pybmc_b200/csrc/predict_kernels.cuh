@@ -81,6 +81,59 @@ struct PredictArgs {
     int s_splits;             // gridDim.y
 };
 
+// One (draw, window) step: below += (x < lo);  hits |= bit when lo <= x < hi.  Written as two compares
+// and two predicated integer ops (the compiler's select + add form costs one instruction more, and this
+// runs 4 x NQ times per step).
+template <typename real>
+__device__ __forceinline__ void window_step(real x, real lo, real hi, unsigned int& below, unsigned int& hits,
+                                            unsigned int bit);
+template <>
+__device__ __forceinline__ void window_step<float>(float x, float lo, float hi, unsigned int& below,
+                                                   unsigned int& hits, unsigned int bit) {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.lt.f32 p, %2, %3;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t"
+        "setp.lt.and.f32 q, %2, %4, !p;\n\t"
+        "@q or.b32 %1, %1, %5;\n\t}"
+        : "+r"(below), "+r"(hits)
+        : "f"(x), "f"(lo), "f"(hi), "r"(bit));
+}
+template <>
+__device__ __forceinline__ void window_step<double>(double x, double lo, double hi, unsigned int& below,
+                                                    unsigned int& hits, unsigned int bit) {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.lt.f64 p, %2, %3;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t"
+        "setp.lt.and.f64 q, %2, %4, !p;\n\t"
+        "@q or.b32 %1, %1, %5;\n\t}"
+        : "+r"(below), "+r"(hits)
+        : "d"(x), "d"(lo), "d"(hi), "r"(bit));
+}
+
+// nlt += (x < t); nle += (x <= t): the two order counts of the coverage rule, predicated adds again
+template <typename real>
+__device__ __forceinline__ void count_step(real x, real t, unsigned int& nlt, unsigned int& nle);
+template <>
+__device__ __forceinline__ void count_step<float>(float x, float t, unsigned int& nlt, unsigned int& nle) {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.lt.f32 p, %2, %3;\n\t"
+        "setp.le.f32 q, %2, %3;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t"
+        "@q add.u32 %1, %1, 1;\n\t}"
+        : "+r"(nlt), "+r"(nle)
+        : "f"(x), "f"(t));
+}
+template <>
+__device__ __forceinline__ void count_step<double>(double x, double t, unsigned int& nlt, unsigned int& nle) {
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.lt.f64 p, %2, %3;\n\t"
+        "setp.le.f64 q, %2, %3;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t"
+        "@q add.u32 %1, %1, 1;\n\t}"
+        : "+r"(nlt), "+r"(nle)
+        : "d"(x), "d"(t));
+}
+
 // ----------------------------------------------------------------------------------------------
 // The pass kernel: lane <-> nucleus, four posterior draws per step (one Philox call = the four
 // normals of this nucleus for draws 4i .. 4i+3), the draws' rows broadcast from a TMA-staged tile.
@@ -201,8 +254,7 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
                     const real dv = valid ? x[r] - ctr : real(0);
                     sx += dv;
                     sxx = M::fma(dv, dv, sxx);
-                    nlt += x[r] < tc ? 1u : 0u;
-                    nle += x[r] <= tc ? 1u : 0u;
+                    count_step<real>(x[r], tc, nlt, nle);
                     if (a.draws_out && valid && live)
                         a.draws_out[(s + r) * a.ld_out + n] = static_cast<double>(x[r]) + mu_d;
                 }
@@ -213,9 +265,7 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
             for (int r = 0; r < 4; ++r) {
 #pragma unroll
                 for (int j = 0; j < NQ; ++j) {
-                    const bool b = x[r] < wlo[j];
-                    below[j] += b ? 1u : 0u;
-                    if (!b && x[r] < whi[j]) hits |= 1u << (r * NQ + j);
+                    window_step<real>(x[r], wlo[j], whi[j], below[j], hits, 1u << (r * NQ + j));
                 }
             }
             while (hits) {                                  // rare per lane: store the draw, count it
