@@ -58,9 +58,8 @@ struct Math<float> {
         float l2, rad, sn, cs;
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u01(ra)));                       // <= 0
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(l2 * -1.3862943611198906f));   // sqrt(-2 ln u)
-        float t = u01(rb);
-        t -= rintf(t);                                             // [-1/2, 1/2]: same angle mod 2 pi
-        const float ang = t * 6.283185307179586f;
+        // angle in [0, 2 pi): inside the range where sin/cos.approx keep their 2^-20.9 absolute error
+        const float ang = u01(rb) * 6.283185307179586f;
         asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
         asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
         za = rad * cs;
