@@ -27,21 +27,40 @@ struct Philox4 {
     uint32_t x, y, z, w;
 };
 
+// Round keys of Philox-4x32-10: key + r * Weyl constant.  They only depend on the seed, so a kernel
+// builds them once (they live in uniform registers) instead of re-deriving them in every call.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+__device__ __forceinline__ PhiloxKeys philox_keys(uint32_t key0, uint32_t key1) {
+    PhiloxKeys ks;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        ks.k0[r] = key0 + static_cast<uint32_t>(r) * kPhiloxW0;
+        ks.k1[r] = key1 + static_cast<uint32_t>(r) * kPhiloxW1;
+    }
+    return ks;
+}
+
 // Philox-4x32, ten rounds (Salmon et al., SC'11).  Two IMAD.WIDE + two LOP3 per round.
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                 uint32_t k0, uint32_t k1) {
+                                                 const PhiloxKeys& ks) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint64_t p0 = static_cast<uint64_t>(kPhiloxM0) * c0;
         const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;
-        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ (k0 + static_cast<uint32_t>(r) * kPhiloxW0);
-        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ (k1 + static_cast<uint32_t>(r) * kPhiloxW1);
+        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ ks.k0[r];
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ ks.k1[r];
         c1 = static_cast<uint32_t>(p1);
         c3 = static_cast<uint32_t>(p0);
         c0 = n0;
         c2 = n2;
     }
     return Philox4{c0, c1, c2, c3};
+}
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+    return philox4x32_10(c0, c1, c2, c3, philox_keys(k0, k1));
 }
 
 template <typename real>
@@ -105,12 +124,17 @@ struct Math<double> {
     static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
 };
 
+template <typename real, typename Key>
+__device__ __forceinline__ void normals4_k(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const Key& ks,
+                                           real (&z)[4]) {
+    const Philox4 r = philox4x32_10(c0, c1, c2, c3, ks);
+    Math<real>::box_muller(r.x, r.y, z[0], z[1]);
+    Math<real>::box_muller(r.z, r.w, z[2], z[3]);
+}
 template <typename real>
 __device__ __forceinline__ void normals4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                          uint32_t k1, real (&z)[4]) {
-    const Philox4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
-    Math<real>::box_muller(r.x, r.y, z[0], z[1]);
-    Math<real>::box_muller(r.z, r.w, z[2], z[3]);
+    normals4_k<real>(c0, c1, c2, c3, philox_keys(k0, k1), z);
 }
 
 // Gamma(shape, 1): Marsaglia & Tsang (2000).  shape >= 1 is the sampler's case
@@ -141,9 +165,9 @@ __host__ __device__ inline GammaConst<real> make_gamma_const(double shape) {
 // One Marsaglia-Tsang attempt from Philox block kBlockGamma + t; returns true when accepted.
 template <typename real>
 __device__ __forceinline__ bool gamma_attempt(const GammaConst<real>& g, uint32_t it, uint32_t t, uint32_t chain,
-                                              uint32_t tag, uint32_t k0, uint32_t k1, real& v, Philox4& r) {
+                                              uint32_t tag, const PhiloxKeys& ks, real& v, Philox4& r) {
     using M = Math<real>;
-    r = philox4x32_10(it, kBlockGamma + t, chain, tag, k0, k1);
+    r = philox4x32_10(it, kBlockGamma + t, chain, tag, ks);
     real x, unused;
     M::box_muller(r.x, r.y, x, unused);
     v = M::fma(g.c, x, real(1));
@@ -158,25 +182,33 @@ __device__ __forceinline__ bool gamma_attempt(const GammaConst<real>& g, uint32_
     return M::log(u) < real(0.5) * x2 + g.d * (real(1) - v + M::log(v));
 }
 
+// rejections are rare (< 1 % for the sampler's shapes): out of line, keys rebuilt from the seed
 template <typename real>
 __device__ __noinline__ void gamma_retry(const GammaConst<real>& g, uint32_t it, uint32_t chain, uint32_t tag,
                                          uint32_t k0, uint32_t k1, real& v, Philox4& r) {
+    const PhiloxKeys ks = philox_keys(k0, k1);
     for (uint32_t t = 1; t < static_cast<uint32_t>(kGammaMaxAttempts); ++t)
-        if (gamma_attempt<real>(g, it, t, chain, tag, k0, k1, v, r)) return;
+        if (gamma_attempt<real>(g, it, t, chain, tag, ks, v, r)) return;
 }
 
-// Gamma(shape, 1).  The first attempt is inlined in the caller's instruction stream (it is accepted
-// with probability > 0.99 for the sampler's shapes); rejections take the out-of-line retry loop.
+// Gamma(shape, 1).  The first attempt is inlined in the caller's instruction stream; rejections take
+// the out-of-line retry loop.
 template <typename real>
 __device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
-                                                 uint32_t tag, uint32_t k0, uint32_t k1) {
+                                                 uint32_t tag, const PhiloxKeys& ks) {
     using M = Math<real>;
     real v;
     Philox4 r;
-    if (!gamma_attempt<real>(g, it, 0u, chain, tag, k0, k1, v, r)) gamma_retry<real>(g, it, chain, tag, k0, k1, v, r);
+    if (!gamma_attempt<real>(g, it, 0u, chain, tag, ks, v, r))
+        gamma_retry<real>(g, it, chain, tag, ks.k0[0], ks.k1[0], v, r);
     real out = g.d * v;
     if (g.boost) out *= M::pow(M::u01(r.w), g.inv_shape);
     return out;
+}
+template <typename real>
+__device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
+                                                 uint32_t tag, uint32_t k0, uint32_t k1) {
+    return gamma_unit_scale<real>(g, it, chain, tag, philox_keys(k0, k1));
 }
 
 }  // namespace bmc
