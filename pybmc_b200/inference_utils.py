@@ -195,7 +195,10 @@ class ConjugateSampler:
         if iterations < 0 or n_chains < 1 or thin < 1 or discard < 0:
             raise ValueError("iterations >= 0, n_chains >= 1, thin >= 1 and discard >= 0 are required")
         kp = lib.bmc_padded_components(self.k)
-        mode = {"auto": _lib.STATS_FULL if self.k <= 16 else _lib.STATS_DIAG, "full": _lib.STATS_FULL,
+        # "auto": all cross moments while they fit in registers (K <= 8: 45 sums), marginal moments beyond
+        # (K = 16 would need 153 sums per thread and runs 2.3x slower, profiles/k_sweep.py); "full" is
+        # available on request up to K = 16
+        mode = {"auto": _lib.STATS_FULL if self.k <= 8 else _lib.STATS_DIAG, "full": _lib.STATS_FULL,
                 "diag": _lib.STATS_DIAG, "none": _lib.STATS_NONE, None: _lib.STATS_NONE}[stats]
         n_kept = max(0, -(-(iterations - discard) // thin)) if keep_samples else 0
         samples = (torch.empty((n_kept, self.k + 1, n_chains), dtype=tdt, device=self.dev)
@@ -238,13 +241,19 @@ def _rhat(cstats, comp, second, jac_d, chain_mean_d, iterations):
         return None
     d = len(comp)
     idx = [[second.get((min(a, b), max(a, b))) for b in comp] for a in comp]
-    if any(i is None for row in idx for i in row):
-        return None
-    flat = torch.tensor([i for row in idx for i in row], device=cstats.device)
-    m2 = cstats[flat, :].t().reshape(n_chains, d, d) / float(iterations)          # E[e e'] per chain
     m1 = cstats[comp, :].t() / float(iterations)
-    cov_e = m2 - m1[:, :, None] * m1[:, None, :]
-    var_b = torch.einsum("ra,cab,rb->cr", jac_d, cov_e, jac_d) * (iterations / (iterations - 1.0))
+    if any(i is None for row in idx for i in row):
+        # diagonal moments only: enough when the coordinates are not rotated (diagonal W)
+        if bool((jac_d - torch.diag(torch.diagonal(jac_d))).abs().max() > 0):
+            return None
+        diag_rows = torch.tensor([second[(a, a)] for a in comp], device=cstats.device)
+        var_e = cstats[diag_rows, :].t() / float(iterations) - m1 * m1
+        var_b = var_e * torch.diagonal(jac_d)[None, :] ** 2 * (iterations / (iterations - 1.0))
+    else:
+        flat = torch.tensor([i for row in idx for i in row], device=cstats.device)
+        m2 = cstats[flat, :].t().reshape(n_chains, d, d) / float(iterations)      # E[e e'] per chain
+        cov_e = m2 - m1[:, :, None] * m1[:, None, :]
+        var_b = torch.einsum("ra,cab,rb->cr", jac_d, cov_e, jac_d) * (iterations / (iterations - 1.0))
     w = var_b.mean(dim=0)
     b_over_n = chain_mean_d.var(dim=0, unbiased=True)
     rhat = torch.sqrt(((iterations - 1.0) / iterations * w + b_over_n) / w)
@@ -333,7 +342,7 @@ class SimplexSampler:
         tdt, code = D.resolve_dtype(dtype)
         iterations, burn, n_chains, thin = int(iterations), int(burn), int(n_chains), int(thin)
         kp = lib.bmc_padded_components(self.k)
-        mode = {"auto": _lib.STATS_FULL if self.k <= 16 else _lib.STATS_DIAG, "full": _lib.STATS_FULL,
+        mode = {"auto": _lib.STATS_FULL if self.k <= 8 else _lib.STATS_DIAG, "full": _lib.STATS_FULL,
                 "diag": _lib.STATS_DIAG, "none": _lib.STATS_NONE, None: _lib.STATS_NONE}[stats]
         n_kept = -(-iterations // thin) if keep_samples else 0
         samples = (torch.empty((n_kept, self.k + 1, n_chains), dtype=tdt, device=self.dev)
