@@ -19,7 +19,10 @@ Stream layout (DESIGN.md "RNG contract"):
   counter  = (c0, c1, c2, c3)
      sampler : c0 = iteration index, c1 = block, c2 = global chain id, c3 = tag
                block j < 0x10000   -> normals 4j .. 4j+3 of the K-vector draw
-               block 0x10000 + t   -> Marsaglia-Tsang attempt t of the gamma draw
+               block 0x10000       -> first Marsaglia-Tsang proposal of iterations 2m AND 2m+1 (counter
+                                      c0 = 2m): even iteration = cosine branch + word 2, odd = sine branch + word 3
+               block 0x10000 + t   -> attempt t >= 1 of the gamma draw of iteration c0 (after a rejection)
+               block 0x18000       -> boost uniform for shapes < 1
                block 0x20000       -> Metropolis uniform (simplex sampler only)
      noise   : c0 = posterior-draw index s >> 2, c1 = global nucleus index, c2 = 0, c3 = tag
                -> 4 normals for draws 4*(s>>2) .. 4*(s>>2)+3 of that nucleus
@@ -86,11 +89,16 @@ def normal_vector(k, it, chain, tag, key):
     return out[:k]
 
 
-def gamma_unit_scale(shape, it, chain, tag, key):
-    """Gamma(shape, 1) by Marsaglia & Tsang (2000), one Philox block per attempt.
+BLOCK_BOOST = BLOCK_GAMMA + 0x8000
 
-    For shape < 1 the usual boost Gamma(a) = Gamma(a+1) * U^(1/a) is applied with
-    the fourth word of the accepted attempt.
+
+def gamma_unit_scale(shape, it, chain, tag, key):
+    """Gamma(shape, 1) by Marsaglia & Tsang (2000).
+
+    The first proposals of iterations 2m and 2m+1 share Philox block (2m, BLOCK_GAMMA): the even
+    iteration uses the cosine branch of its Box-Muller pair and word 2 as the uniform, the odd one the
+    sine branch and word 3.  Attempt t >= 1 (after a rejection) has block (it, BLOCK_GAMMA + t).  For
+    shape < 1 the usual boost Gamma(a) = Gamma(a+1) * U^(1/a) takes U from block (it, BLOCK_BOOST).
     """
     a = float(shape)
     boost = a < 1.0
@@ -98,17 +106,22 @@ def gamma_unit_scale(shape, it, chain, tag, key):
         a += 1.0
     d = a - 1.0 / 3.0
     c = 1.0 / math.sqrt(9.0 * d)
+    odd = it & 1
     v = 1.0
-    r = (0, 0, 0, 0)
     for t in range(GAMMA_MAX_ATTEMPTS):
-        r = philox4x32_10((it, BLOCK_GAMMA + t, chain, tag), key)
-        x, _ = box_muller(r[0], r[1])
+        if t == 0:
+            r = philox4x32_10((it - odd, BLOCK_GAMMA, chain, tag), key)
+            x = box_muller(r[0], r[1])[odd]
+            u = u01(r[2 + odd])
+        else:
+            r = philox4x32_10((it, BLOCK_GAMMA + t, chain, tag), key)
+            x = box_muller(r[0], r[1])[0]
+            u = u01(r[2])
         v = 1.0 + c * x
         if v <= 0.0:
             v = 1.0
             continue
         v = v * v * v
-        u = u01(r[2])
         x2 = x * x
         if u < 1.0 - 0.0331 * x2 * x2:
             break
@@ -116,7 +129,7 @@ def gamma_unit_scale(shape, it, chain, tag, key):
             break
     g = d * v
     if boost:
-        g *= u01(r[3]) ** (1.0 / float(shape))
+        g *= u01(philox4x32_10((it, BLOCK_BOOST, chain, tag), key)[0]) ** (1.0 / float(shape))
     return g
 
 

@@ -80,8 +80,13 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     long long next_store = a.samples ? a.store_from : -1;
     long long slot = 0;
 
+    GammaPair<real> gp;                                 // first Gamma proposals of iterations 2m, 2m+1
+    gp.x[1] = real(0);
+    gp.u[1] = real(1);
     for (long long it = 0; it < a.iterations; ++it) {
         const uint32_t it32 = static_cast<uint32_t>(it);
+        const bool odd = (it32 & 1u) != 0u;
+        if (!odd) gp = gamma_pair<real>(it32, chain, kTagGibbs, philox_keys(a.key0, a.key1));   // every other iteration
         real e[KP];
         real rss0 = rss_min, rss1 = real(0);
 #pragma unroll
@@ -101,7 +106,8 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
             }
         }
         const real scale = real(0.5) * (prior_scale + (rss0 + rss1));
-        const real gm = gamma_unit_scale<real>(gc, it32, chain, kTagGibbs, a.key0, a.key1);
+        const real gm = gamma_from_first<real>(gc, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0], it32, chain,
+                                              kTagGibbs, a.key0, a.key1);
         s2 = M::div(scale, gm);
         s2 = s2 > real(1e-6) ? s2 : real(1e-6);
         sig = M::sqrt(s2);

@@ -162,53 +162,77 @@ __host__ __device__ inline GammaConst<real> make_gamma_const(double shape) {
     return g;
 }
 
-// One Marsaglia-Tsang attempt from Philox block kBlockGamma + t; returns true when accepted.
+// ---- Gamma(shape, 1) by Marsaglia & Tsang (2000) -------------------------------------------------
+// Variates used: a standard normal x and a uniform u per attempt.  The FIRST attempts of iterations
+// 2m and 2m+1 share one Philox block, (2m, kBlockGamma): the even iteration takes the cosine branch of
+// the Box-Muller pair and word z, the odd one the sine branch and word w -- every bit of the block is
+// used, and a kernel that walks the iterations in order makes the call only every other iteration.
+// Later attempts t >= 1 (rejections: < 1 % for the sampler's shapes) have their own blocks
+// (it, kBlockGamma + t); the boost uniform of shapes < 1 has block (it, kBlockBoost).
+constexpr uint32_t kBlockBoost = kBlockGamma + 0x8000u;
+
 template <typename real>
-__device__ __forceinline__ bool gamma_attempt(const GammaConst<real>& g, uint32_t it, uint32_t t, uint32_t chain,
-                                              uint32_t tag, const PhiloxKeys& ks, real& v, Philox4& r) {
+struct GammaPair {
+    real x[2], u[2];
+};
+
+template <typename real, typename Key>
+__device__ __forceinline__ GammaPair<real> gamma_pair(uint32_t it_even, uint32_t chain, uint32_t tag, const Key& ks) {
+    const Philox4 r = philox4x32_10(it_even, kBlockGamma, chain, tag, ks);
+    GammaPair<real> p;
+    Math<real>::box_muller(r.x, r.y, p.x[0], p.x[1]);
+    p.u[0] = Math<real>::u01(r.z);
+    p.u[1] = Math<real>::u01(r.w);
+    return p;
+}
+
+// accept / reject one proposal; on acceptance v holds (1 + c x)^3
+template <typename real>
+__device__ __forceinline__ bool gamma_accept(const GammaConst<real>& g, real x, real u, real& v) {
     using M = Math<real>;
-    r = philox4x32_10(it, kBlockGamma + t, chain, tag, ks);
-    real x, unused;
-    M::box_muller(r.x, r.y, x, unused);
     v = M::fma(g.c, x, real(1));
     if (v <= real(0)) {
         v = real(1);
         return false;
     }
     v = v * v * v;
-    const real u = M::u01(r.z);
     const real x2 = x * x;
     if (u < real(1) - real(0.0331) * x2 * x2) return true;                 // squeeze: almost always
     return M::log(u) < real(0.5) * x2 + g.d * (real(1) - v + M::log(v));
 }
 
-// rejections are rare (< 1 % for the sampler's shapes): out of line, keys rebuilt from the seed
+// rejections are rare: out of line, keys rebuilt from the seed
 template <typename real>
 __device__ __noinline__ void gamma_retry(const GammaConst<real>& g, uint32_t it, uint32_t chain, uint32_t tag,
-                                         uint32_t k0, uint32_t k1, real& v, Philox4& r) {
+                                         uint32_t k0, uint32_t k1, real& v) {
     const PhiloxKeys ks = philox_keys(k0, k1);
-    for (uint32_t t = 1; t < static_cast<uint32_t>(kGammaMaxAttempts); ++t)
-        if (gamma_attempt<real>(g, it, t, chain, tag, ks, v, r)) return;
+    for (uint32_t t = 1; t < static_cast<uint32_t>(kGammaMaxAttempts); ++t) {
+        const Philox4 r = philox4x32_10(it, kBlockGamma + t, chain, tag, ks);
+        real x, unused;
+        Math<real>::box_muller(r.x, r.y, x, unused);
+        if (gamma_accept<real>(g, x, Math<real>::u01(r.z), v)) return;
+    }
 }
 
-// Gamma(shape, 1).  The first attempt is inlined in the caller's instruction stream; rejections take
-// the out-of-line retry loop.
+// finish a draw whose first proposal (x, u) is already known
 template <typename real>
-__device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
-                                                 uint32_t tag, const PhiloxKeys& ks) {
+__device__ __forceinline__ real gamma_from_first(const GammaConst<real>& g, real x, real u, uint32_t it,
+                                                 uint32_t chain, uint32_t tag, uint32_t k0, uint32_t k1) {
     using M = Math<real>;
     real v;
-    Philox4 r;
-    if (!gamma_attempt<real>(g, it, 0u, chain, tag, ks, v, r))
-        gamma_retry<real>(g, it, chain, tag, ks.k0[0], ks.k1[0], v, r);
+    if (!gamma_accept<real>(g, x, u, v)) gamma_retry<real>(g, it, chain, tag, k0, k1, v);
     real out = g.d * v;
-    if (g.boost) out *= M::pow(M::u01(r.w), g.inv_shape);
+    if (g.boost) out *= M::pow(M::u01(philox4x32_10(it, kBlockBoost, chain, tag, k0, k1).x), g.inv_shape);
     return out;
 }
+
+// stand-alone draw for iteration `it` (kernels that do not walk the iterations in order)
 template <typename real>
 __device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
                                                  uint32_t tag, uint32_t k0, uint32_t k1) {
-    return gamma_unit_scale<real>(g, it, chain, tag, philox_keys(k0, k1));
+    const GammaPair<real> p = gamma_pair<real>(it & ~1u, chain, tag, philox_keys(k0, k1));
+    const int odd = static_cast<int>(it & 1u);
+    return gamma_from_first<real>(g, odd ? p.x[1] : p.x[0], odd ? p.u[1] : p.u[0], it, chain, tag, k0, k1);
 }
 
 }  // namespace bmc
