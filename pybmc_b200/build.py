@@ -65,6 +65,11 @@ def build_library(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    for obj in objs:            # only the shared object needs to travel with the snapshot
+        try:
+            os.remove(obj)
+        except OSError:
+            pass
     return LIB
 
 

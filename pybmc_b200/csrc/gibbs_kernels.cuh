@@ -1,7 +1,9 @@
-// Batched samplers: one independent chain per thread, sufficient-statistic form.
+// Batched samplers in sufficient-statistic form.
 //
-//   gibbs_conjugate_kernel : pybmc/inference_utils.py:39-54 (gibbs_sampler hot loop)
-//   gibbs_simplex_kernel   : pybmc/inference_utils.py:97-141 (gibbs_sampler_simplex loops)
+//   gibbs_conjugate_kernel        one chain per thread   pybmc/inference_utils.py:39-54 (gibbs_sampler loop)
+//   gibbs_conjugate_group_kernel  eight lanes per chain  same loop, for fewer than 16,384 chains
+//   gibbs_simplex_kernel          one chain per thread   pybmc/inference_utils.py:97-141 (gibbs_sampler_simplex)
+//   gibbs_simplex_group_kernel    eight lanes per chain  same loops, for fewer than 16,384 chains
 //
 // The reference recomputes X'y, the residual y - X b and a K-by-K inverse in every
 // iteration.  Both are functions of b through K-sized statistics only:
