@@ -117,7 +117,7 @@ struct Math<double> {
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
-    static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+    static __device__ __forceinline__ double rsqrt(double x) { return ::rsqrt(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double div(double a, double b) { return a / b; }
     static __device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }
