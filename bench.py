@@ -567,6 +567,23 @@ def extras_config5(out, torch, dev, world, rank, timed, pb, steps, hbm_peak):
     out["config5_orthogonalize_f64"] = {"config": f"configs[4]: {n} x 256 fp64 rows per GPU, K=64", **res}
     del preds, xc
 
+    # prediction contraction at K = 64 (FP32 FMA pipe; the tcgen05 split-TF32 variant is not built yet)
+    from pybmc_b200.sampling_utils import PredictiveProblem
+    rng = np.random.default_rng(1005)
+    n_draws = 10000
+    lo, hi = rank * n, (rank + 1) * n
+    pr = rng.uniform(100, 2000, n)[:, None] + rng.normal(0, 3.0, (n, 80))
+    vt64 = rng.normal(size=(k, 80)) * 0.02
+    theta = np.column_stack([rng.normal(size=k)[None, :] + 0.1 * rng.normal(size=(n_draws, k)),
+                             np.abs(rng.normal(0.15, 0.01, n_draws))])
+    prob = PredictiveProblem(pr, theta, vt64, truth=pr.mean(axis=1), dtype="float32", device=dev, point0=lo)
+    ws = torch.empty(int(lib.bmc_predict_workspace_bytes(_lib.F32, n, 3, n_draws)), dtype=torch.uint8, device=dev)
+    ms = timed(lambda: prob.run(percentiles=[2.5, 50.0, 97.5], seed=SEED, as_numpy=False, workspace=ws), steps, 1)
+    out["config5_predict_f32"] = {"metric": "posterior_pred_samples_x_points_per_sec",
+                                  "value": float(n) * world * n_draws / (ms * 1e-3), "unit": "samples*points/s",
+                                  "ms_per_step": ms, "config": f"configs[4]: {n} nuclei per GPU x 10000 draws x K=64, "
+                                  "3 percentiles + coverage counts"}
+
 
 def _cpu_predict(args):
     os.environ["OMP_NUM_THREADS"] = "1"
