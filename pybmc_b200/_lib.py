@@ -63,6 +63,7 @@ SIGNATURES = {
                                      _p, _p]),
     "bmc_predict_workspace_bytes": (_sz, [_int, _i64, _int, _i64]),
     "bmc_predict_theta_stride": (_int, [_int]),
+    "bmc_predict_set_tensor_path": (None, [_int]),
     "bmc_predict_fused": (_int, [_int, C.POINTER(PredictProblem), _p, _p, _p, _p, _p, _p, _i64, _p, _sz,
                                  C.POINTER(_int), _p]),
     "bmc_coverage_counts": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),

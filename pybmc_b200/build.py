@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libbmc_b200.so")
 UNITS = ["linalg.cu", "gibbs.cu", "simplex.cu", "predict.cu", "literal.cu", "probe.cu"]
-HEADERS = ["common.h", "rng.cuh", "gibbs_kernels.cuh", "linalg_kernels.cuh", "predict_kernels.cuh",
+HEADERS = ["common.h", "rng.cuh", "gibbs_kernels.cuh", "linalg_kernels.cuh", "predict_kernels.cuh", "predict_tc_kernels.cuh",
            "literal_kernels.cuh", "tma.cuh", "select_logic.h", os.path.join("..", "..", "include", "bmc_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",

@@ -5,6 +5,7 @@
 #include <cstring>
 #include "common.h"
 #include "predict_kernels.cuh"
+#include "predict_tc_kernels.cuh"
 
 using namespace bmc;
 
@@ -36,6 +37,9 @@ double norm_ppf(double p) {
     return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
            (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
 }
+
+// 0 = automatic (tensor cores for fp32 with K > 16), 1 = FFMA contraction everywhere (A/B measurements, tests)
+int g_tensor_path_off = 0;
 
 struct QuantPlan {
     int nq;
@@ -80,10 +84,39 @@ int segment_len(double expected_total, int splits) {
 }
 
 struct PassShape {
-    int s_splits, seg_len, cand_stride, retry_splits;
+    int s_splits;       // sample slots of the first pass
+    int seg_len, cand_stride;
+    int retry_splits;   // sample slots of a retry pass
 };
 
-PassShape make_shape(long long n_points, long long n_draws, double expected) {
+// tensor-core pass: blocks of 128 nuclei, one block per SM, four slots per block
+PassShape make_shape_tc(long long n_points, long long n_draws, double expected) {
+    PassShape sh{};
+    const int tiles = static_cast<int>((n_draws + kTcTile - 1) / kTcTile);
+    const long long blocks_x = (n_points + kTcRows - 1) / kTcRows;
+    const int gy_max = std::max(1, std::min(tiles, kMaxSlots / kTcSlotsPerBlock));
+    int gy = 1;
+    double best = 0.0;
+    for (int g = 1; g <= gy_max; ++g) {          // fewest splits that fill whole waves of 148 blocks
+        const long long total = blocks_x * g;
+        const double eff = static_cast<double>(total) / static_cast<double>((total + 147) / 148 * 148);
+        if (eff > best + 1e-9) {
+            best = eff;
+            gy = g;
+        }
+        if (eff >= 0.92) break;
+    }
+    sh.s_splits = kTcSlotsPerBlock * gy;
+    sh.seg_len = segment_len(expected, sh.s_splits);
+    sh.cand_stride = (sh.s_splits * sh.seg_len + 3) / 4 * 4;
+    int rs = kTcSlotsPerBlock * std::max(1, std::min(4, tiles));
+    while (rs > kTcSlotsPerBlock && rs * segment_len(expected, rs) > sh.cand_stride) rs >>= 1;
+    sh.retry_splits = rs;
+    return sh;
+}
+
+PassShape make_shape(long long n_points, long long n_draws, double expected, bool tc = false) {
+    if (tc) return make_shape_tc(n_points, n_draws, expected);
     PassShape sh{};
     const int tiles = static_cast<int>((n_draws + kPredTile - 1) / kPredTile);
     const long long blocks_x = (n_points + kPredWarps * 32 - 1) / (kPredWarps * 32);
@@ -106,10 +139,10 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 struct Layout {
     // byte offsets inside the workspace for a chunk of nc nuclei
     size_t center, scale, win_lo, win_hi, brk_lo, brk_hi, pair_hi, aux, phase, cnt_below, cnt_slot, sub, resolved,
-        cand, mom, c_lt, c_le, flag, list_a, list_b, counter, plan, total;
+        cand, mom, c_lt, c_le, flag, list_a, list_b, counter, plan, image, total;
 };
 
-Layout make_layout(long long nc, int nq, int cand_stride, size_t sz) {
+Layout make_layout(long long nc, int nq, int cand_stride, size_t sz, size_t image_bytes = 0) {
     Layout l{};
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -140,6 +173,7 @@ Layout make_layout(long long nc, int nq, int cand_stride, size_t sz) {
     l.flag = take(nc * 4);
     l.list_a = take(nc * 4);
     l.list_b = take(nc * 4);
+    l.image = take(image_bytes);
     l.total = off;
     return l;
 }
@@ -173,22 +207,49 @@ int dispatch_nq(const PredictArgs& a, cudaStream_t st) {
 }
 
 
+template <int KP, int NQ>
+int launch_pass_tc(const PredictArgs& a, const unsigned char* image, cudaStream_t st) {
+    dim3 grid((a.n_active + kTcRows - 1) / kTcRows, a.s_splits / kTcSlotsPerBlock);
+    auto kern = predict_pass_tc_kernel<KP, NQ>;
+    BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcImage<KP>::kSmemBytes));
+    kern<<<grid, kTcThreads, TcImage<KP>::kSmemBytes, st>>>(a, image);
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+template <int KP>
+int dispatch_nq_tc(const PredictArgs& a, const unsigned char* image, cudaStream_t st) {
+    if (a.nq <= 3) return launch_pass_tc<KP, 3>(a, image, st);
+    if (a.nq <= 5) return launch_pass_tc<KP, 5>(a, image, st);
+    return launch_pass_tc<KP, 8>(a, image, st);
+}
+
 template <typename real>
 int run_predict(const bmc_predict_problem* p, double* mean, double* var, double* quant, int64_t* c_lt,
                 int64_t* c_le, double* draws_out, int64_t ld_out, void* workspace, size_t workspace_bytes,
                 int* passes_out, cudaStream_t st) {
     const size_t sz = sizeof(real);
     const QuantPlan plan = make_plan(p->probs, p->nq, p->n_draws);
+    const int kp = bmc_padded_components(p->k > 0 ? p->k : 1);
+    // wide bases in fp32: the contraction goes to the tensor cores (predict_tc_kernels.cuh)
+    const bool tc = sizeof(real) == 4 && p->theta && kp >= 32 && p->noise_mode != BMC_NOISE_EXTERNAL &&
+                    !g_tensor_path_off;
+    const long long tiles_tc = (p->n_draws + kTcTile - 1) / kTcTile;
+    const size_t image_bytes =
+        tc ? static_cast<size_t>(tiles_tc) * (kp == 32 ? TcImage<32>::kStride : TcImage<64>::kStride) : 0;
+    auto total_for = [&](long long n, const PassShape& sh) {
+        return make_layout(n, p->nq, sh.cand_stride, sz, image_bytes).total;
+    };
     // largest chunk of nuclei the workspace can hold (the shape depends on the chunk size)
     long long nc = std::min<long long>(p->n_points, kChunkPoints);
-    PassShape shape = make_shape(nc, p->n_draws, plan.max_expected);
-    while (nc > 32 && make_layout(nc, p->nq, shape.cand_stride, sz).total > workspace_bytes) {
+    PassShape shape = make_shape(nc, p->n_draws, plan.max_expected, tc);
+    while (nc > 32 && total_for(nc, shape) > workspace_bytes) {
         nc = std::max<long long>(32, nc / 2);
-        shape = make_shape(nc, p->n_draws, plan.max_expected);
+        shape = make_shape(nc, p->n_draws, plan.max_expected, tc);
     }
-    if (make_layout(nc, p->nq, shape.cand_stride, sz).total > workspace_bytes) {
+    if (total_for(nc, shape) > workspace_bytes) {
         set_error("bmc_predict_fused: workspace of %zu bytes is too small (need %zu for %lld nuclei)",
-                  workspace_bytes, make_layout(nc, p->nq, shape.cand_stride, sz).total, nc);
+                  workspace_bytes, total_for(nc, shape), nc);
         return BMC_ERR_WORKSPACE;
     }
     // equal chunks (a short last chunk would run at a fraction of the machine)
@@ -196,11 +257,14 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         const long long n_chunks = (p->n_points + nc - 1) / nc;
         const long long even = ((p->n_points + n_chunks - 1) / n_chunks + 255) / 256 * 256;
         if (even < nc) {
-            nc = even;
-            shape = make_shape(nc, p->n_draws, plan.max_expected);
+            const PassShape es = make_shape(even, p->n_draws, plan.max_expected, tc);
+            if (total_for(even, es) <= workspace_bytes) {
+                nc = even;
+                shape = es;
+            }
         }
     }
-    const Layout lay = make_layout(nc, p->nq, shape.cand_stride, sz);
+    const Layout lay = make_layout(nc, p->nq, shape.cand_stride, sz, image_bytes);
     if (lay.total > workspace_bytes) {
         set_error("bmc_predict_fused: workspace of %zu bytes is too small (need %zu)", workspace_bytes, lay.total);
         return BMC_ERR_WORKSPACE;
@@ -219,8 +283,18 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
     BMC_CUDA(cudaStreamSynchronize(st));   // the plan lives on this stack frame
 
     auto select_kern = predict_select_kernel<real>;
-    const int kp = bmc_padded_components(p->k > 0 ? p->k : 1);
-    const int tiles = static_cast<int>((p->n_draws + kPredTile - 1) / kPredTile);
+    const int tiles = tc ? static_cast<int>(tiles_tc) * kTcSlotsPerBlock
+                         : static_cast<int>((p->n_draws + kPredTile - 1) / kPredTile);
+    const unsigned char* image = tc ? ws + lay.image : nullptr;
+    if (tc) {
+        if (kp == 32)
+            theta_image_kernel<32><<<static_cast<unsigned>(tiles_tc), 256, 0, st>>>(
+                static_cast<const float*>(p->theta), p->n_draws, ws + lay.image);
+        else
+            theta_image_kernel<64><<<static_cast<unsigned>(tiles_tc), 256, 0, st>>>(
+                static_cast<const float*>(p->theta), p->n_draws, ws + lay.image);
+        BMC_LAUNCH_CHECK();
+    }
 
     int max_passes = 0;
     for (long long c0 = 0; c0 < p->n_points; c0 += nc) {
@@ -251,7 +325,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         BMC_LAUNCH_CHECK();
 
         // the first pass of a short last chunk may use more sample splits than the full-size chunk
-        PassShape cs = make_shape(n, p->n_draws, plan.max_expected);
+        PassShape cs = make_shape(n, p->n_draws, plan.max_expected, tc);
         if (cs.cand_stride > shape.cand_stride) cs = shape;
         if (cs.s_splits * segment_len(plan.max_expected, cs.s_splits) > shape.cand_stride) cs = shape;
 
@@ -337,12 +411,16 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         for (;;) {
             ++pass;
             int rc = BMC_OK;
-            switch (kp) {
-                case 4: rc = dispatch_nq<real, 4>(a, st); break;
-                case 8: rc = dispatch_nq<real, 8>(a, st); break;
-                case 16: rc = dispatch_nq<real, 16>(a, st); break;
-                case 32: rc = dispatch_nq<real, 32>(a, st); break;
-                default: rc = dispatch_nq<real, 64>(a, st); break;
+            if (tc) {
+                rc = kp == 32 ? dispatch_nq_tc<32>(a, image, st) : dispatch_nq_tc<64>(a, image, st);
+            } else {
+                switch (kp) {
+                    case 4: rc = dispatch_nq<real, 4>(a, st); break;
+                    case 8: rc = dispatch_nq<real, 8>(a, st); break;
+                    case 16: rc = dispatch_nq<real, 16>(a, st); break;
+                    case 32: rc = dispatch_nq<real, 32>(a, st); break;
+                    default: rc = dispatch_nq<real, 64>(a, st); break;
+                }
             }
             if (rc != BMC_OK) return rc;
             const long long items = static_cast<long long>(s.n_active) * p->nq;
@@ -394,8 +472,17 @@ size_t bmc_predict_workspace_bytes(int dtype, int64_t n_points, int nq, int64_t 
     // chunks of 32768 nuclei keep the candidate buffers in the hundreds of MB
     const long long nc = std::min<long long>(n_points, kChunkPoints);
     const PassShape shape = make_shape(nc, n_draws, plan.max_expected);
-    return make_layout(nc, nq, shape.cand_stride, sz).total;
+    size_t need = make_layout(nc, nq, shape.cand_stride, sz).total;
+    if (dtype == BMC_F32) {
+        // room for the tensor-core path (K > 16): its slot layout and the operand image of the draws
+        const PassShape ts = make_shape(nc, n_draws, plan.max_expected, true);
+        const size_t image = static_cast<size_t>((n_draws + kTcTile - 1) / kTcTile) * TcImage<64>::kStride;
+        need = std::max(need, make_layout(nc, nq, ts.cand_stride, sz, image).total);
+    }
+    return need;
 }
+
+void bmc_predict_set_tensor_path(int enabled) { g_tensor_path_off = enabled ? 0 : 1; }
 
 int bmc_predict_theta_stride(int k) { return bmc_padded_components(k > 0 ? k : 1) + 4; }
 

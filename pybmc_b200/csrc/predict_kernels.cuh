@@ -17,9 +17,10 @@
 // normal approximation; a miss or an overflow re-centres the window from the counts and repeats the
 // pass for the affected nuclei only, so the result is exact for any distribution.
 //
-// Work layout: lane <-> posterior draw, warp <-> quad of 4 consecutive nuclei (one Philox call gives
-// the quad's four normals), block = 8 warps sharing one TMA-staged tile of the transposed sample
-// matrix thetaT[K+1][S] in shared memory.
+// Work layout: lane <-> nucleus, four posterior draws per step (one Philox call gives the four normals
+// of a nucleus for draws 4i .. 4i+3).  K <= 16 (and fp64): the contraction is an FFMA chain over rows
+// broadcast from a TMA-staged tile (predict_pass_kernel).  fp32 with K > 16: the contraction runs on
+// the tensor cores (predict_tc_kernels.cuh) and the same per-lane consumer reads it back from TMEM.
 #pragma once
 #include <cfloat>
 #include "rng.cuh"
@@ -134,6 +135,115 @@ __device__ __forceinline__ void count_step<double>(double x, double t, unsigned 
         : "d"(x), "d"(t));
 }
 
+// What one lane (= one nucleus) accumulates over its draws, and the step that folds four draws in.
+// Shared by the FFMA pass kernel below and the tensor-core pass kernel so both count identically.
+template <typename real, int NQ>
+struct LaneAcc {
+    real wlo[NQ], whi[NQ];
+    unsigned int below[NQ], inwin[NQ];
+    real sx, sxx;
+    unsigned int nlt, nle;
+};
+
+struct LaneCtx {
+    int n, idx0, slot;
+    bool live;
+    unsigned int seg;
+    double mu_d;
+};
+
+template <typename real, int NQ>
+__device__ __forceinline__ void lane_init(const PredictArgs& a, const LaneCtx& c, LaneAcc<real, NQ>& st) {
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+        const bool on = c.live && j < a.nq;
+        st.wlo[j] = on ? static_cast<const real*>(a.win_lo)[c.idx0 + j] : real(FLT_MAX);
+        st.whi[j] = on ? static_cast<const real*>(a.win_hi)[c.idx0 + j] : real(FLT_MAX);
+        st.below[j] = 0u;
+        st.inwin[j] = 0u;
+    }
+    st.sx = real(0);
+    st.sxx = real(0);
+    st.nlt = 0u;
+    st.nle = 0u;
+}
+
+// x[0..3] are draws s .. s+3 of nucleus c.n (FLT_MAX = no such draw)
+template <typename real, int NQ>
+__device__ __forceinline__ void consume4(const PredictArgs& a, const LaneCtx& c, LaneAcc<real, NQ>& st,
+                                         const real (&x)[4], long long s, real tc, real ctr) {
+    using M = Math<real>;
+    if (a.first) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const bool valid = x[r] < real(FLT_MAX);
+            const real dv = valid ? x[r] - ctr : real(0);
+            st.sx += dv;
+            st.sxx = M::fma(dv, dv, st.sxx);
+            count_step<real>(x[r], tc, st.nlt, st.nle);
+            if (a.draws_out && valid && c.live)
+                a.draws_out[(s + r) * a.ld_out + c.n] = static_cast<double>(x[r]) + c.mu_d;
+        }
+    }
+    // windows: two compares and a predicated add per (draw, window); hits only set a bit
+    unsigned int hits = 0u;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+            window_step<real>(x[r], st.wlo[j], st.whi[j], st.below[j], hits, 1u << (r * NQ + j));
+        }
+    }
+    while (hits) {                                  // rare per lane: store the draw, count it
+        const int bit = __ffs(hits) - 1;
+        hits &= hits - 1u;
+        const int r = bit / NQ, j = bit - r * NQ;
+        const real xv = r == 0 ? x[0] : (r == 1 ? x[1] : (r == 2 ? x[2] : x[3]));
+        unsigned int have = 0u;
+        real lo_j = real(0), hi_j = real(1);
+#pragma unroll
+        for (int jj = 0; jj < NQ; ++jj) {
+            if (jj == j) {
+                have = st.inwin[jj];
+                st.inwin[jj] = have + 1u;
+                lo_j = st.wlo[jj];
+                hi_j = st.whi[jj];
+            }
+        }
+        if (have < c.seg)
+            static_cast<real*>(a.cand)[static_cast<long long>(c.idx0 + j) * a.cand_stride + c.slot * c.seg + have] = xv;
+        if (a.count_slices) {
+            // which 1/32 slice of the window: lets an overflowing window be narrowed with exact
+            // counts whatever the distribution (atoms, gaps, heavy tails)
+            const real rel = (xv - lo_j) * (real(kSubBins) / (hi_j - lo_j));
+            int bin = static_cast<int>(rel);
+            bin = bin < 0 ? 0 : (bin > kSubBins - 1 ? kSubBins - 1 : bin);
+            atomicAdd(a.sub_cnt + static_cast<long long>(c.idx0 + j) * kSubBins + bin, 1u);
+        }
+    }
+}
+
+// what a lane leaves behind for the select kernel
+template <typename real, int NQ>
+__device__ __forceinline__ void lane_flush(const PredictArgs& a, const LaneCtx& c, const LaneAcc<real, NQ>& st) {
+    if (!c.live) return;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+        if (j < a.nq) {
+            if (st.below[j]) atomicAdd(a.cnt_below + c.idx0 + j, st.below[j]);
+            a.cnt_slot[static_cast<long long>(c.idx0 + j) * kMaxSlots + c.slot] = st.inwin[j];
+        }
+    }
+    if (a.first) {
+        a.mom_part[(static_cast<long long>(c.slot) * 2 + 0) * a.n_points + c.n] = static_cast<double>(st.sx);
+        a.mom_part[(static_cast<long long>(c.slot) * 2 + 1) * a.n_points + c.n] = static_cast<double>(st.sxx);
+        if (a.truth) {
+            atomicAdd(a.c_lt + c.n, st.nlt);
+            atomicAdd(a.c_le + c.n, st.nle);
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // The pass kernel: lane <-> nucleus, four posterior draws per step (one Philox call = the four
 // normals of this nucleus for draws 4i .. 4i+3), the draws' rows broadcast from a TMA-staged tile.
@@ -189,25 +299,18 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
 #pragma unroll
     for (int k = 0; k < KP; ++k)
         u[k] = (live && k < a.k) ? static_cast<const real*>(a.u)[static_cast<long long>(n) * a.k + k] : real(0);
-    const double mu_d = (live && a.mu) ? a.mu[n] : 0.0;
-    const real tc = (live && a.truth) ? static_cast<real>(a.truth[n] - mu_d) : real(0);
+    LaneCtx c;
+    c.n = n;
+    c.idx0 = n * a.nq;
+    c.slot = slot;
+    c.live = live;
+    c.seg = static_cast<unsigned int>(a.seg_len);
+    c.mu_d = (live && a.mu) ? a.mu[n] : 0.0;
+    const real tc = (live && a.truth) ? static_cast<real>(a.truth[n] - c.mu_d) : real(0);
     const real ctr = (live && a.center) ? static_cast<const real*>(a.center)[n] : real(0);
-    const int idx0 = n * a.nq;
-    real wlo[NQ], whi[NQ];
-    unsigned int below[NQ], inwin[NQ];
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) {
-        const bool on = live && j < a.nq;
-        wlo[j] = on ? static_cast<const real*>(a.win_lo)[idx0 + j] : real(FLT_MAX);
-        whi[j] = on ? static_cast<const real*>(a.win_hi)[idx0 + j] : real(FLT_MAX);
-        below[j] = 0u;
-        inwin[j] = 0u;
-    }
-    real sx = real(0), sxx = real(0);
-    unsigned int nlt = 0u, nle = 0u;
+    LaneAcc<real, NQ> st;
+    lane_init<real, NQ>(a, c, st);
     const uint32_t nglob = static_cast<uint32_t>(a.point0 + static_cast<unsigned long long>(n));
-    real* const cand = static_cast<real*>(a.cand);
-    const unsigned int seg = static_cast<unsigned int>(a.seg_len);
 
     if (n_tiles > 0) issue_tile(0);
     if (!tma_ok) __syncthreads();
@@ -247,74 +350,12 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
                 for (int r = 0; r < 4; ++r)
                     if (g + r >= cnt) x[r] = real(FLT_MAX);
             }
-            if (a.first) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const bool valid = x[r] < real(FLT_MAX);
-                    const real dv = valid ? x[r] - ctr : real(0);
-                    sx += dv;
-                    sxx = M::fma(dv, dv, sxx);
-                    count_step<real>(x[r], tc, nlt, nle);
-                    if (a.draws_out && valid && live)
-                        a.draws_out[(s + r) * a.ld_out + n] = static_cast<double>(x[r]) + mu_d;
-                }
-            }
-            // windows: two compares and a predicated add per (draw, window); hits only set a bit
-            unsigned int hits = 0u;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                for (int j = 0; j < NQ; ++j) {
-                    window_step<real>(x[r], wlo[j], whi[j], below[j], hits, 1u << (r * NQ + j));
-                }
-            }
-            while (hits) {                                  // rare per lane: store the draw, count it
-                const int bit = __ffs(hits) - 1;
-                hits &= hits - 1u;
-                const int r = bit / NQ, j = bit - r * NQ;
-                const real xv = r == 0 ? x[0] : (r == 1 ? x[1] : (r == 2 ? x[2] : x[3]));
-                unsigned int have = 0u;
-                real lo_j = real(0), hi_j = real(1);
-#pragma unroll
-                for (int jj = 0; jj < NQ; ++jj) {
-                    if (jj == j) {
-                        have = inwin[jj];
-                        inwin[jj] = have + 1u;
-                        lo_j = wlo[jj];
-                        hi_j = whi[jj];
-                    }
-                }
-                if (have < seg)
-                    cand[static_cast<long long>(idx0 + j) * a.cand_stride + slot * seg + have] = xv;
-                if (a.count_slices) {
-                    // which 1/32 slice of the window: lets an overflowing window be narrowed with exact
-                    // counts whatever the distribution (atoms, gaps, heavy tails)
-                    const real rel = (xv - lo_j) * (real(kSubBins) / (hi_j - lo_j));
-                    int bin = static_cast<int>(rel);
-                    bin = bin < 0 ? 0 : (bin > kSubBins - 1 ? kSubBins - 1 : bin);
-                    atomicAdd(a.sub_cnt + static_cast<long long>(idx0 + j) * kSubBins + bin, 1u);
-                }
-            }
+            consume4<real, NQ>(a, c, st, x, s, tc, ctr);
         }
         __syncthreads();                                   // everyone is done with this stage
     }
 
-    if (!live) return;
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) {
-        if (j < a.nq) {
-            if (below[j]) atomicAdd(a.cnt_below + idx0 + j, below[j]);
-            a.cnt_slot[static_cast<long long>(idx0 + j) * kMaxSlots + slot] = inwin[j];
-        }
-    }
-    if (a.first) {
-        a.mom_part[(static_cast<long long>(slot) * 2 + 0) * a.n_points + n] = static_cast<double>(sx);
-        a.mom_part[(static_cast<long long>(slot) * 2 + 1) * a.n_points + n] = static_cast<double>(sxx);
-        if (a.truth) {
-            atomicAdd(a.c_lt + n, nlt);
-            atomicAdd(a.c_le + n, nle);
-        }
-    }
+    lane_flush<real, NQ>(a, c, st);
 }
 
 // ----------------------------------------------------------------------------------------------
