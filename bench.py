@@ -567,13 +567,14 @@ def extras_config5(out, torch, dev, world, rank, timed, pb, steps, hbm_peak):
     out["config5_orthogonalize_f64"] = {"config": f"configs[4]: {n} x 256 fp64 rows per GPU, K=64", **res}
     del preds, xc
 
-    # prediction contraction at K = 64 (FP32 FMA pipe; the tcgen05 split-TF32 variant is not built yet)
+    # prediction at K = 64: the contraction runs on the tensor cores (tcgen05 kind::tf32, split TF32)
     from pybmc_b200.sampling_utils import PredictiveProblem
     rng = np.random.default_rng(1005)
     n_draws = 10000
     lo, hi = rank * n, (rank + 1) * n
     pr = rng.uniform(100, 2000, n)[:, None] + rng.normal(0, 3.0, (n, 80))
     vt64 = rng.normal(size=(k, 80)) * 0.02
+    vt64 -= vt64.mean(axis=1, keepdims=True)          # Vt_hat of row-centred predictions is orthogonal to 1
     theta = np.column_stack([rng.normal(size=k)[None, :] + 0.1 * rng.normal(size=(n_draws, k)),
                              np.abs(rng.normal(0.15, 0.01, n_draws))])
     prob = PredictiveProblem(pr, theta, vt64, truth=pr.mean(axis=1), dtype="float32", device=dev, point0=lo)

@@ -212,7 +212,7 @@ int launch_pass_tc(const PredictArgs& a, const unsigned char* image, cudaStream_
     dim3 grid((a.n_active + kTcRows - 1) / kTcRows, a.s_splits / kTcSlotsPerBlock);
     auto kern = predict_pass_tc_kernel<KP, NQ>;
     BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcImage<KP>::kSmemBytes));
-    kern<<<grid, kTcThreads, TcImage<KP>::kSmemBytes, st>>>(a, image);
+    kern<<<grid, kTcThreads + 32, TcImage<KP>::kSmemBytes, st>>>(a, image);
     BMC_LAUNCH_CHECK();
     return BMC_OK;
 }

@@ -14,7 +14,7 @@
 //   accumulator row i lives in TMEM lane i, so `tcgen05.ld.32x32b` hands every thread the draws of
 //   ITS nucleus: exactly the lane <-> nucleus layout the per-lane consumer (consume4) wants.
 //
-// Block = 16 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (the quarter a warp may address) and
+// Block = 16 consumer warps + 1 producer warp: consumer warp w reads TMEM lanes 32 (w % 4) .. +31 (the quarter a warp may address) and
 // columns 32 (w / 4) .. +31 of each 128-draw tile, i.e. four warps share a nucleus and act as four
 // sample splits ("slots").  The draws arrive as a pre-split image (theta_image_kernel) moved by one
 // 64 KB TMA bulk copy per tile, two stages; the accumulator is double-buffered in TMEM (2 x 128
@@ -137,24 +137,27 @@ __global__ void __launch_bounds__(256) theta_image_kernel(const float* __restric
 
 // ---- the pass -------------------------------------------------------------------------------------
 // grid = (ceil(n_active / 128), sample splits);  a.s_splits = 4 * gridDim.y slots.
+// Warps 0..15 consume (lane <-> nucleus); warp 16 is the producer: one elected thread issues the TMA
+// copies and the MMAs.  No block-wide barrier in the loop: mbarriers carry "tile landed" (full),
+// "accumulator complete" (done) and "accumulator copied to registers by all 16 warps" (empty).
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int KP, int NQ>
-__global__ void __launch_bounds__(kTcThreads, 1) predict_pass_tc_kernel(const PredictArgs a,
-                                                                        const unsigned char* __restrict__ img) {
+__global__ void __launch_bounds__(kTcThreads + 32, 1) predict_pass_tc_kernel(const PredictArgs a,
+                                                                             const unsigned char* __restrict__ img) {
     using IM = TcImage<KP>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* const a_hi = smem_raw;
     unsigned char* const a_lo = smem_raw + IM::kOperandBytes;
     unsigned char* const stage0 = smem_raw + 2 * IM::kOperandBytes;
-    __shared__ __align__(8) uint64_t full_bar[2], done_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[2], done_bar[2], empty_bar[2];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int quarter = warp & 3;                 // TMEM lanes 32 q .. 32 q + 31 are this warp's
-    const int colgrp = warp >> 2;                 // columns 32 c .. 32 c + 31 of every tile
-    const int row = 32 * quarter + lane;
-    const int pslot = blockIdx.x * kTcRows + row;
-    const bool live = pslot < a.n_active;
-    const int n = live ? (a.point_list ? a.point_list[pslot] : pslot) : 0;
+    constexpr int kConsumerWarps = kTcThreads / 32;
+    const bool producer = warp == kConsumerWarps;
 
     const int gy = gridDim.y;
     const long long per = ((a.n_draws + gy - 1) / gy + kTcTile - 1) / kTcTile * kTcTile;
@@ -165,14 +168,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) predict_pass_tc_kernel(const Pr
 
     if (warp == 0) tmem_alloc(&tmem_slot, kTcTmemCols);
     if (tid == 0) {
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
-        mbar_init(&done_bar[0], 1);
-        mbar_init(&done_bar[1], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&done_bar[i], 1);
+            mbar_init(&empty_bar[i], kConsumerWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // A operand: the u rows of this block's nuclei, split and laid out [chunk][row][16 B]
-    for (int i = tid; i < (KP / 4) * kTcRows; i += kTcThreads) {
+    for (int i = tid; i < (KP / 4) * kTcRows; i += kTcThreads + 32) {
         const int r = i & 127, c = i >> 7;
         const int ps = blockIdx.x * kTcRows + r;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -197,96 +201,115 @@ __global__ void __launch_bounds__(kTcThreads, 1) predict_pass_tc_kernel(const Pr
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    auto issue_tma = [&](int t) {                 // one thread
-        const int st = t & 1;
-        mbar_expect_tx(&full_bar[st], IM::kTileBytes);
-        tma_load_1d(stage0 + st * IM::kTileBytes, img + (tile0 + t) * IM::kStride, IM::kTileBytes, &full_bar[st]);
-    };
-    auto issue_mma = [&](int t) {                 // one thread: 3 K/8 MMAs into accumulator buffer t & 1
-        const int st = t & 1;
-        const uint32_t d = tmem_base + static_cast<uint32_t>(st * kTcTile);
-        const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo);
-        const uint32_t bhi = smem_u32(stage0 + st * IM::kTileBytes), blo = bhi + IM::kOperandBytes;
-        uint32_t acc = 0u;
+    if (producer) {
+        if (lane == 0) {
+            auto issue_tma = [&](int t) {
+                const int st = t & 1;
+                mbar_expect_tx(&full_bar[st], IM::kTileBytes);
+                tma_load_1d(stage0 + st * IM::kTileBytes, img + (tile0 + t) * IM::kStride, IM::kTileBytes,
+                            &full_bar[st]);
+            };
+            if (n_tiles > 0) issue_tma(0);
+            if (n_tiles > 1) issue_tma(1);
+            const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int st = t & 1;
+                const uint32_t ph = static_cast<uint32_t>(t >> 1) & 1u;
+                mbar_wait(&full_bar[st], ph);                       // operands of tile t are in shared memory
+                if (t >= 2) mbar_wait(&empty_bar[st], ph ^ 1u);     // tile t-2 left this accumulator buffer
+                tc_fence_after();
+                const uint32_t d = tmem_base + static_cast<uint32_t>(st * kTcTile);
+                const uint32_t bhi = smem_u32(stage0 + st * IM::kTileBytes), blo = bhi + IM::kOperandBytes;
+                uint32_t acc = 0u;
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {    // small terms first
-            const uint32_t ab = pass == 0 ? alo : ahi, bb = pass == 1 ? blo : bhi;
+                for (int pass = 0; pass < 3; ++pass) {              // small terms first
+                    const uint32_t ab = pass == 0 ? alo : ahi, bb = pass == 1 ? blo : bhi;
 #pragma unroll
-            for (int j = 0; j < KP / 8; ++j) {
-                umma_tf32(d, umma_desc(ab + j * 4096), umma_desc(bb + j * 4096), acc);
-                acc = 1u;
+                    for (int j = 0; j < KP / 8; ++j) {
+                        umma_tf32(d, umma_desc(ab + j * 4096), umma_desc(bb + j * 4096), acc);
+                        acc = 1u;
+                    }
+                }
+                umma_commit(&done_bar[st]);
+                if (t + 2 < n_tiles) {
+                    mbar_wait(&done_bar[st], ph);                   // the MMAs have read the stage: refill it
+                    issue_tma(t + 2);
+                }
             }
         }
-        umma_commit(&done_bar[st]);
-    };
+    } else {
+        const int quarter = warp & 3;             // TMEM lanes 32 q .. 32 q + 31 are this warp's
+        const int colgrp = warp >> 2;             // columns 32 c .. 32 c + 31 of every tile
+        const int row = 32 * quarter + lane;
+        const int pslot = blockIdx.x * kTcRows + row;
+        const bool live = pslot < a.n_active;
+        const int n = live ? (a.point_list ? a.point_list[pslot] : pslot) : 0;
+        LaneCtx c;
+        c.n = n;
+        c.idx0 = n * a.nq;
+        c.slot = blockIdx.y * kTcSlotsPerBlock + colgrp;
+        c.live = live;
+        c.seg = static_cast<unsigned int>(a.seg_len);
+        c.mu_d = (live && a.mu) ? a.mu[n] : 0.0;
+        const float tc = (live && a.truth) ? static_cast<float>(a.truth[n] - c.mu_d) : 0.f;
+        const float ctr = (live && a.center) ? static_cast<const float*>(a.center)[n] : 0.f;
+        LaneAcc<float, NQ> acc;
+        lane_init<float, NQ>(a, c, acc);
+        const uint32_t nglob = static_cast<uint32_t>(a.point0 + static_cast<unsigned long long>(n));
 
-    LaneCtx c;
-    c.n = n;
-    c.idx0 = n * a.nq;
-    c.slot = blockIdx.y * kTcSlotsPerBlock + colgrp;
-    c.live = live;
-    c.seg = static_cast<unsigned int>(a.seg_len);
-    c.mu_d = (live && a.mu) ? a.mu[n] : 0.0;
-    const float tc = (live && a.truth) ? static_cast<float>(a.truth[n] - c.mu_d) : 0.f;
-    const float ctr = (live && a.center) ? static_cast<const float*>(a.center)[n] : 0.f;
-    LaneAcc<float, NQ> acc;
-    lane_init<float, NQ>(a, c, acc);
-    const uint32_t nglob = static_cast<uint32_t>(a.point0 + static_cast<unsigned long long>(n));
-
-    if (tid == 0 && n_tiles > 0) {
-        issue_tma(0);
-        if (n_tiles > 1) issue_tma(1);
-        mbar_wait(&full_bar[0], 0);
-        tc_fence_after();
-        issue_mma(0);
-    }
-    __syncwarp();
-    for (int t = 0; t < n_tiles; ++t) {
-        const int st = t & 1;
-        if (tid == 0 && t + 1 < n_tiles) {        // tile t+1's MMAs run under this tile's consumer
-            mbar_wait(&full_bar[st ^ 1], ((t + 1) >> 1) & 1);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int st = t & 1;
+            mbar_wait(&done_bar[st], static_cast<uint32_t>(t >> 1) & 1u);   // accumulator of tile t complete
             tc_fence_after();
-            issue_mma(t + 1);
-        }
-        __syncwarp();
-        mbar_wait(&done_bar[st], (t >> 1) & 1);   // accumulator t complete; its smem stage is free
-        tc_fence_after();
-        if (tid == 0 && t + 2 < n_tiles) issue_tma(t + 2);
-        __syncwarp();
-
-        float xs[32];
-        tmem_load32(tmem_base + (static_cast<uint32_t>(32 * quarter) << 16) +
-                        static_cast<uint32_t>(st * kTcTile + 32 * colgrp),
-                    xs);
-        const long long s0 = s_begin + static_cast<long long>(t) * kTcTile + 32 * colgrp;
-        const float* sig = reinterpret_cast<const float*>(img + (tile0 + t) * IM::kStride + IM::kTileBytes) + 32 * colgrp;
+            float xs[32];
+            tmem_load32(tmem_base + (static_cast<uint32_t>(32 * quarter) << 16) +
+                            static_cast<uint32_t>(st * kTcTile + 32 * colgrp),
+                        xs);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);                     // this warp's copy is in registers
+            const long long s0 = s_begin + static_cast<long long>(t) * kTcTile + 32 * colgrp;
+            const float* sig =
+                reinterpret_cast<const float*>(img + (tile0 + t) * IM::kStride + IM::kTileBytes) + 32 * colgrp;
 #pragma unroll
-        for (int g = 0; g < 32; g += 4) {
-            const long long s = s0 + g;
-            if (s < s_end) {                      // warp-uniform
-                float x[4] = {xs[g], xs[g + 1], xs[g + 2], xs[g + 3]};
+            for (int g = 0; g < 32; g += 8) {
+                if (s0 + g >= s_end) break;                                 // warp-uniform
+                // two Philox calls side by side: independent chains for the scheduler to interleave
+                float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                float sg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (a.noise_mode == 1) {
-                    const float4 sg = *reinterpret_cast<const float4*>(sig + g);
-                    float z[4];
-                    normals4<float>(static_cast<uint32_t>(s >> 2), nglob, 0u, kTagNoise, a.key0, a.key1, z);
-                    x[0] = fmaf(sg.x, z[0], x[0]);
-                    x[1] = fmaf(sg.y, z[1], x[1]);
-                    x[2] = fmaf(sg.z, z[2], x[2]);
-                    x[3] = fmaf(sg.w, z[3], x[3]);
-                }
-                if (s + 4 > s_end) {
+                    const float4 s_a = *reinterpret_cast<const float4*>(sig + g);
+                    const float4 s_b = *reinterpret_cast<const float4*>(sig + g + 4);
+                    sg[0] = s_a.x; sg[1] = s_a.y; sg[2] = s_a.z; sg[3] = s_a.w;
+                    sg[4] = s_b.x; sg[5] = s_b.y; sg[6] = s_b.z; sg[7] = s_b.w;
+                    float za[4], zb[4];
+                    const uint32_t blk = static_cast<uint32_t>((s0 + g) >> 2);
+                    normals4<float>(blk, nglob, 0u, kTagNoise, a.key0, a.key1, za);
+                    normals4<float>(blk + 1u, nglob, 0u, kTagNoise, a.key0, a.key1, zb);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (s + r >= s_end) x[r] = FLT_MAX;
+                    for (int r = 0; r < 4; ++r) {
+                        z[r] = za[r];
+                        z[4 + r] = zb[r];
+                    }
                 }
-                consume4<float, NQ>(a, c, acc, x, s, tc, ctr);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const long long s = s0 + g + 4 * h;
+                    if (s < s_end) {
+                        float x[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            x[r] = fmaf(sg[4 * h + r], z[4 * h + r], xs[g + 4 * h + r]);
+                            if (s + r >= s_end) x[r] = FLT_MAX;
+                        }
+                        consume4<float, NQ>(a, c, acc, x, s, tc, ctr);
+                    }
+                }
             }
         }
-        tc_fence_before();
-        __syncthreads();                          // accumulator buffer t & 1 may be overwritten (tile t + 2)
+        lane_flush<float, NQ>(a, c, acc);
     }
-
-    lane_flush<float, NQ>(a, c, acc);
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_free(tmem_base, kTcTmemCols);
 }
