@@ -180,9 +180,10 @@ int bmc_predict_theta_stride(int k);
 int bmc_predict_fused(int dtype, const bmc_predict_problem* problem /*host*/, double* mean, double* var,
                       double* quant, int64_t* c_lt, int64_t* c_le, double* draws_out, int64_t ld_out,
                       void* workspace, size_t workspace_bytes, int* passes_out /*host, may be NULL*/, void* stream);
-/* fp32 with k > 16 contracts u . beta on the tensor cores (tcgen05, split TF32: fp32-level accuracy).
- * enabled = 0 forces the FFMA contraction for every k (A/B timing and tests); default 1. */
-void bmc_predict_set_tensor_path(int enabled);
+/* fp32 contractions u . beta run on the tensor cores (tcgen05 kind::tf32, split TF32: fp32-level
+ * accuracy) when the padded component count reaches a threshold.  mode 0: never (FFMA kernels for
+ * every k); mode 1: the default threshold; mode >= 2: threshold = mode (A/B timing and tests). */
+void bmc_predict_set_tensor_path(int mode);
 
 /* Order counts of a materialised S-by-N matrix (the reference's rndm_m): sort-free form of
  * pybmc/sampling_utils.py:28-33.  c_lt/c_le dev int64 [n_cols]. */

@@ -38,8 +38,10 @@ double norm_ppf(double p) {
            (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
 }
 
-// 0 = automatic (tensor cores for fp32 with K > 16), 1 = FFMA contraction everywhere (A/B measurements, tests)
-int g_tensor_path_off = 0;
+// fp32 contractions with padded K >= this go to the tensor cores; kTensorOff sends every K to the FFMA kernels
+constexpr int kTensorOff = 1 << 20;
+constexpr int kTensorDefaultMinK = 4;      // measured faster for every K (profiles/r1_notes.md)
+int g_tensor_min_k = kTensorDefaultMinK;
 
 struct QuantPlan {
     int nq;
@@ -232,11 +234,10 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
     const QuantPlan plan = make_plan(p->probs, p->nq, p->n_draws);
     const int kp = bmc_padded_components(p->k > 0 ? p->k : 1);
     // wide bases in fp32: the contraction goes to the tensor cores (predict_tc_kernels.cuh)
-    const bool tc = sizeof(real) == 4 && p->theta && kp >= 32 && p->noise_mode != BMC_NOISE_EXTERNAL &&
-                    !g_tensor_path_off;
+    const bool tc = sizeof(real) == 4 && p->theta && kp >= g_tensor_min_k && p->noise_mode != BMC_NOISE_EXTERNAL;
+    const int kt = std::max(kp, 8);               // operand width of the tensor path (one MMA spans 8 components)
     const long long tiles_tc = (p->n_draws + kTcTile - 1) / kTcTile;
-    const size_t image_bytes =
-        tc ? static_cast<size_t>(tiles_tc) * (kp == 32 ? TcImage<32>::kStride : TcImage<64>::kStride) : 0;
+    const size_t image_bytes = tc ? static_cast<size_t>(tiles_tc) * (2 * kt * 128 * 4 + kTcTile * 4) : 0;
     auto total_for = [&](long long n, const PassShape& sh) {
         return make_layout(n, p->nq, sh.cand_stride, sz, image_bytes).total;
     };
@@ -287,12 +288,14 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
                          : static_cast<int>((p->n_draws + kPredTile - 1) / kPredTile);
     const unsigned char* image = tc ? ws + lay.image : nullptr;
     if (tc) {
-        if (kp == 32)
-            theta_image_kernel<32><<<static_cast<unsigned>(tiles_tc), 256, 0, st>>>(
-                static_cast<const float*>(p->theta), p->n_draws, ws + lay.image);
-        else
-            theta_image_kernel<64><<<static_cast<unsigned>(tiles_tc), 256, 0, st>>>(
-                static_cast<const float*>(p->theta), p->n_draws, ws + lay.image);
+        const float* th = static_cast<const float*>(p->theta);
+        const unsigned gt = static_cast<unsigned>(tiles_tc);
+        switch (kt) {
+            case 8: theta_image_kernel<8><<<gt, 256, 0, st>>>(th, p->n_draws, kp + 4, kp, ws + lay.image); break;
+            case 16: theta_image_kernel<16><<<gt, 256, 0, st>>>(th, p->n_draws, kp + 4, kp, ws + lay.image); break;
+            case 32: theta_image_kernel<32><<<gt, 256, 0, st>>>(th, p->n_draws, kp + 4, kp, ws + lay.image); break;
+            default: theta_image_kernel<64><<<gt, 256, 0, st>>>(th, p->n_draws, kp + 4, kp, ws + lay.image); break;
+        }
         BMC_LAUNCH_CHECK();
     }
 
@@ -412,7 +415,12 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
             ++pass;
             int rc = BMC_OK;
             if (tc) {
-                rc = kp == 32 ? dispatch_nq_tc<32>(a, image, st) : dispatch_nq_tc<64>(a, image, st);
+                switch (kt) {
+                    case 8: rc = dispatch_nq_tc<8>(a, image, st); break;
+                    case 16: rc = dispatch_nq_tc<16>(a, image, st); break;
+                    case 32: rc = dispatch_nq_tc<32>(a, image, st); break;
+                    default: rc = dispatch_nq_tc<64>(a, image, st); break;
+                }
             } else {
                 switch (kp) {
                     case 4: rc = dispatch_nq<real, 4>(a, st); break;
@@ -482,7 +490,9 @@ size_t bmc_predict_workspace_bytes(int dtype, int64_t n_points, int nq, int64_t 
     return need;
 }
 
-void bmc_predict_set_tensor_path(int enabled) { g_tensor_path_off = enabled ? 0 : 1; }
+void bmc_predict_set_tensor_path(int mode) {
+    g_tensor_min_k = mode == 0 ? kTensorOff : (mode == 1 ? kTensorDefaultMinK : mode);
+}
 
 int bmc_predict_theta_stride(int k) { return bmc_padded_components(k > 0 ? k : 1) + 4; }
 

@@ -1,4 +1,4 @@
-// Tensor-core variant of the fused prediction pass for wide bases (fp32, K > 16).
+// Tensor-core variant of the fused prediction pass (fp32).
 //
 // The contraction  x[s][n] = u[n] . beta[s]  of pybmc/sampling_utils.py:64-77 is a GEMM whose output
 // is consumed at once (noise added, compared, counted) and never stored.  With K = 64 the FFMA form
@@ -111,27 +111,31 @@ __device__ __forceinline__ void tmem_load32(uint32_t taddr, float (&v)[32]) {
 // img[tile] = [hi: K/4 chunks x 128 rows x 16 B][lo: same][sigma: 128 floats]; rows past n_draws are 0.
 template <int KP>
 __global__ void __launch_bounds__(256) theta_image_kernel(const float* __restrict__ theta, long long n_draws,
-                                                          unsigned char* __restrict__ img) {
-    constexpr int LDT = KP + 4;
+                                                          int ldt, int sigma_col, unsigned char* __restrict__ img) {
+    // theta rows: beta in columns 0 .. sigma_col-1 (zero padded), sigma in column sigma_col, stride ldt
     const long long t = blockIdx.x;
     unsigned char* out = img + t * TcImage<KP>::kStride;
     for (int i = threadIdx.x; i < (KP / 4) * 128; i += blockDim.x) {
         const int r = i & 127, c = i >> 7;
         const long long s = t * kTcTile + r;
-        float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (s < n_draws) {
-            const float* row = theta + s * LDT + 4 * c;
-            split_tf32(row[0], hi.x, lo.x);
-            split_tf32(row[1], hi.y, lo.y);
-            split_tf32(row[2], hi.z, lo.z);
-            split_tf32(row[3], hi.w, lo.w);
+            const float* row = theta + s * ldt;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * c + e < sigma_col) v[e] = row[4 * c + e];
         }
+        float4 hi, lo;
+        split_tf32(v[0], hi.x, lo.x);
+        split_tf32(v[1], hi.y, lo.y);
+        split_tf32(v[2], hi.z, lo.z);
+        split_tf32(v[3], hi.w, lo.w);
         *reinterpret_cast<float4*>(out + (c * 128 + r) * 16) = hi;
         *reinterpret_cast<float4*>(out + TcImage<KP>::kOperandBytes + (c * 128 + r) * 16) = lo;
     }
     for (int r = threadIdx.x; r < kTcTile; r += blockDim.x) {
         const long long s = t * kTcTile + r;
-        reinterpret_cast<float*>(out + TcImage<KP>::kTileBytes)[r] = s < n_draws ? theta[s * LDT + KP] : 1.0f;
+        reinterpret_cast<float*>(out + TcImage<KP>::kTileBytes)[r] = s < n_draws ? theta[s * ldt + sigma_col] : 1.0f;
     }
 }
 

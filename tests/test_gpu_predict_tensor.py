@@ -32,7 +32,8 @@ def tensor_switch():
     lib.bmc_predict_set_tensor_path(1)
 
 
-@pytest.mark.parametrize("k,n,s", [(17, 300, 3000), (40, 129, 1000), (64, 700, 2500), (32, 128, 128), (64, 5, 130)])
+@pytest.mark.parametrize("k,n,s", [(17, 300, 3000), (40, 129, 1000), (64, 700, 2500), (32, 128, 128), (64, 5, 130),
+                                   (3, 200, 1000), (8, 131, 900), (12, 64, 515), (16, 400, 2000)])
 def test_contraction_accuracy_and_agreement_with_ffma(k, n, s, tensor_switch):
     from pybmc_b200.sampling_utils import PredictiveProblem
     preds, vt, theta, truth = _problem(k, n, s)
@@ -53,9 +54,10 @@ def test_contraction_accuracy_and_agreement_with_ffma(k, n, s, tensor_switch):
     np.testing.assert_allclose(tc.draws, ff.draws, rtol=0, atol=6e-7 * scale.max())
 
 
-@pytest.mark.parametrize("k", [24, 64])
-def test_noise_counts_and_percentiles_are_exact_functions_of_the_draws(k):
+@pytest.mark.parametrize("k", [6, 16, 24, 64])
+def test_noise_counts_and_percentiles_are_exact_functions_of_the_draws(k, tensor_switch):
     from pybmc_b200.sampling_utils import PredictiveProblem
+    tensor_switch(1)
     n, s = 333, 4000
     preds, vt, theta, truth = _problem(k, n, s, seed=1)
     q = [2.5, 16, 50, 84, 97.5]
