@@ -284,6 +284,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
     BMC_CUDA(cudaStreamSynchronize(st));   // the plan lives on this stack frame
 
     auto select_kern = predict_select_kernel<real>;
+    BMC_CUDA(cudaFuncSetAttribute(select_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kSelStageBytes));
     const int tiles = tc ? static_cast<int>(tiles_tc) * kTcSlotsPerBlock
                          : static_cast<int>((p->n_draws + kPredTile - 1) / kPredTile);
     const unsigned char* image = tc ? ws + lay.image : nullptr;
@@ -315,9 +316,13 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
             copy_guess_kernel<real><<<gb, 256, 0, st>>>(p->center + c0, p->scale + c0, n, ws + lay.center,
                                                         ws + lay.scale);
         } else {
-            predict_guess_kernel<real><<<gb, 256, 0, st>>>(u_chunk, n, p->k, p->theta_mean, p->theta_cov,
-                                                           p->noise_mode != BMC_NOISE_NONE, ws + lay.center,
-                                                           ws + lay.scale);
+            const size_t gs = (static_cast<size_t>(p->k + 1) + 32) * (p->k + 2) * sizeof(double);
+            if (gs > 32 * 1024)
+                BMC_CUDA(cudaFuncSetAttribute(predict_guess_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(gs)));
+            predict_guess_kernel<real><<<static_cast<unsigned>((n + 31) / 32), 256, gs, st>>>(
+                u_chunk, n, p->k, p->theta_mean, p->theta_cov, p->noise_mode != BMC_NOISE_NONE, ws + lay.center,
+                ws + lay.scale);
         }
         BMC_LAUNCH_CHECK();
         predict_window_kernel<real><<<static_cast<unsigned>((nqn + 255) / 256), 256, 0, st>>>(
@@ -432,7 +437,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
             }
             if (rc != BMC_OK) return rc;
             const long long items = static_cast<long long>(s.n_active) * p->nq;
-            select_kern<<<static_cast<unsigned>((items + 7) / 8), 256, 0, st>>>(s);
+            select_kern<<<static_cast<unsigned>((items + 7) / 8), 256, 8 * kSelStageBytes, st>>>(s);
             BMC_LAUNCH_CHECK();
             int pending = 0;
             BMC_CUDA(cudaMemcpyAsync(&pending, d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));

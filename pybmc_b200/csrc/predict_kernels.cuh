@@ -520,11 +520,16 @@ __device__ void warp_radix_select(const real* src, const unsigned int* slot_cnt,
 
 // one warp per (nucleus, quantile): exact selection among the window's candidates when they were
 // all stored, then sel_decide (select_logic.h) reads the answer or chooses the next window
+constexpr int kSelStageBytes = 8192;   // per warp: candidates gathered from their slots before the radix passes
 template <typename real>
 __global__ void __launch_bounds__(256) predict_select_kernel(const SelectArgs a) {
     __shared__ unsigned int hist_all[8][256];
+    __shared__ unsigned int staged_cnt[8];
+    extern __shared__ __align__(16) unsigned char select_smem[];
+    constexpr int kStageCap = kSelStageBytes / static_cast<int>(sizeof(real));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned int* const hist = hist_all[warp];
+    real* const stage = reinterpret_cast<real*>(select_smem) + warp * kStageCap;
     const long long item = static_cast<long long>(blockIdx.x) * 8 + warp;       // (active slot, j)
     const long long pslot = item / a.nq;
     if (pslot >= a.n_active) return;
@@ -580,7 +585,19 @@ __global__ void __launch_bounds__(256) predict_select_kernel(const SelectArgs a)
 
     bool stored_equal = false;
     real stored_value = real(0), v_first = real(0), v_second = real(0);
-    if (inside && storable) {
+    if (inside && storable && cw <= kStageCap) {
+        // gather the slots' candidates once; the radix passes then run out of shared memory
+        int off = 0;
+        for (int sl = 0; sl < a.n_slots; ++sl) {
+            const int c = static_cast<int>(slot_cnt[sl]);
+            const real* seg = src + static_cast<long long>(sl) * a.seg_len;
+            for (int i = lane; i < c; i += 32) stage[off + i] = seg[i];
+            off += c;
+        }
+        if (lane == 0) staged_cnt[warp] = static_cast<unsigned int>(off);
+        __syncwarp();
+        warp_radix_select<real>(stage, staged_cnt + warp, 1, kStageCap, t1 - cb, hist, &v_first, &v_second);
+    } else if (inside && storable) {
         warp_radix_select<real>(src, slot_cnt, a.n_slots, a.seg_len, t1 - cb, hist, &v_first, &v_second);
     } else if (inside && first_slot >= 0) {
         const int c = min(static_cast<int>(slot_cnt[first_slot]), a.seg_len);
@@ -630,23 +647,45 @@ __global__ void __launch_bounds__(256) predict_select_kernel(const SelectArgs a)
 // ----------------------------------------------------------------------------------------------
 // first guess of centre and spread per nucleus from the posterior sample moments:
 //   E x = u.E[beta],  Var x = u' Cov[beta] u + noise * E[sigma^2]
+// Eight threads per nucleus: thread q takes rows r = q, q + 8, ... of the quadratic form; the covariance
+// and the block's u rows are staged in shared memory (row stride k + 2: conflict-free).  Block = 256
+// threads = 32 nuclei; dynamic shared memory = ((k + 1) (k + 2) + 32 (k + 2)) doubles.
+constexpr int kGuessSub = 8;
 template <typename real>
-__global__ void predict_guess_kernel(const void* u_, long long n, int k, const double* theta_mean,
-                                     const double* theta_cov /* [(k+1)^2] */, int noise_on, void* center_,
-                                     void* scale_) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const real* u = static_cast<const real*>(u_) + i * k;
-    const int d = k + 1;
-    double m = 0.0, v = 0.0;
-    for (int r = 0; r < k; ++r) {
-        const double ur = static_cast<double>(u[r]);
-        m += ur * theta_mean[r];
-        double t = 0.0;
-        for (int c = 0; c < k; ++c) t += theta_cov[r * d + c] * static_cast<double>(u[c]);
-        v += ur * t;
+__global__ void __launch_bounds__(256) predict_guess_kernel(const void* u_, long long n, int k,
+                                                            const double* theta_mean,
+                                                            const double* theta_cov /* [(k+1)^2] */, int noise_on,
+                                                            void* center_, void* scale_) {
+    extern __shared__ double guess_smem[];
+    const int d = k + 1, ld = k + 2;
+    double* const cov = guess_smem;                       // [d][ld]
+    double* const us = guess_smem + d * ld;               // [32][ld]
+    for (int i = threadIdx.x; i < d * d; i += blockDim.x) cov[(i / d) * ld + i % d] = theta_cov[i];
+    const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+    const real* u = static_cast<const real*>(u_);
+    for (int i = threadIdx.x; i < 32 * k; i += blockDim.x) {
+        const long long p = p0 + i / k;
+        us[(i / k) * ld + i % k] = p < n ? static_cast<double>(u[p * k + i % k]) : 0.0;
     }
-    if (noise_on) v += theta_cov[k * d + k] + theta_mean[k] * theta_mean[k];
+    __syncthreads();
+    const int local = threadIdx.x / kGuessSub, q = threadIdx.x % kGuessSub;
+    const double* ur = us + local * ld;
+    double m = 0.0, v = 0.0;
+    for (int r = q; r < k; r += kGuessSub) {
+        const double x = ur[r];
+        m = fma(x, theta_mean[r], m);
+        double t = 0.0;
+        for (int c = 0; c < k; ++c) t = fma(cov[r * ld + c], ur[c], t);
+        v = fma(x, t, v);
+    }
+#pragma unroll
+    for (int o = kGuessSub / 2; o > 0; o >>= 1) {
+        m += __shfl_xor_sync(0xffffffffu, m, o);
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    const long long i = p0 + local;
+    if (q != 0 || i >= n) return;
+    if (noise_on) v += cov[k * ld + k] + theta_mean[k] * theta_mean[k];
     static_cast<real*>(center_)[i] = static_cast<real>(m);
     static_cast<real*>(scale_)[i] = static_cast<real>(sqrt(fmax(v, 0.0)));
 }
