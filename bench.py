@@ -325,6 +325,7 @@ def run_native(args):
     nominal_issue = 148 * 4 * sm_mhz * 1e6 / 1e9                 # 148 SMs x 4 schedulers x clock, Gwarp-inst/s
     pipe_peaks = measure_pipe_peaks(torch, dev)
     issue_peak = max(pipe_peaks["issue"]["Gwarp_inst_per_s"], pipe_peaks["ffma"]["Gwarp_inst_per_s"])
+    _PEAKS["issue"] = issue_peak
     line["roofline"] = {
         "kernel": "gibbs_conjugate_kernel<float,8,2>",
         "bound": "issue", "unit": "Gwarp-inst/s",
@@ -383,6 +384,31 @@ def measure_pipe_peaks(torch, dev):
         out[name] = {"Gwarp_inst_per_s": thread_ops / 32 / (best * 1e-3) / 1e9, "ms": best}
     out["ffma"]["TFLOP_per_s"] = out["ffma"]["Gwarp_inst_per_s"] * 32 * 2 / 1e3
     return out
+
+
+_PEAKS = {}
+
+
+def predict_roofline(torch, dev, units_per_s_per_gpu, ms_step):
+    """Issue roofline of the fused prediction step: the tensor-core pass is bound by its consumer
+    (Philox, Box-Muller, compares, predicated counts), not by the MMAs or HBM."""
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))["predict_pass_tc_f32_k16_q5"]
+    except (OSError, KeyError, ValueError):
+        return None
+    if "issue" not in _PEAKS:
+        pk = measure_pipe_peaks(torch, dev)
+        _PEAKS["issue"] = max(pk["issue"]["Gwarp_inst_per_s"], pk["ffma"]["Gwarp_inst_per_s"])
+    per_unit = float(c["thread_inst_per_sample_point"]) / 32.0
+    achieved = per_unit * units_per_s_per_gpu / 1e9
+    flops = 2.0 * 16 * 3 * units_per_s_per_gpu / 1e12          # three TF32 products per component
+    return {"kernel": "predict_pass_tc_kernel<16,5> (+ predict_select_kernel)", "bound": "issue", "unit": "Gwarp-inst/s",
+            "achieved": achieved, "peak": _PEAKS["issue"], "frac": achieved / _PEAKS["issue"],
+            "thread_inst_per_sample_point": float(c["thread_inst_per_sample_point"]),
+            "traffic": float(c["dram_bytes_per_launch"]),
+            "tensor": {"kind": "tcgen05.mma kind::tf32, split TF32 (3 products)", "TFLOP_per_s": flops,
+                       "note": "K=16: the MMAs keep the tensor pipe ~3 % busy (ncu); the 16 consumer warps are the bound"},
+            "note": "whole step (pass + select + window set-up) against the pass kernel's instruction count"}
 
 
 def fma_pipe_view(rate_per_gpu, sm_mhz):
@@ -497,6 +523,7 @@ def extras_predict(out, args, torch, dev, world, rank, timed, barrier, flush, hb
     out["predict_f32"] = {"metric": "posterior_pred_samples_x_points_per_sec",
                           "value": n_total * n_draws / (ms * 1e-3), "unit": "samples*points/s", "ms_per_step": ms,
                           "passes": holder["r"].passes,
+                          "roofline": predict_roofline(torch, dev, n_total * n_draws / (ms * 1e-3) / world, ms),
                           "config": "configs[3]: 1e5 nuclei x 1e5 draws x K=16, mean/var/5 percentiles/coverage "
                                     "counts, no S x N matrix, nuclei sharded over ranks"}
     del prob, ws

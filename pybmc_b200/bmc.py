@@ -21,7 +21,7 @@ from .sampling_utils import (DEFAULT_DRAWS, coverage_from_counts, predictive_sum
 GRAM_RATIO_MIN = 1e-5
 
 
-def orthogonalize_arrays(preds, truth, components_kept, method="auto", device=None):
+def orthogonalize_arrays(preds, truth, components_kept, method="auto", device=None, reduce=None):
     """Centre the model predictions per point and project on the truncated SVD basis
     (pybmc/bmc.py:102-130 + pybmc/inference_utils.py:147-168) on the device.
 
@@ -29,7 +29,12 @@ def orthogonalize_arrays(preds, truth, components_kept, method="auto", device=No
     M-by-M eigenproblem (or the thin SVD when the spectrum is too graded for the Gram route),
     ``bmc_project_rows`` (U_hat = Xc Vt_hat').  The reference's n-by-n U is never formed.
 
-    Returns dict(y, mu, U_hat, S_hat, Vt_hat, Vt_hat_normalized, method).
+    ``reduce`` (optional): a callable summing a device tensor over ranks; ``preds`` / ``truth`` are
+    then this rank's rows, the M-by-M Gram matrix is all-reduced, every rank solves the same small
+    eigenproblem and projects its own rows (Gram route only).
+
+    Returns dict(y, mu, U_hat, S_hat, Vt_hat, Vt_hat_normalized, method); with ``reduce`` the
+    per-point entries (y, mu, U_hat) cover this rank's rows.
     """
     lib = _lib.load()
     dev = D.device(device)
@@ -38,7 +43,9 @@ def orthogonalize_arrays(preds, truth, components_kept, method="auto", device=No
         raise ValueError("model predictions must be [n_points, n_models]")
     n, m = preds.shape
     k = int(components_kept)
-    if k < 1 or k > min(n, m):
+    if reduce is not None:
+        method = "gram"
+    if k < 1 or k > (m if reduce is not None else min(n, m)):
         raise IndexError(f"components_kept={k} outside 1..{min(n, m)}")   # upstream: IndexError from U.T[i]
     pd_ = D.to_device(preds, dev)
     td = D.to_device(np.asarray(truth, dtype=np.float64).reshape(-1), dev)
@@ -54,6 +61,8 @@ def orthogonalize_arrays(preds, truth, components_kept, method="auto", device=No
         gram = torch.empty((m, m), dtype=torch.float64, device=dev)
         ws = torch.empty(max(int(lib.bmc_gram_workspace_bytes(n, m)), 8), dtype=torch.uint8, device=dev)
         _lib.check(lib.bmc_gram(D.ptr(xc), n, m, m, None, None, D.ptr(gram), D.ptr(ws), ws.numel(), st), "bmc_gram")
+        if reduce is not None:
+            gram = reduce(gram)
         lam, vec = torch.linalg.eigh(gram)                       # cuSOLVER, M-by-M
         lam = torch.flip(lam, dims=[0]).clamp_min(0.0)
         vec = torch.flip(vec, dims=[1])

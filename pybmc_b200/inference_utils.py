@@ -71,8 +71,9 @@ def USVt_hat_extraction(U, S, Vt, components_kept):
 # --------------------------------------------------------------------------------------------
 # sufficient statistics on the device
 # --------------------------------------------------------------------------------------------
-def _gram_with_response(Xd, yd, dev):
-    """[X | y]'[X | y] by ``bmc_gram`` -> (X'X, X'y, y'y) on the host (fp64)."""
+def _gram_with_response(Xd, yd, dev, reduce=None):
+    """[X | y]'[X | y] by ``bmc_gram`` -> (X'X, X'y, y'y) on the host (fp64).  ``reduce`` sums the
+    (K+1)-by-(K+1) matrix over the ranks holding the other rows (pybmc_b200.parallel)."""
     lib = _lib.load()
     n, k = Xd.shape
     out = torch.empty((k + 1, k + 1), dtype=torch.float64, device=dev)
@@ -80,11 +81,13 @@ def _gram_with_response(Xd, yd, dev):
     ws = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=dev)
     _lib.check(lib.bmc_gram(D.ptr(Xd), n, k, Xd.stride(0), None, D.ptr(yd), D.ptr(out), D.ptr(ws), ws.numel(),
                             D.stream_ptr(dev)), "bmc_gram")
+    if reduce is not None:
+        out = reduce(out)
     a = D.to_host(out)
     return a[:k, :k].copy(), a[:k, k].copy(), float(a[k, k])
 
 
-def _residual_ss(Xd, yd, b, dev):
+def _residual_ss(Xd, yd, b, dev, reduce=None):
     """|y - X b|^2 by ``bmc_residual_ss`` (pybmc/inference_utils.py:29-31)."""
     lib = _lib.load()
     n, k = Xd.shape
@@ -93,6 +96,8 @@ def _residual_ss(Xd, yd, b, dev):
     ws = torch.empty(max(int(lib.bmc_rss_workspace_bytes(n)), 8), dtype=torch.uint8, device=dev)
     _lib.check(lib.bmc_residual_ss(D.ptr(Xd), n, k, Xd.stride(0), D.ptr(yd), D.ptr(bd), D.ptr(out), D.ptr(ws),
                                    ws.numel(), D.stream_ptr(dev)), "bmc_residual_ss")
+    if reduce is not None:
+        out = reduce(out)
     return float(out.item())
 
 
@@ -141,22 +146,29 @@ class ConjugateSampler:
     Building the object uploads (y, X), computes X'X, X'y, y'y, b_ols, RSS_min and the
     diagonalising transform; ``run`` only launches ``bmc_gibbs_run`` (what bench.py times as the
     HBM-resident step).
+
+    ``reduce`` (optional): a callable summing a device tensor over ranks.  With it, (y, X) are this
+    rank's ROWS of the training set and the sufficient statistics are the all-reduced ones, so every
+    rank ends up with the same sampler constants (SURVEY.md section 8e, configs[4]).
     """
 
-    def __init__(self, y, X, prior_info, device=None):
+    def __init__(self, y, X, prior_info, device=None, reduce=None):
         self.dev = D.device(device)
         b0, B0, nu0, sigma20 = prior_info
         yd, Xd = _as_design(y, X, self.dev)
         self.n, self.k = Xd.shape
+        if reduce is not None:
+            self.n = int(round(float(reduce(torch.tensor([float(self.n)], dtype=torch.float64,
+                                                         device=self.dev)).item())))
         b0 = np.asarray(b0, dtype=np.float64).reshape(-1)
         B0 = np.asarray(B0, dtype=np.float64)
         if b0.shape[0] != self.k or B0.shape != (self.k, self.k):
             raise ValueError("prior mean / covariance do not match the number of components")
         lam = np.linalg.inv(B0)                                   # :22
-        gram, xty, yty = _gram_with_response(Xd, yd, self.dev)    # :25 (+ X'y, y'y)
+        gram, xty, yty = _gram_with_response(Xd, yd, self.dev, reduce)    # :25 (+ X'y, y'y)
         gram_inv = np.linalg.inv(gram)                            # :26 (LinAlgError on singular X'X)
         b_ols = gram_inv @ xty                                    # :28
-        rss_min = _residual_ss(Xd, yd, b_ols, self.dev)           # :29-31
+        rss_min = _residual_ss(Xd, yd, b_ols, self.dev, reduce)   # :29-31
         self.sigma2_init = max(rss_min / self.n, SIGMA2_FLOOR)    # :31, :37
         low = np.linalg.cholesky(lam + RIDGE * np.eye(self.k))    # prior precision incl. the ridge of :41
         low_inv = np.linalg.inv(low)

@@ -75,6 +75,31 @@ def merge_coverage_counts(local_covered, group=None):
     return t
 
 
+def sum_over_ranks(group=None):
+    """A ``reduce`` callable for ``orthogonalize_arrays`` / ``ConjugateSampler``: in-place all-reduce
+    (sum) of a tensor over ``group``; the identity when not distributed."""
+    def reduce(t):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t
+    return reduce
+
+
+def row_range(n_rows_total, rank=None, world=None, group=None):
+    """Training rows [start, stop) owned by ``rank`` (contiguous, sizes differ by at most one)."""
+    return chain_range(n_rows_total, rank, world, group)
+
+
+def sharded_orthogonalize(preds_rows, truth_rows, components_kept, *, group=None, device=None):
+    """pybmc/bmc.py:102-130 with the ROWS of the prediction table split over ranks (configs[4]: 1e5 x 256):
+    local centring and partial Gram, one all-reduce of the M-by-M matrix (512 KB at M = 256), the
+    same small eigenproblem on every rank, local projection.  Returns this rank's y, mu, U_hat rows
+    and the replicated S_hat, Vt_hat, Vt_hat_normalized."""
+    from .bmc import orthogonalize_arrays
+    return orthogonalize_arrays(preds_rows, truth_rows, components_kept, method="gram", device=device,
+                                reduce=sum_over_ranks(group))
+
+
 def posterior_from_sums(sums, count, k):
     """First / full second moment sums of a (k+1)-vector -> (mean, covariance)."""
     sums = np.asarray(sums, dtype=np.float64)
@@ -93,16 +118,19 @@ def posterior_from_sums(sums, count, k):
 # the two sharded entry points (one process per GPU; call them from every rank)
 # ------------------------------------------------------------------------------------------------
 def sharded_gibbs(y, X, iterations, prior_info, n_chains_total, *, seed, dtype="float32", thin=1, discard=0,
-                  keep_samples=False, group=None, device=None):
+                  keep_samples=False, group=None, device=None, rows_sharded=False):
     """Run this rank's share of ``n_chains_total`` conjugate chains and all-reduce the moment sums.
 
     Every rank returns the same posterior mean / covariance of [b, sigma] (what a single GPU running
-    all chains would report) plus its own ``GibbsResult`` (samples of its chains, if kept)."""
+    all chains would report) plus its own ``GibbsResult`` (samples of its chains, if kept).
+    ``rows_sharded=True``: (y, X) are this rank's rows (from ``sharded_orthogonalize``); X'X, X'y,
+    y'y and RSS_min are all-reduced first, so every rank samples the same posterior."""
     from .inference_utils import ConjugateSampler, GibbsResult, _finish_samples, _moments_from_stats
     rank, world = _world(group)
     lo, hi = chain_range(n_chains_total, rank, world)
-    sampler = ConjugateSampler(y, X, prior_info, device)
-    samples, cstats, meta = sampler.run(iterations, hi - lo, seed, dtype, thin, discard, keep_samples, "full", lo)
+    sampler = ConjugateSampler(y, X, prior_info, device, reduce=sum_over_ranks(group) if rows_sharded else None)
+    stats = "full" if sampler.k <= 8 else "auto"           # cross moments only while they fit in registers
+    samples, cstats, meta = sampler.run(iterations, hi - lo, seed, dtype, thin, discard, keep_samples, stats, lo)
     total, count = merge_moment_sums(cstats.sum(dim=1), float(iterations) * (hi - lo), group)
     k, kp = sampler.k, meta["kp"]
     mean_e, cov_e = _moments_from_stats(total.cpu().numpy(), k, kp, meta["mode"], count)

@@ -32,6 +32,12 @@ def _chains(first, last, iters):
             for c in range(first, last)]
 
 
+def _table():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    return cases.ensemble(11, 41, 6)
+
+
 def _sums(samples):
     s = np.concatenate(samples)
     d = s.shape[1]
@@ -52,8 +58,15 @@ def _worker(rank, world, port, out):
     local = torch.arange(plo, phi, dtype=torch.float64).repeat(3, 1) * 1.5
     gathered = par.gather_points(local, n_points)
     covered = par.merge_coverage_counts(torch.tensor([phi - plo, rank + 1], dtype=torch.int64))
+    # rows of the prediction table sharded (SURVEY.md 8e, configs[4]): partial Gram of the row-centred
+    # matrix, all-reduced by the callable the device path hands to orthogonalize_arrays / ConjugateSampler
+    preds, truth = _table()
+    rlo, rhi = par.row_range(len(truth))
+    xc = preds[rlo:rhi] - preds[rlo:rhi].mean(axis=1, keepdims=True)
+    gram = par.sum_over_ranks()(torch.from_numpy(xc.T @ xc))
     if rank == 0:
-        torch.save(dict(total=total, n=n, gathered=gathered, covered=covered, ranges=(lo, hi, plo, phi)), out)
+        torch.save(dict(total=total, n=n, gathered=gathered, covered=covered, ranges=(lo, hi, plo, phi),
+                        gram=gram, rows=(rlo, rhi)), out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,6 +87,16 @@ def test_two_rank_merge_equals_single_rank(tmp_path):
     assert torch.equal(got["gathered"], torch.arange(10, dtype=torch.float64).repeat(3, 1) * 1.5)
     assert got["covered"].tolist() == [10, 3]
     assert got["ranges"] == (0, 3, 0, 8)
+    # the all-reduced Gram matrix gives the singular values / right vectors of the whole table
+    from oracle import bmc_oracle as oc
+    preds, truth = _table()
+    assert got["rows"] == (0, 21)
+    ref = oc.orthogonalize_arrays(preds, truth, 3, full_matrices=False)
+    lam, vec = np.linalg.eigh(got["gram"].numpy())
+    np.testing.assert_allclose(np.sqrt(lam[::-1][:3]), ref["S_hat"], rtol=1e-10)
+    for i in range(3):
+        v = vec[:, ::-1][:, i]
+        np.testing.assert_allclose(abs(v @ ref["Vt_hat_normalized"][i]), 1.0, rtol=1e-10)
 
 
 def test_ranges_cover_everything_once():
