@@ -103,3 +103,22 @@ def test_retry_passes_regenerate_the_same_draws():
     np.testing.assert_allclose(lean.percentiles, np.percentile(full.draws, q, axis=0), rtol=1e-13)
     c_lt, c_le = oc.order_counts(full.draws, truth)
     assert np.array_equal(lean.c_lt, c_lt) and np.array_equal(lean.c_le, c_le)
+
+
+@pytest.mark.parametrize("k,n,s,q", [(1, 1, 5, [50.0]), (2, 3, 127, [0, 100]), (5, 130, 129, [1, 5, 25, 50, 75, 95, 99, 99.9]),
+                                     (64, 257, 4, [2.5, 97.5]), (9, 1000, 1, [50.0])])
+def test_small_and_ragged_shapes(k, n, s, q):
+    """Fewer draws than one tile, one nucleus, eight percentiles (the widest template), a single draw."""
+    from pybmc_b200.sampling_utils import PredictiveProblem
+    preds, vt, theta, truth = _problem(k, n, s, seed=3)
+    prob = PredictiveProblem(preds, theta, vt, truth=truth, dtype="float32", point0=5)
+    full = prob.run(percentiles=q, seed=8, return_draws=True)
+    lean = prob.run(percentiles=q, seed=8)
+    assert full.draws.shape == (s, n)
+    assert np.array_equal(full.percentiles, lean.percentiles)
+    np.testing.assert_allclose(lean.percentiles, np.percentile(full.draws, q, axis=0), rtol=1e-13)
+    c_lt, c_le = oc.order_counts(full.draws, truth)
+    assert np.array_equal(lean.c_lt, c_lt) and np.array_equal(lean.c_le, c_le)
+    f64 = PredictiveProblem(preds, theta, vt, truth=truth, dtype="float64", point0=5).run(
+        percentiles=q, seed=8, return_draws=True)
+    np.testing.assert_allclose(full.draws, f64.draws, rtol=1e-5)
