@@ -29,19 +29,19 @@ int launch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream
     return BMC_OK;
 }
 
-template <typename real, int KP>
+template <typename real, int KP, int GEN>
 int launch_group(const GibbsArgs& a, int stats_mode, cudaStream_t stream) {
-    const int wpb = 4, cpw = 32 / kConjGroup;
+    const int wpb = 4, cpw = 32 / GEN;
     const unsigned blocks = static_cast<unsigned>((a.n_chains + wpb * cpw - 1) / (wpb * cpw));
     switch (stats_mode) {
         case BMC_STATS_NONE:
-            gibbs_conjugate_group_kernel<real, KP, 0><<<blocks, wpb * 32, 0, stream>>>(a);
+            gibbs_conjugate_group_kernel<real, KP, 0, GEN><<<blocks, wpb * 32, 0, stream>>>(a);
             break;
         case BMC_STATS_DIAG:
-            gibbs_conjugate_group_kernel<real, KP, 1><<<blocks, wpb * 32, 0, stream>>>(a);
+            gibbs_conjugate_group_kernel<real, KP, 1, GEN><<<blocks, wpb * 32, 0, stream>>>(a);
             break;
         default:
-            gibbs_conjugate_group_kernel<real, KP, 2><<<blocks, wpb * 32, 0, stream>>>(a);
+            gibbs_conjugate_group_kernel<real, KP, 2, GEN><<<blocks, wpb * 32, 0, stream>>>(a);
     }
     BMC_LAUNCH_CHECK();
     return BMC_OK;
@@ -51,13 +51,20 @@ int launch_group(const GibbsArgs& a, int stats_mode, cudaStream_t stream) {
 // cost ~50 % more instructions per chain-iteration but bring eight times the warps.  Measured crossover
 // on B200 (profiles/layout_sweep.py): 16,384 chains (1.23 vs 1.18 ms); 32,768: 1.8 vs 2.3; 4096: 1.2 vs 0.5.
 constexpr long long kConjGroupBelow = 16384;
+// below this a chain gets the whole warp for generating its variates: one chain of 50,000 fp64 iterations
+// 23.5 -> 16.2 ms; break-even near 2,048 chains (profiles/warp_sweep.py)
+constexpr long long g_conj_warp_below = 1536;
 
 template <typename real>
 int dispatch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream_t stream) {
     // (a two-lanes-per-chain variant was measured in round 1: 46 % more instructions for 70 % instead of
     //  61 % issue utilisation and register-limited to 16 warps/SM -- slower; see profiles/r1_notes.md)
+    if (a.n_chains < g_conj_warp_below && a.k <= 8)
+        return a.k <= 4 ? launch_group<real, 4, 32>(a, stats_mode, stream)
+                        : launch_group<real, 8, 32>(a, stats_mode, stream);
     if (a.n_chains < kConjGroupBelow && a.k <= 8)
-        return a.k <= 4 ? launch_group<real, 4>(a, stats_mode, stream) : launch_group<real, 8>(a, stats_mode, stream);
+        return a.k <= 4 ? launch_group<real, 4, 8>(a, stats_mode, stream)
+                        : launch_group<real, 8, 8>(a, stats_mode, stream);
     if (a.k <= 4) return launch_conjugate<real, 4>(a, stats_mode, threads, stream);
     if (a.k <= 8) return launch_conjugate<real, 8>(a, stats_mode, threads, stream);
     if (a.k <= 16) return launch_conjugate<real, 16>(a, stats_mode, threads, stream);

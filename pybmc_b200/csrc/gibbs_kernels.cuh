@@ -1,7 +1,7 @@
 // Batched samplers in sufficient-statistic form.
 //
 //   gibbs_conjugate_kernel        one chain per thread   pybmc/inference_utils.py:39-54 (gibbs_sampler loop)
-//   gibbs_conjugate_group_kernel  eight lanes per chain  same loop, for fewer than 16,384 chains
+//   gibbs_conjugate_group_kernel  eight lanes (or a warp) per chain  same loop, for fewer than 16,384 (1,536) chains
 //   gibbs_simplex_kernel          one chain per thread   pybmc/inference_utils.py:97-141 (gibbs_sampler_simplex)
 //   gibbs_simplex_group_kernel    eight lanes per chain  same loops, for fewer than 16,384 chains
 //
@@ -179,13 +179,18 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
 // group kernel below, the state-independent variates of 32 consecutive iterations are generated in
 // parallel by the group (lane g: iterations base + g + 8t) and parked in shared memory; the 32 state
 // updates then run in order with lane g owning component g and RSS summed by three shuffles.
+// G = 32 gives a chain the whole warp: the 32 iterations of a batch are generated one per lane (lanes
+// 8..31 only generate; the state lives in lanes 0..7), for launches of so few chains that latency, not
+// issue slots, is what is scarce -- the reference's own single chain of 50,000 iterations.
 constexpr int kConjGroup = 8;
+constexpr int kConjLanes = 8;             // lanes that hold state: one per component
 
-template <typename real, int KP, int MODE>
+template <typename real, int KP, int MODE, int GEN = kConjGroup>
 __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsArgs a) {
     using M = Math<real>;
-    static_assert(KP <= kConjGroup, "one lane per component");
-    constexpr int G = kConjGroup;
+    static_assert(KP <= kConjLanes, "one lane per component");
+    static_assert(GEN == 8 || GEN == 32, "eight lanes or a warp per chain");
+    constexpr int G = GEN;
     constexpr int D = KP + 1;
     constexpr int WPB = 4, CPW = 32 / G;
     constexpr int ROW = KP + 1;                                           // z[KP], gamma
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
             const real e = sd * M::fma(pull, sd, z);                      // pull/p + z/sqrt(p)
             real rss = (d * e) * e;
 #pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) rss += __shfl_xor_sync(0xffffffffu, rss, o, G);
+            for (int o = kConjLanes / 2; o > 0; o >>= 1) rss += __shfl_xor_sync(0xffffffffu, rss, o, kConjLanes);
             s2 = (real(0.5) * (prior_scale + (rss_min + rss))) * inv_gm;
             s2 = s2 > real(1e-6) ? s2 : real(1e-6);
             sig = M::sqrt(s2);

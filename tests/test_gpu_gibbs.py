@@ -93,18 +93,21 @@ def test_chain_ids_are_global():
 
 
 def test_conjugate_layouts_agree():
-    """Few chains use eight lanes per chain, many chains one thread per chain: same stream, same chains
-    (up to the summation order of RSS), same moment sums."""
+    """A handful of chains get a warp each, a few thousand eight lanes each, many chains one thread each:
+    same stream, same chains (up to the summation order of RSS), same moment sums."""
     import pybmc_b200 as pb
     for name in ("ensemble_default", "wide_k8"):
         y, X, prior = CASES[name]()
         width = np.asarray(X).shape[1] + 1
         many = pb.run_gibbs(y, X, 50, prior, n_chains=16384, seed=13, stats="full")
         few = pb.run_gibbs(y, X, 50, prior, n_chains=6, seed=13, stats="full")
+        mid = pb.run_gibbs(y, X, 50, prior, n_chains=2000, seed=13, stats="full")
         a = many.samples.reshape(16384, 50, width)[:6]
         b = few.samples.reshape(6, 50, width)
+        c = mid.samples.reshape(2000, 50, width)[:6]
         np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
-        for res in (few, many):
+        np.testing.assert_allclose(c, b, rtol=1e-9, atol=1e-12)
+        for res in (few, mid, many):
             smp = res.samples
             np.testing.assert_allclose(res.mean, smp.mean(axis=0), rtol=1e-9, atol=1e-12)
             want = np.cov(smp.T, ddof=0)
