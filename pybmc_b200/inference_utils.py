@@ -48,6 +48,7 @@ class GibbsResult:
     acceptance: np.ndarray = None
     info: dict = field(default_factory=dict)
     rhat: np.ndarray = None   # [K+1] Gelman-Rubin potential scale reduction (needs >= 2 chains, full stats)
+    ess: np.ndarray = None    # [K+1] effective sample size of the whole run (all chains), same requirements
 
 
 def USVt_hat_extraction(U, S, Vt, components_kept):
@@ -240,24 +241,30 @@ class ConjugateSampler:
         jac_d = torch.from_numpy(jac).to(cstats.device)
         base_d = torch.from_numpy(base).to(cstats.device)
         chain_mean_d = base_d[None, :] + (cstats[comp, :].t() / float(iterations)) @ jac_d.t()
-        self.last_rhat = _rhat(cstats, comp, _stat_layout(k, kp, mode)[2], jac_d, chain_mean_d, iterations)
+        self.last_rhat, self.last_ess = _chain_diagnostics(cstats, comp, _stat_layout(k, kp, mode)[2], jac_d,
+                                                           chain_mean_d, iterations)
         return mean, cov, D.to_host(chain_mean_d)
 
 
-def _rhat(cstats, comp, second, jac_d, chain_mean_d, iterations):
-    """Gelman-Rubin R-hat per coordinate of [b, sigma] from the per-chain moment sums (device, fp64):
-    sqrt(((n-1)/n W + B/n) / W) with W the mean within-chain variance and B/n the variance of the
-    chain means.  None when there is a single chain or only diagonal moments of rotated coordinates."""
+def _chain_diagnostics(cstats, comp, second, jac_d, chain_mean_d, iterations):
+    """Between-chain diagnostics per coordinate of [b, sigma] from the per-chain moment sums (device, fp64).
+
+    R-hat (Gelman-Rubin): sqrt(((n-1)/n W + B/n) / W), W the mean within-chain variance and B/n the
+    variance of the chain means.  Effective sample size of the whole run: a chain mean over n iterations
+    has variance var * tau / n (tau = integrated autocorrelation time), and with many independent chains
+    that variance is *observed* as B/n, so ESS = chains * n / tau = chains * var+ / (B/n), var+ the
+    pooled variance.  Returns (None, None) when there is a single chain or only diagonal moments of
+    rotated coordinates."""
     n_chains = cstats.shape[1]
     if n_chains < 2 or iterations < 2:
-        return None
+        return None, None
     d = len(comp)
     idx = [[second.get((min(a, b), max(a, b))) for b in comp] for a in comp]
     m1 = cstats[comp, :].t() / float(iterations)
     if any(i is None for row in idx for i in row):
         # diagonal moments only: enough when the coordinates are not rotated (diagonal W)
         if bool((jac_d - torch.diag(torch.diagonal(jac_d))).abs().max() > 0):
-            return None
+            return None, None
         diag_rows = torch.tensor([second[(a, a)] for a in comp], device=cstats.device)
         var_e = cstats[diag_rows, :].t() / float(iterations) - m1 * m1
         var_b = var_e * torch.diagonal(jac_d)[None, :] ** 2 * (iterations / (iterations - 1.0))
@@ -268,8 +275,10 @@ def _rhat(cstats, comp, second, jac_d, chain_mean_d, iterations):
         var_b = torch.einsum("ra,cab,rb->cr", jac_d, cov_e, jac_d) * (iterations / (iterations - 1.0))
     w = var_b.mean(dim=0)
     b_over_n = chain_mean_d.var(dim=0, unbiased=True)
-    rhat = torch.sqrt(((iterations - 1.0) / iterations * w + b_over_n) / w)
-    return rhat.cpu().numpy()
+    var_plus = (iterations - 1.0) / iterations * w + b_over_n
+    rhat = torch.sqrt(var_plus / w)
+    ess = n_chains * var_plus / b_over_n
+    return rhat.cpu().numpy(), ess.cpu().numpy()
 
 
 def _finish_samples(samples, as_numpy):
@@ -294,7 +303,7 @@ def run_gibbs(y, X, iterations, prior_info, *, n_chains=1, seed=None, dtype="flo
                        n_chains=int(n_chains), iterations=int(iterations), n_kept=meta["n_kept"], seed=seed,
                        dtype=str(dtype), info=dict(rss_min=sampler.rss_min, b_ols=sampler.b_ols,
                                                    sigma2_init=sampler.sigma2_init),
-                       rhat=getattr(sampler, "last_rhat", None))
+                       rhat=getattr(sampler, "last_rhat", None), ess=getattr(sampler, "last_ess", None))
 
 
 def gibbs_sampler(y, X, iterations, prior_info, *, n_chains=1, seed=None, dtype="float64", thin=1, discard=0,
@@ -381,7 +390,8 @@ class SimplexSampler:
         base_d = torch.from_numpy(base).to(cstats.device)
         chain_mean_d = base_d[None, :] + cstats[comp, :].t() / float(iterations)
         eye = torch.eye(k + 1, dtype=torch.float64, device=cstats.device)
-        self.last_rhat = _rhat(cstats, comp, _stat_layout(k, kp, mode)[2], eye, chain_mean_d, iterations)
+        self.last_rhat, self.last_ess = _chain_diagnostics(cstats, comp, _stat_layout(k, kp, mode)[2], eye,
+                                                           chain_mean_d, iterations)
         return base + mean_e, cov_e, D.to_host(chain_mean_d)
 
 
@@ -403,7 +413,7 @@ def run_gibbs_simplex(y, X, Vt_hat, S_hat, iterations, prior_info, burn=10000, s
     return GibbsResult(samples=_finish_samples(samples, as_numpy), mean=mean, cov=cov, chain_mean=chain_mean,
                        n_chains=int(n_chains), iterations=int(iterations), n_kept=meta["n_kept"], seed=seed,
                        dtype=str(dtype), acceptance=acc, info=dict(rss_min=sampler.rss_min, b_ols=sampler.b_ols),
-                       rhat=getattr(sampler, "last_rhat", None))
+                       rhat=getattr(sampler, "last_rhat", None), ess=getattr(sampler, "last_ess", None))
 
 
 def gibbs_sampler_simplex(y, X, Vt_hat, S_hat, iterations, prior_info, burn=10000, stepsize=0.001, *,

@@ -125,3 +125,33 @@ def test_moment_layout_roundtrip():
     mean, cov = _moments_from_stats(diag, k, kp, _lib.STATS_DIAG, n)
     np.testing.assert_allclose(np.diag(cov), e[:, keep].var(0))
     assert np.count_nonzero(cov - np.diag(np.diag(cov))) == 0
+
+
+def test_chain_diagnostics_on_ar1_chains():
+    """R-hat and the between-chain effective sample size from per-chain moment sums (host logic, torch on
+    the CPU): AR(1) chains with coefficient rho have integrated autocorrelation time (1+rho)/(1-rho)."""
+    import torch
+    from pybmc_b200.inference_utils import _chain_diagnostics, _stat_layout
+    rng = np.random.default_rng(5)
+    k, kp, chains, n = 2, 4, 600, 4000
+    rhos = np.array([0.0, 0.8, 0.5])                      # two components + sigma
+    x = np.empty((chains, n, 3))
+    x[:, 0] = rng.standard_normal((chains, 3))
+    innov = rng.standard_normal((chains, n, 3)) * np.sqrt(1 - rhos ** 2)
+    for t in range(1, n):
+        x[:, t] = rhos * x[:, t - 1] + innov[:, t]
+    d, comp, second = _stat_layout(k, kp, 2)
+    stats = np.zeros((d + d * (d + 1) // 2, chains))
+    for a, ia in enumerate(comp):
+        stats[ia] = x[:, :, a].sum(axis=1)
+        for b, ib in enumerate(comp):
+            if ib >= ia:
+                stats[second[(ia, ib)]] = (x[:, :, a] * x[:, :, b]).sum(axis=1)
+    cs = torch.from_numpy(stats)
+    chain_mean = torch.from_numpy(x.mean(axis=1))
+    rhat, ess = _chain_diagnostics(cs, comp, second, torch.eye(3, dtype=torch.float64), chain_mean, n)
+    assert np.all(np.abs(rhat - 1.0) < 5e-3)
+    want = chains * n * (1 - rhos) / (1 + rhos)
+    assert np.all(np.abs(ess / want - 1.0) < 0.2), (ess, want)        # sd of the estimate ~ sqrt(2/chains) = 6 %
+    one = _chain_diagnostics(cs[:, :1], comp, second, torch.eye(3, dtype=torch.float64), chain_mean[:1], n)
+    assert one == (None, None)

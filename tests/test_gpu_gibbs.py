@@ -131,6 +131,10 @@ def test_rhat_from_device_moments():
     ys, Xs, Vt, S = _simplex_case()
     slow = pb.run_gibbs_simplex(ys, Xs, Vt, S, 300, [1.0, 0.02], burn=0, stepsize=0.002, n_chains=32, seed=2)
     assert slow.rhat is not None and slow.rhat[:3].max() > 1.05
+    # effective sample size: the conjugate sampler mixes in a few iterations, the random walk does not
+    big = pb.run_gibbs(y, X, 400, prior, n_chains=4096, seed=3, stats="full", keep_samples=False)
+    assert np.all(big.ess > 0.5 * 4096 * 400) and np.all(big.ess < 1.3 * 4096 * 400)
+    assert slow.ess[:3].max() < 0.05 * 32 * 300
 
 
 def test_thinning_and_discard_select_the_same_iterates():
