@@ -2,13 +2,15 @@
 
 Same public names as upstream ``pybmc`` (pybmc/__init__.py:11-24) for the inference path:
 
-    BayesianModelCombination, gibbs_sampler, USVt_hat_extraction, coverage
+    Dataset, BayesianModelCombination, gibbs_sampler, USVt_hat_extraction, coverage
 
 plus, importable from their submodules as upstream, ``gibbs_sampler_simplex`` and
-``rndm_m_random_calculator``.  Importing the package does not touch the GPU; the first call
+``rndm_m_random_calculator``.  ``Dataset`` (pybmc/data.py) is host-side pandas glue except for its
+distance split, which runs on the device.  Importing the package does not touch the GPU; the first call
 loads ``csrc/libbmc_b200.so`` and raises if it or a CUDA device is missing (no CPU path).
 """
 from .bmc import BayesianModelCombination, orthogonalize_arrays
+from .data import Dataset
 from .inference_utils import (ConjugateSampler, GibbsResult, SimplexSampler, USVt_hat_extraction, gibbs_sampler,
                               gibbs_sampler_literal, gibbs_sampler_simplex, run_gibbs, run_gibbs_simplex)
 from .sampling_utils import (PredictiveProblem, PredictiveResult, column_percentiles, coverage,
@@ -17,6 +19,7 @@ from .sampling_utils import (PredictiveProblem, PredictiveResult, column_percent
 __version__ = "0.1.0"
 
 __all__ = [
+    "Dataset",
     "BayesianModelCombination",
     "gibbs_sampler",
     "gibbs_sampler_simplex",
@@ -24,16 +27,3 @@ __all__ = [
     "coverage",
     "rndm_m_random_calculator",
 ]
-
-
-def __getattr__(name):
-    """``Dataset`` (HDF5/CSV loading and splitting, pybmc/data.py) is outside the accelerated path: it is
-    re-exported from an installed upstream ``pybmc`` when there is one."""
-    if name == "Dataset":
-        try:
-            from pybmc.data import Dataset
-        except ImportError as exc:
-            raise AttributeError("pybmc_b200 accelerates the inference path only; install pybmc for its "
-                                 "Dataset loader (or build the data_dict of DataFrames yourself)") from exc
-        return Dataset
-    raise AttributeError(f"module 'pybmc_b200' has no attribute {name!r}")

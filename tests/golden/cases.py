@@ -73,6 +73,24 @@ def ensemble_frame(seed, n, n_models):
     return pd.DataFrame(cols), [f"m{m}" for m in range(n_models)]
 
 
+def long_table(seed=41, n_points=60):
+    """A CSV-style long table (one row per model and point, pybmc/data.py:86-107): three models that each
+    miss a few points, two properties, and a ``truth`` pseudo-model covering everything."""
+    rng = np.random.default_rng(seed)
+    n = np.arange(n_points) % 12 + 8
+    z = np.arange(n_points) // 12 + 20
+    base = 8.0 * (n + z) - 0.05 * (n - z) ** 2
+    rows = []
+    for j, model in enumerate(["mA", "mB", "mC", "truth"]):
+        keep = np.ones(n_points, bool) if model == "truth" else rng.random(n_points) > 0.15
+        order = rng.permutation(np.flatnonzero(keep))
+        rows.append(pd.DataFrame({
+            "model": model, "N": n[order], "Z": z[order],
+            "BE": np.round(base[order] * (1 + 0.002 * j) + rng.normal(0, 0.3, order.size), 6),
+            "Rad": np.round(1.2 * (n[order] + z[order]) ** (1 / 3) + rng.normal(0, 0.01, order.size), 6)}))
+    return pd.concat(rows, ignore_index=True)
+
+
 def posterior_like(seed, rows, k):
     """Rows shaped like sampler output: K coefficients and a positive sigma."""
     rng = np.random.default_rng(seed)

@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import cases  # noqa: E402
 
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+REF = next((a for a in sys.argv[1:] if not a.startswith("--")), "/root/reference")
 sys.path.insert(0, REF)
 from pybmc.bmc import BayesianModelCombination  # noqa: E402
 from pybmc.inference_utils import (  # noqa: E402
@@ -142,5 +142,42 @@ def main():
          upper=up_df["Predicted_Upper"].values, coverage=np.array(cov), coverage_filtered=np.array(cov_f))
 
 
+def dataset_golden():
+    """Dataset.load_data / split_data / get_subset / view_data (data.py:30-374) on a CSV written from
+    ``cases.long_table``."""
+    import tempfile
+    from pybmc.data import Dataset
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "ensemble.csv")
+        cases.long_table().to_csv(path, index=False)
+        ds = Dataset(path)
+        with contextlib.redirect_stdout(io.StringIO()):
+            data = ds.load_data(models=["mA", "mB", "mC", "truth"], keys=["BE", "Rad"], domain_keys=["N", "Z"])
+    out = {"BE": data["BE"].values.astype(float), "Rad": data["Rad"].values.astype(float),
+           "columns": np.array(list(data["BE"].columns))}
+    tr, va, te = ds.split_data(data, "BE", "random", train_size=0.6, val_size=0.2, test_size=0.2)
+    out.update(train_idx=tr.index.values, val_idx=va.index.values, test_idx=te.index.values)
+    tr2, va2, te2 = ds.split_data(data, "Rad", "random", train_size=0.5, val_size=0.3, test_size=0.2)
+    out.update(train_idx2=tr2.index.values, val_idx2=va2.index.values, test_idx2=te2.index.values)
+    subsets = {
+        "tuple": ds.get_subset("BE", filters={"N": (10, 14)}),
+        "list": ds.get_subset("BE", filters={"Z": [20, 22]}),
+        "scalar": ds.get_subset("BE", filters={"Z": 23}, models_to_include=["mB", "truth"]),
+        "callable": ds.get_subset("BE", filters={"N": lambda c: c % 2 == 0, "Z": (21, 24)}),
+        "multi": ds.get_subset("Rad", filters={"multi": lambda r: r["N"] + r["Z"] > 35}, models_to_include=["mC"]),
+    }
+    for name, frame in subsets.items():
+        out["subset_" + name] = frame.values.astype(float)
+        out["subset_" + name + "_index"] = frame.index.values
+        out["subset_" + name + "_columns"] = np.array(list(frame.columns))
+    view = ds.view_data()
+    out["view_models"] = np.array(view["available_models"])
+    out["view_properties"] = np.array(view["available_properties"])
+    out["view_series"] = ds.view_data("Rad", "mB").values
+    save("dataset", **out)
+
+
 if __name__ == "__main__":
-    main()
+    if "--dataset-only" not in sys.argv:
+        main()
+    dataset_golden()
