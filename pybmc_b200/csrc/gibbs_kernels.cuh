@@ -72,9 +72,25 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     const real sig_ref = static_cast<real>(a.sigma_ref);
     const GammaConst<real> gc = make_gamma_const<real>(a.shape);
 
-    real acc[NS > 0 ? NS : 1];
+    // fp32: Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2) take two components at a time.
+    // With all cross moments, the 45 + 9 sums are kept as register pairs (30 instructions instead of 54 for
+    // K = 8): pair (i, c), c = 2i+1 .. KP, holds the products of e_2i and e_2i+1 with e_c (e_KP = sigma
+    // deviation); pair i of `dg` holds their squares.  Every half is the same rounding as the scalar form.
+    constexpr bool PACK2 = sizeof(real) == 4 && KP % 4 == 0;
+    constexpr bool PACK = sizeof(real) == 4 && MODE == 2 && KP % 2 == 0;
+    constexpr int H = KP / 2;
+    constexpr int NX = PACK ? H * KP - H * (H - 1) : 1;
+    f32x2 m1p[PACK ? H : 1], dg[PACK ? H : 1], cx[NX];
+    float m1s = 0.f, m2s = 0.f;
+    if (PACK) {
 #pragma unroll
-    for (int j = 0; j < (NS > 0 ? NS : 1); ++j) acc[j] = real(0);
+        for (int i = 0; i < H; ++i) m1p[i] = dg[i] = 0ull;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) cx[j] = 0ull;
+    }
+    real acc[(NS > 0 && !PACK) ? NS : 1];
+#pragma unroll
+    for (int j = 0; j < ((NS > 0 && !PACK) ? NS : 1); ++j) acc[j] = real(0);
 
     real s2 = static_cast<real>(a.sigma2_init);
     real sig = M::sqrt(s2);
@@ -91,19 +107,42 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         if (!odd) gp = gamma_pair<real>(it32, chain, kTagGibbs, philox_keys(a.key0, a.key1));   // every other iteration
         real e[KP];
         real rss0 = rss_min, rss1 = real(0);
+        if constexpr (PACK2) {
+            // two components at a time on packed fp32 instructions (same roundings as the scalar form below)
+            f32x2 rssp = pack2(rss_min, 0.f);
+            const f32x2 s2b = pack2(s2, s2), sigb = pack2(sig, sig);
 #pragma unroll
-        for (int j = 0; j < (KP + 3) / 4; ++j) {
-            real z[4];
-            normals4<real>(it32, static_cast<uint32_t>(j), chain, kTagGibbs, a.key0, a.key1, z);
+            for (int j = 0; j < KP / 4; ++j) {
+                const Philox4 r = philox4x32_10(it32, static_cast<uint32_t>(j), chain, kTagGibbs, a.key0, a.key1);
+                const f32x2 zp[2] = {M::box_muller2(r.x, r.y), M::box_muller2(r.z, r.w)};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int k = 4 * j + q;
-                if (k < KP) {
-                    // 1/sqrt(p_k) = sigma / sqrt(d_k + s2): one MUFU on the s2 -> e -> RSS -> s2 dependency
-                    const real sd = sig * M::rsqrt(d[k] + s2);
-                    e[k] = sd * M::fma(pull[k], sd, z[q]);          // pull/p + z/sqrt(p)
-                    if (k & 1) rss1 = M::fma(d[k] * e[k], e[k], rss1);
-                    else rss0 = M::fma(d[k] * e[k], e[k], rss0);
+                for (int h = 0; h < 2; ++h) {
+                    const int k = 4 * j + 2 * h;
+                    const f32x2 dp = pack2(d[k], d[k + 1]);
+                    float t0, t1;
+                    unpack2(add2(dp, s2b), t0, t1);
+                    const f32x2 sdp = mul2(pack2(M::rsqrt(t0), M::rsqrt(t1)), sigb);
+                    const f32x2 ep = mul2(sdp, fma2(pack2(pull[k], pull[k + 1]), sdp, zp[h]));
+                    rssp = fma2(mul2(dp, ep), ep, rssp);
+                    unpack2(ep, e[k], e[k + 1]);
+                }
+            }
+            unpack2(rssp, rss0, rss1);
+        } else {
+#pragma unroll
+            for (int j = 0; j < (KP + 3) / 4; ++j) {
+                real z[4];
+                normals4<real>(it32, static_cast<uint32_t>(j), chain, kTagGibbs, a.key0, a.key1, z);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = 4 * j + q;
+                    if (k < KP) {
+                        // 1/sqrt(p_k) = sigma / sqrt(d_k + s2): one MUFU on the s2 -> e -> RSS -> s2 dependency
+                        const real sd = sig * M::rsqrt(d[k] + s2);
+                        e[k] = sd * M::fma(pull[k], sd, z[q]);          // pull/p + z/sqrt(p)
+                        if (k & 1) rss1 = M::fma(d[k] * e[k], e[k], rss1);
+                        else rss0 = M::fma(d[k] * e[k], e[k], rss0);
+                    }
                 }
             }
         }
@@ -114,7 +153,51 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         s2 = s2 > real(1e-6) ? s2 : real(1e-6);
         sig = M::sqrt(s2);
 
-        if (MODE != 0) {
+        if constexpr (PACK) {
+            const float es = sig - sig_ref;
+            const f32x2 esb = pack2(es, es);
+            auto row_of = [&](int r, int c) { return D + r * D - r * (r - 1) / 2 + (c - r); };
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                const f32x2 ep = pack2(e[2 * i], e[2 * i + 1]);
+                m1p[i] = add2(m1p[i], ep);
+                dg[i] = fma2(ep, ep, dg[i]);
+#pragma unroll
+                for (int c = 2 * i + 1; c <= KP; ++c) {
+                    const int j = i * KP - i * (i - 1) + (c - 2 * i - 1);
+                    cx[j] = fma2(ep, c < KP ? pack2(e[c < KP ? c : 0], e[c < KP ? c : 0]) : esb, cx[j]);
+                }
+            }
+            m1s += es;
+            m2s = fmaf(es, es, m2s);
+            if (((it + 1) % kFlushEvery) == 0 || it + 1 == a.iterations) {
+                auto flush = [&](int row, float v) {
+                    double* p = a.chain_stats + static_cast<long long>(row) * a.n_chains + tid;
+                    *p += static_cast<double>(v);
+                };
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    float lo, hi;
+                    unpack2(m1p[i], lo, hi);
+                    flush(2 * i, lo);
+                    flush(2 * i + 1, hi);
+                    unpack2(dg[i], lo, hi);
+                    flush(row_of(2 * i, 2 * i), lo);             // hi repeats pair (i, 2i+1)'s second half
+                    m1p[i] = dg[i] = 0ull;
+#pragma unroll
+                    for (int c = 2 * i + 1; c <= KP; ++c) {
+                        const int j = i * KP - i * (i - 1) + (c - 2 * i - 1);
+                        unpack2(cx[j], lo, hi);
+                        flush(row_of(2 * i, c), lo);
+                        flush(row_of(2 * i + 1, c), hi);
+                        cx[j] = 0ull;
+                    }
+                }
+                flush(KP, m1s);
+                flush(row_of(KP, KP), m2s);
+                m1s = m2s = 0.f;
+            }
+        } else if (MODE != 0) {
             const real es = sig - sig_ref;
 #pragma unroll
             for (int k = 0; k < KP; ++k) acc[k] += e[k];
@@ -397,9 +480,25 @@ __global__ void __launch_bounds__(128) gibbs_simplex_kernel(const SimplexArgs a)
     }
     real s2 = static_cast<real>(a.sigma2_init);                               // :86, RSS(0)/n
 
-    real acc[NS > 0 ? NS : 1];
+    // fp32: Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2) take two components at a time.
+    // With all cross moments, the 45 + 9 sums are kept as register pairs (30 instructions instead of 54 for
+    // K = 8): pair (i, c), c = 2i+1 .. KP, holds the products of e_2i and e_2i+1 with e_c (e_KP = sigma
+    // deviation); pair i of `dg` holds their squares.  Every half is the same rounding as the scalar form.
+    constexpr bool PACK2 = sizeof(real) == 4 && KP % 4 == 0;
+    constexpr bool PACK = sizeof(real) == 4 && MODE == 2 && KP % 2 == 0;
+    constexpr int H = KP / 2;
+    constexpr int NX = PACK ? H * KP - H * (H - 1) : 1;
+    f32x2 m1p[PACK ? H : 1], dg[PACK ? H : 1], cx[NX];
+    float m1s = 0.f, m2s = 0.f;
+    if (PACK) {
 #pragma unroll
-    for (int j = 0; j < (NS > 0 ? NS : 1); ++j) acc[j] = real(0);
+        for (int i = 0; i < H; ++i) m1p[i] = dg[i] = 0ull;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) cx[j] = 0ull;
+    }
+    real acc[(NS > 0 && !PACK) ? NS : 1];
+#pragma unroll
+    for (int j = 0; j < ((NS > 0 && !PACK) ? NS : 1); ++j) acc[j] = real(0);
     int n_acc = 0;
     real* const out = static_cast<real*>(a.samples);
     long long slot = 0;

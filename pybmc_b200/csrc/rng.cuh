@@ -66,6 +66,35 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 template <typename real>
 struct Math;
 
+// Two fp32 values in one 64-bit register pair, for Blackwell's packed FFMA2 / FADD2 / FMUL2 (PTX *.f32x2,
+// sm_100+).  Each half is an ordinary round-to-nearest fp32 operation, so results are bit-identical to the
+// scalar instructions; the gain is one issue slot for two operations.  ptxas folds pack2(x, x) and swapped
+// halves into operand modifiers (R.F32, .F32x2.LO_HI): no moves are spent on broadcasts.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 template <>
 struct Math<float> {
     // (r + 1/2) 2^-32, evaluated in one FFMA; never 0, at most 1.
@@ -83,6 +112,19 @@ struct Math<float> {
         asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
         za = rad * cs;
         zb = rad * sn;
+    }
+    // the same pair of normals (bit for bit) with the two-at-a-time steps packed: {za, zb}
+    static __device__ __forceinline__ f32x2 box_muller2(uint32_t ra, uint32_t rb) {
+        float ua, ub, l2, rad, sn, cs, arg, ang;
+        unpack2(fma2(pack2(__uint2float_rn(ra), __uint2float_rn(rb)),
+                     pack2(2.3283064365386963e-10f, 2.3283064365386963e-10f),
+                     pack2(1.1641532182693481e-10f, 1.1641532182693481e-10f)), ua, ub);
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(ua));
+        unpack2(mul2(pack2(l2, ub), pack2(-1.3862943611198906f, 6.283185307179586f)), arg, ang);
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(arg));
+        asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+        asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+        return mul2(pack2(rad, rad), pack2(cs, sn));
     }
     static __device__ __forceinline__ float log(float x) { return __logf(x); }
     static __device__ __forceinline__ float exp(float x) { return __expf(x); }
