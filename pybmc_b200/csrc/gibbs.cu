@@ -126,6 +126,9 @@ int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t
     a.prior_scale = p->nu0 * p->sigma20;                      // :51
     a.sigma2_init = p->sigma2_init;
     a.sigma_ref = sqrt(p->sigma2_init);
+    a.cf = make_run_consts<float>(a.rss_min, a.prior_scale, a.sigma_ref, a.sigma2_init, a.shape);
+    a.cd = make_run_consts<double>(a.rss_min, a.prior_scale, a.sigma_ref, a.sigma2_init, a.shape);
+    a.gamma_boost = a.shape < 1.0;
     a.key0 = static_cast<uint32_t>(seed);
     a.key1 = static_cast<uint32_t>(seed >> 32);
     a.chain0 = chain0;

@@ -33,6 +33,9 @@ struct GibbsArgs {
     int dense_w;
     double rss_min, shape, prior_scale;   // prior_scale = nu0 * sigma20
     double sigma2_init, sigma_ref;
+    RunConsts<float> cf;                  // the same scalars + Gamma constants, ready in either type
+    RunConsts<double> cd;
+    int gamma_boost;                      // shape < 1
     uint32_t key0, key1;
     unsigned long long chain0;            // global id of this launch's first chain
     long long n_chains;
@@ -44,6 +47,12 @@ struct GibbsArgs {
 };
 
 constexpr int kFlushEvery = 64;           // iterations between fp64 flushes of the moment sums
+
+template <typename real, typename Args>
+__device__ __forceinline__ const RunConsts<real>& run_consts(const Args& a) {
+    if constexpr (sizeof(real) == 4) return a.cf;
+    else return a.cd;
+}
 
 template <int KP, int MODE>
 struct StatCount {
@@ -67,10 +76,11 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         d[k] = k < a.k ? static_cast<real>(a.d[k]) : real(0);
         pull[k] = k < a.k ? static_cast<real>(a.pull[k]) : real(0);
     }
-    const real rss_min = static_cast<real>(a.rss_min);
-    const real prior_scale = static_cast<real>(a.prior_scale);
-    const real sig_ref = static_cast<real>(a.sigma_ref);
-    const GammaConst<real> gc = make_gamma_const<real>(a.shape);
+    const RunConsts<real>& rc = run_consts<real>(a);
+    const real rss_min = rc.rss_min;
+    const real prior_scale = run_consts<real>(a).prior_scale;
+    const real sig_ref = run_consts<real>(a).sigma_ref;
+    const GammaConst<real> gc = gamma_const_of(run_consts<real>(a), a.gamma_boost);
 
     // fp32: Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2) take two components at a time.
     // With all cross moments, the 45 + 9 sums are kept as register pairs (30 instructions instead of 54 for
@@ -92,7 +102,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
 #pragma unroll
     for (int j = 0; j < ((NS > 0 && !PACK) ? NS : 1); ++j) acc[j] = real(0);
 
-    real s2 = static_cast<real>(a.sigma2_init);
+    real s2 = run_consts<real>(a).sigma2_init;
     real sig = M::sqrt(s2);
     real* const out = static_cast<real*>(a.samples);
     long long next_store = a.samples ? a.store_from : -1;
@@ -291,16 +301,17 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
     const real d = comp ? static_cast<real>(a.d[g]) : real(0);
     const real pull = comp ? static_cast<real>(a.pull[g]) : real(0);
     const real g_ols = comp ? static_cast<real>(a.g_ols[g]) : real(0);
-    const real rss_min = static_cast<real>(a.rss_min);
-    const real prior_scale = static_cast<real>(a.prior_scale);
-    const real sig_ref = static_cast<real>(a.sigma_ref);
-    const GammaConst<real> gc = make_gamma_const<real>(a.shape);
+    const RunConsts<real>& rc = run_consts<real>(a);
+    const real rss_min = rc.rss_min;
+    const real prior_scale = run_consts<real>(a).prior_scale;
+    const real sig_ref = run_consts<real>(a).sigma_ref;
+    const GammaConst<real> gc = gamma_const_of(run_consts<real>(a), a.gamma_boost);
 
     real acc1 = real(0), accs = real(0), acce = real(0), accee = real(0);
     real acc2[KP];
 #pragma unroll
     for (int c = 0; c < KP; ++c) acc2[c] = real(0);
-    real s2 = static_cast<real>(a.sigma2_init);
+    real s2 = run_consts<real>(a).sigma2_init;
     real sig = M::sqrt(s2);
     real* const out = static_cast<real*>(a.samples);
     const int total = static_cast<int>(a.iterations);
@@ -428,6 +439,9 @@ struct SimplexArgs {
     int stats_mode;
     double sigma_ref, sigma2_init;
     int* accepted;          // [n_chains] sampling-phase acceptances        (:135)
+    RunConsts<float> cf;    // scalars + Gamma constants in either arithmetic type (constant-bank operands)
+    RunConsts<double> cd;
+    int gamma_boost;
 };
 
 template <typename real, int KP, int MODE>
@@ -461,15 +475,15 @@ __global__ void __launch_bounds__(128) gibbs_simplex_kernel(const SimplexArgs a)
         b_ols[k] = k < a.k ? static_cast<real>(a.b_ols[k]) : real(0);
     }
     const real bias0 = static_cast<real>(1.0 / static_cast<double>(a.m));       // :78
-    const real prior_scale = static_cast<real>(a.prior_scale);
-    const real sig_ref = static_cast<real>(a.sigma_ref);
-    const GammaConst<real> gc = make_gamma_const<real>(a.shape);
+    const real prior_scale = run_consts<real>(a).prior_scale;
+    const real sig_ref = run_consts<real>(a).sigma_ref;
+    const GammaConst<real> gc = gamma_const_of(run_consts<real>(a), a.gamma_boost);
 
     // state: dc = b - b_ols (b starts at 0, :82), gdc = G dc, rss = RSS(b)
     real dc[KP], gdc[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) dc[k] = -b_ols[k];
-    real rss = static_cast<real>(a.rss_min);
+    real rss = run_consts<real>(a).rss_min;
 #pragma unroll UR
     for (int r = 0; r < KP; ++r) {
         real s = real(0);
@@ -478,27 +492,11 @@ __global__ void __launch_bounds__(128) gibbs_simplex_kernel(const SimplexArgs a)
         gdc[r] = s;
         rss = M::fma(s, dc[r], rss);
     }
-    real s2 = static_cast<real>(a.sigma2_init);                               // :86, RSS(0)/n
+    real s2 = run_consts<real>(a).sigma2_init;                               // :86, RSS(0)/n
 
-    // fp32: Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2) take two components at a time.
-    // With all cross moments, the 45 + 9 sums are kept as register pairs (30 instructions instead of 54 for
-    // K = 8): pair (i, c), c = 2i+1 .. KP, holds the products of e_2i and e_2i+1 with e_c (e_KP = sigma
-    // deviation); pair i of `dg` holds their squares.  Every half is the same rounding as the scalar form.
-    constexpr bool PACK2 = sizeof(real) == 4 && KP % 4 == 0;
-    constexpr bool PACK = sizeof(real) == 4 && MODE == 2 && KP % 2 == 0;
-    constexpr int H = KP / 2;
-    constexpr int NX = PACK ? H * KP - H * (H - 1) : 1;
-    f32x2 m1p[PACK ? H : 1], dg[PACK ? H : 1], cx[NX];
-    float m1s = 0.f, m2s = 0.f;
-    if (PACK) {
+    real acc[NS > 0 ? NS : 1];
 #pragma unroll
-        for (int i = 0; i < H; ++i) m1p[i] = dg[i] = 0ull;
-#pragma unroll
-        for (int j = 0; j < NX; ++j) cx[j] = 0ull;
-    }
-    real acc[(NS > 0 && !PACK) ? NS : 1];
-#pragma unroll
-    for (int j = 0; j < ((NS > 0 && !PACK) ? NS : 1); ++j) acc[j] = real(0);
+    for (int j = 0; j < (NS > 0 ? NS : 1); ++j) acc[j] = real(0);
     int n_acc = 0;
     real* const out = static_cast<real*>(a.samples);
     long long slot = 0;
@@ -655,9 +653,9 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group_kernel(const SimplexA
 #pragma unroll
     for (int c = 0; c < KP; ++c) grow[c] = (comp && c < a.k) ? static_cast<real>(a.gram[g * a.k + c]) : real(0);
     const real bias0 = static_cast<real>(1.0 / static_cast<double>(a.m));  // :78
-    const real prior_scale = static_cast<real>(a.prior_scale);
-    const real sig_ref = static_cast<real>(a.sigma_ref);
-    const GammaConst<real> gc = make_gamma_const<real>(a.shape);
+    const real prior_scale = run_consts<real>(a).prior_scale;
+    const real sig_ref = run_consts<real>(a).sigma_ref;
+    const GammaConst<real> gc = gamma_const_of(run_consts<real>(a), a.gamma_boost);
     // models g, g + 8 in registers; more (m > 16) are read from shared memory
     const int n_pass = mg / G;
     real vcol[RREG][KP];
@@ -676,8 +674,8 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group_kernel(const SimplexA
     real rss = comp ? gdc * dc : real(0);
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) rss += __shfl_xor_sync(0xffffffffu, rss, o, G);
-    rss += static_cast<real>(a.rss_min);
-    real s2 = static_cast<real>(a.sigma2_init);                           // :86
+    rss += run_consts<real>(a).rss_min;
+    real s2 = run_consts<real>(a).sigma2_init;                           // :86
 
     // moment sums of lane g: dc_g, dc_g * dc_c (c = 0..KP-1), dc_g * es, and (used from lane 0) es, es^2
     real acc1 = real(0), accs = real(0), acce = real(0), accee = real(0);

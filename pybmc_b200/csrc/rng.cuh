@@ -126,14 +126,24 @@ struct Math<float> {
         asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
         return mul2(pack2(rad, rad), pack2(cs, sn));
     }
-    static __device__ __forceinline__ float log(float x) { return __logf(x); }
+    // natural log of a positive normal number: lg2.approx.ftz * ln 2 (what __logf does, minus its
+    // denormal fix-up instructions)
+    static __device__ __forceinline__ float log(float x) {
+        float l2;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(x));
+        return l2 * 0.6931471805599453f;
+    }
     static __device__ __forceinline__ float exp(float x) { return __expf(x); }
     static __device__ __forceinline__ float sqrt(float x) {
         float r;
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
         return r;
     }
-    static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float rsqrt(float x) {       // arguments are never denormal here
+        float r;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
     static __device__ __forceinline__ float rcp(float x) {
         float r;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -204,6 +214,31 @@ __host__ __device__ inline GammaConst<real> make_gamma_const(double shape) {
     return g;
 }
 
+// Scalar constants of a sampler run in the arithmetic type of the kernel.  They travel in the kernel
+// parameters (constant bank), so the loop uses them as instruction operands: no registers, and no
+// per-iteration fp64 -> fp32 conversions when the compiler rematerialises them.
+template <typename T>
+struct RunConsts {
+    T rss_min, prior_scale, sigma_ref, sigma2_init;
+    T gamma_d, gamma_c, gamma_inv_shape;
+};
+template <typename T>
+inline RunConsts<T> make_run_consts(double rss_min, double prior_scale, double sigma_ref, double sigma2_init,
+                                    double shape) {
+    const GammaConst<T> g = make_gamma_const<T>(shape);
+    return RunConsts<T>{static_cast<T>(rss_min), static_cast<T>(prior_scale), static_cast<T>(sigma_ref),
+                        static_cast<T>(sigma2_init), g.d, g.c, g.inv_shape};
+}
+template <typename T>
+__device__ __forceinline__ GammaConst<T> gamma_const_of(const RunConsts<T>& c, int boost) {
+    GammaConst<T> g;
+    g.d = c.gamma_d;
+    g.c = c.gamma_c;
+    g.inv_shape = c.gamma_inv_shape;
+    g.boost = boost;
+    return g;
+}
+
 // ---- Gamma(shape, 1) by Marsaglia & Tsang (2000) -------------------------------------------------
 // Variates used: a standard normal x and a uniform u per attempt.  The FIRST attempts of iterations
 // 2m and 2m+1 share one Philox block, (2m, kBlockGamma): the even iteration takes the cosine branch of
@@ -228,19 +263,19 @@ __device__ __forceinline__ GammaPair<real> gamma_pair(uint32_t it_even, uint32_t
     return p;
 }
 
-// accept / reject one proposal; on acceptance v holds (1 + c x)^3
+// accept / reject one proposal; on acceptance v holds (1 + c x)^3.  Squeeze and full test are both
+// evaluated (a warp nearly always has a lane that needs the full test) and combined without branches.
 template <typename real>
 __device__ __forceinline__ bool gamma_accept(const GammaConst<real>& g, real x, real u, real& v) {
     using M = Math<real>;
-    v = M::fma(g.c, x, real(1));
-    if (v <= real(0)) {
-        v = real(1);
-        return false;
-    }
-    v = v * v * v;
+    const real t = M::fma(g.c, x, real(1));
+    const real v3 = t * t * t;
     const real x2 = x * x;
-    if (u < real(1) - real(0.0331) * x2 * x2) return true;                 // squeeze: almost always
-    return M::log(u) < real(0.5) * x2 + g.d * (real(1) - v + M::log(v));
+    const bool squeeze = u < real(1) - real(0.0331) * x2 * x2;                 // almost always
+    const bool full = M::log(u) < real(0.5) * x2 + g.d * (real(1) - v3 + M::log(v3));   // NaN (t <= 0): false
+    const bool ok = (t > real(0)) & (squeeze | full);
+    v = ok ? v3 : real(1);
+    return ok;
 }
 
 // rejections are rare: out of line, keys rebuilt from the seed

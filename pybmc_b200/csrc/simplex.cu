@@ -121,6 +121,9 @@ int bmc_gibbs_simplex_run(int dtype, const bmc_simplex_problem* p, uint64_t seed
     a.prior_scale = p->nu0 * p->sigma20;                     // :116 / :139
     a.sigma2_init = p->rss_zero / p->n_obs;                  // :86
     a.sigma_ref = sqrt(a.sigma2_init > 0 ? a.sigma2_init : 1.0);
+    a.cf = make_run_consts<float>(a.rss_min, a.prior_scale, a.sigma_ref, a.sigma2_init, a.shape);
+    a.cd = make_run_consts<double>(a.rss_min, a.prior_scale, a.sigma_ref, a.sigma2_init, a.shape);
+    a.gamma_boost = a.shape < 1.0;
     a.key0 = static_cast<uint32_t>(seed);
     a.key1 = static_cast<uint32_t>(seed >> 32);
     a.chain0 = chain0;
