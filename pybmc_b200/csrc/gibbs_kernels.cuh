@@ -37,6 +37,7 @@ struct GibbsArgs {
     RunConsts<double> cd;
     int gamma_boost;                      // shape < 1
     uint32_t key0, key1;
+    PhiloxKeys keys;                      // the ten round keys of (key0, key1): constant-bank operands in the kernels
     unsigned long long chain0;            // global id of this launch's first chain
     long long n_chains;
     long long iterations;
@@ -78,9 +79,9 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     }
     const RunConsts<real>& rc = run_consts<real>(a);
     const real rss_min = rc.rss_min;
-    const real prior_scale = run_consts<real>(a).prior_scale;
-    const real sig_ref = run_consts<real>(a).sigma_ref;
-    const GammaConst<real> gc = gamma_const_of(run_consts<real>(a), a.gamma_boost);
+    const real prior_scale = rc.prior_scale;
+    const real sig_ref = rc.sigma_ref;
+    const GammaConst<real> gc = gamma_const_of(rc, a.gamma_boost);
 
     // fp32: Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2) take two components at a time.
     // With all cross moments, the 45 + 9 sums are kept as register pairs (30 instructions instead of 54 for
@@ -101,90 +102,128 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     real acc[(NS > 0 && !PACK) ? NS : 1];
 #pragma unroll
     for (int j = 0; j < ((NS > 0 && !PACK) ? NS : 1); ++j) acc[j] = real(0);
+    auto row_of = [&](int r, int c) { return D + r * D - r * (r - 1) / 2 + (c - r); };
+    auto flush = [&](int row, real v) {
+        double* p = a.chain_stats + static_cast<long long>(row) * a.n_chains + tid;
+        *p += static_cast<double>(v);
+    };
 
-    real s2 = run_consts<real>(a).sigma2_init;
+    real s2 = rc.sigma2_init;
     real sig = M::sqrt(s2);
+    real e[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) e[k] = real(0);
     real* const out = static_cast<real*>(a.samples);
+    const uint32_t total = static_cast<uint32_t>(a.iterations);          // < 2^32 (checked by the host)
     long long next_store = a.samples ? a.store_from : -1;
     long long slot = 0;
 
     GammaPair<real> gp;                                 // first Gamma proposals of iterations 2m, 2m+1
     gp.x[1] = real(0);
     gp.u[1] = real(1);
-    for (long long it = 0; it < a.iterations; ++it) {
-        const uint32_t it32 = static_cast<uint32_t>(it);
-        const bool odd = (it32 & 1u) != 0u;
-        if (!odd) gp = gamma_pair<real>(it32, chain, kTagGibbs, philox_keys(a.key0, a.key1));   // every other iteration
-        real e[KP];
-        real rss0 = rss_min, rss1 = real(0);
-        if constexpr (PACK2) {
-            // two components at a time on packed fp32 instructions (same roundings as the scalar form below)
-            f32x2 rssp = pack2(rss_min, 0.f);
-            const f32x2 s2b = pack2(s2, s2), sigb = pack2(sig, sig);
+    // The iterations run in segments that end where something other than arithmetic happens (a flush
+    // of the moment sums every kFlushEvery iterations, a kept draw, the end): the inner loop is pure
+    // arithmetic with one 32-bit counter.
+    uint32_t it32 = 0;
+    while (it32 < total) {
+        uint32_t seg_end = (it32 | static_cast<uint32_t>(kFlushEvery - 1)) + 1u;
+        if (seg_end > total || seg_end == 0u) seg_end = total;
+        if (next_store >= static_cast<long long>(it32) && next_store < static_cast<long long>(seg_end))
+            seg_end = static_cast<uint32_t>(next_store) + 1u;
+        for (; it32 < seg_end; ++it32) {
+            const bool odd = (it32 & 1u) != 0u;
+            if (!odd) gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);           // every other iteration
+            real rss0 = rss_min, rss1 = real(0);
+            if constexpr (PACK2) {
+                // two components at a time on packed fp32 instructions (same roundings as the scalar form)
+                f32x2 rssp = pack2(rss_min, 0.f);
+                const f32x2 s2b = pack2(s2, s2), sigb = pack2(sig, sig);
 #pragma unroll
-            for (int j = 0; j < KP / 4; ++j) {
-                const Philox4 r = philox4x32_10(it32, static_cast<uint32_t>(j), chain, kTagGibbs, a.key0, a.key1);
-                const f32x2 zp[2] = {M::box_muller2(r.x, r.y), M::box_muller2(r.z, r.w)};
+                for (int j = 0; j < KP / 4; ++j) {
+                    const Philox4 r = philox4x32_10(it32, static_cast<uint32_t>(j), chain, kTagGibbs, a.keys);
+                    const f32x2 zp[2] = {M::box_muller2(r.x, r.y), M::box_muller2(r.z, r.w)};
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int k = 4 * j + 2 * h;
-                    const f32x2 dp = pack2(d[k], d[k + 1]);
-                    float t0, t1;
-                    unpack2(add2(dp, s2b), t0, t1);
-                    const f32x2 sdp = mul2(pack2(M::rsqrt(t0), M::rsqrt(t1)), sigb);
-                    const f32x2 ep = mul2(sdp, fma2(pack2(pull[k], pull[k + 1]), sdp, zp[h]));
-                    rssp = fma2(mul2(dp, ep), ep, rssp);
-                    unpack2(ep, e[k], e[k + 1]);
+                    for (int h = 0; h < 2; ++h) {
+                        const int k = 4 * j + 2 * h;
+                        const f32x2 dp = pack2(d[k], d[k + 1]);
+                        float t0, t1;
+                        unpack2(add2(dp, s2b), t0, t1);
+                        const f32x2 sdp = mul2(pack2(M::rsqrt(t0), M::rsqrt(t1)), sigb);
+                        const f32x2 ep = mul2(sdp, fma2(pack2(pull[k], pull[k + 1]), sdp, zp[h]));
+                        rssp = fma2(mul2(dp, ep), ep, rssp);
+                        unpack2(ep, e[k], e[k + 1]);
+                    }
+                }
+                unpack2(rssp, rss0, rss1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < (KP + 3) / 4; ++j) {
+                    real z[4];
+                    normals4_k<real>(it32, static_cast<uint32_t>(j), chain, kTagGibbs, a.keys, z);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = 4 * j + q;
+                        if (k < KP) {
+                            // 1/sqrt(p_k) = sigma / sqrt(d_k + s2): one MUFU on the s2 -> e -> RSS -> s2 dependency
+                            const real sd = sig * M::rsqrt(d[k] + s2);
+                            e[k] = sd * M::fma(pull[k], sd, z[q]);          // pull/p + z/sqrt(p)
+                            if (k & 1) rss1 = M::fma(d[k] * e[k], e[k], rss1);
+                            else rss0 = M::fma(d[k] * e[k], e[k], rss0);
+                        }
+                    }
                 }
             }
-            unpack2(rssp, rss0, rss1);
-        } else {
+            const real scale = real(0.5) * (prior_scale + (rss0 + rss1));
+            const real gm = gamma_from_first<real>(gc, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0], it32,
+                                                  chain, kTagGibbs, a.key0, a.key1);
+            s2 = M::div(scale, gm);
+            s2 = s2 > real(1e-6) ? s2 : real(1e-6);
+            sig = M::sqrt(s2);
+
+            if constexpr (PACK) {
+                const float es = sig - sig_ref;
+                const f32x2 esb = pack2(es, es);
 #pragma unroll
-            for (int j = 0; j < (KP + 3) / 4; ++j) {
-                real z[4];
-                normals4<real>(it32, static_cast<uint32_t>(j), chain, kTagGibbs, a.key0, a.key1, z);
+                for (int i = 0; i < H; ++i) {
+                    const f32x2 ep = pack2(e[2 * i], e[2 * i + 1]);
+                    m1p[i] = add2(m1p[i], ep);
+                    dg[i] = fma2(ep, ep, dg[i]);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k = 4 * j + q;
-                    if (k < KP) {
-                        // 1/sqrt(p_k) = sigma / sqrt(d_k + s2): one MUFU on the s2 -> e -> RSS -> s2 dependency
-                        const real sd = sig * M::rsqrt(d[k] + s2);
-                        e[k] = sd * M::fma(pull[k], sd, z[q]);          // pull/p + z/sqrt(p)
-                        if (k & 1) rss1 = M::fma(d[k] * e[k], e[k], rss1);
-                        else rss0 = M::fma(d[k] * e[k], e[k], rss0);
+                    for (int c = 2 * i + 1; c <= KP; ++c) {
+                        const int j = i * KP - i * (i - 1) + (c - 2 * i - 1);
+                        cx[j] = fma2(ep, c < KP ? pack2(e[c < KP ? c : 0], e[c < KP ? c : 0]) : esb, cx[j]);
+                    }
+                }
+                m1s += es;
+                m2s = fmaf(es, es, m2s);
+            } else if (MODE != 0) {
+                const real es = sig - sig_ref;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) acc[k] += e[k];
+                acc[KP] += es;
+                if (MODE == 1) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) acc[D + k] = M::fma(e[k], e[k], acc[D + k]);
+                    acc[D + KP] = M::fma(es, es, acc[D + KP]);
+                } else {
+                    int idx = D;
+#pragma unroll
+                    for (int r = 0; r < D; ++r) {
+                        const real er = r < KP ? e[r < KP ? r : 0] : es;
+#pragma unroll
+                        for (int c = r; c < D; ++c) {
+                            const real ec = c < KP ? e[c < KP ? c : 0] : es;
+                            acc[idx] = M::fma(er, ec, acc[idx]);
+                            ++idx;
+                        }
                     }
                 }
             }
         }
-        const real scale = real(0.5) * (prior_scale + (rss0 + rss1));
-        const real gm = gamma_from_first<real>(gc, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0], it32, chain,
-                                              kTagGibbs, a.key0, a.key1);
-        s2 = M::div(scale, gm);
-        s2 = s2 > real(1e-6) ? s2 : real(1e-6);
-        sig = M::sqrt(s2);
 
-        if constexpr (PACK) {
-            const float es = sig - sig_ref;
-            const f32x2 esb = pack2(es, es);
-            auto row_of = [&](int r, int c) { return D + r * D - r * (r - 1) / 2 + (c - r); };
-#pragma unroll
-            for (int i = 0; i < H; ++i) {
-                const f32x2 ep = pack2(e[2 * i], e[2 * i + 1]);
-                m1p[i] = add2(m1p[i], ep);
-                dg[i] = fma2(ep, ep, dg[i]);
-#pragma unroll
-                for (int c = 2 * i + 1; c <= KP; ++c) {
-                    const int j = i * KP - i * (i - 1) + (c - 2 * i - 1);
-                    cx[j] = fma2(ep, c < KP ? pack2(e[c < KP ? c : 0], e[c < KP ? c : 0]) : esb, cx[j]);
-                }
-            }
-            m1s += es;
-            m2s = fmaf(es, es, m2s);
-            if (((it + 1) % kFlushEvery) == 0 || it + 1 == a.iterations) {
-                auto flush = [&](int row, float v) {
-                    double* p = a.chain_stats + static_cast<long long>(row) * a.n_chains + tid;
-                    *p += static_cast<double>(v);
-                };
+        // ---- end of a segment: it32 iterations are done
+        if (MODE != 0 && ((it32 & static_cast<uint32_t>(kFlushEvery - 1)) == 0u || it32 == total)) {
+            if constexpr (PACK) {
 #pragma unroll
                 for (int i = 0; i < H; ++i) {
                     float lo, hi;
@@ -206,40 +245,15 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 flush(KP, m1s);
                 flush(row_of(KP, KP), m2s);
                 m1s = m2s = 0.f;
-            }
-        } else if (MODE != 0) {
-            const real es = sig - sig_ref;
-#pragma unroll
-            for (int k = 0; k < KP; ++k) acc[k] += e[k];
-            acc[KP] += es;
-            if (MODE == 1) {
-#pragma unroll
-                for (int k = 0; k < KP; ++k) acc[D + k] = M::fma(e[k], e[k], acc[D + k]);
-                acc[D + KP] = M::fma(es, es, acc[D + KP]);
             } else {
-                int idx = D;
-#pragma unroll
-                for (int r = 0; r < D; ++r) {
-                    const real er = r < KP ? e[r < KP ? r : 0] : es;
-#pragma unroll
-                    for (int c = r; c < D; ++c) {
-                        const real ec = c < KP ? e[c < KP ? c : 0] : es;
-                        acc[idx] = M::fma(er, ec, acc[idx]);
-                        ++idx;
-                    }
-                }
-            }
-            if (((it + 1) % kFlushEvery) == 0 || it + 1 == a.iterations) {
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
-                    double* p = a.chain_stats + static_cast<long long>(j) * a.n_chains + tid;
-                    *p += static_cast<double>(acc[j]);
+                    flush(j, acc[j]);
                     acc[j] = real(0);
                 }
             }
         }
-
-        if (it == next_store) {
+        if (static_cast<long long>(it32) - 1 == next_store) {
             // b = W (g_ols + e);  row layout [slot][component][chain] keeps lanes coalesced
             real* row = out + (slot * static_cast<long long>(a.k + 1)) * a.n_chains + tid;
             if (a.dense_w) {
