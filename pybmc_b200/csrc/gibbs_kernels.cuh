@@ -130,9 +130,8 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         if (seg_end > total || seg_end == 0u) seg_end = total;
         if (next_store >= static_cast<long long>(it32) && next_store < static_cast<long long>(seg_end))
             seg_end = static_cast<uint32_t>(next_store) + 1u;
-        for (; it32 < seg_end; ++it32) {
-            const bool odd = (it32 & 1u) != 0u;
-            if (!odd) gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);           // every other iteration
+        // one iteration; (gx, gu) = the first Gamma proposal of this iteration
+        auto iterate = [&](const uint32_t it32, const real gx, const real gu) {
             real rss0 = rss_min, rss1 = real(0);
             if constexpr (PACK2) {
                 // two components at a time on packed fp32 instructions (same roundings as the scalar form)
@@ -174,8 +173,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 }
             }
             const real scale = real(0.5) * (prior_scale + (rss0 + rss1));
-            const real gm = gamma_from_first<real>(gc, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0], it32,
-                                                  chain, kTagGibbs, a.key0, a.key1);
+            const real gm = gamma_from_first<real>(gc, gx, gu, it32, chain, kTagGibbs, a.key0, a.key1);
             s2 = M::div(scale, gm);
             s2 = s2 > real(1e-6) ? s2 : real(1e-6);
             sig = M::sqrt(s2);
@@ -218,6 +216,31 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                         }
                     }
                 }
+            }
+        };
+        // iterations 2m and 2m+1 share one Gamma proposal block.  fp32 walks them in pairs where the segment
+        // allows: the Philox rounds of 2m+1 then sit in the same basic block as the MUFU work of 2m and
+        // overlap with it (9.98 -> 9.32 ms); fp64 has no registers to spare for that and is faster one by one.
+        if constexpr (sizeof(real) == 4) {
+            if ((it32 & 1u) != 0u) {
+                iterate(it32, gp.x[1], gp.u[1]);
+                ++it32;
+            }
+            for (; it32 + 1u < seg_end; it32 += 2u) {
+                gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);
+                iterate(it32, gp.x[0], gp.u[0]);
+                iterate(it32 + 1u, gp.x[1], gp.u[1]);
+            }
+            if (it32 < seg_end) {
+                gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);
+                iterate(it32, gp.x[0], gp.u[0]);
+                ++it32;
+            }
+        } else {
+            for (; it32 < seg_end; ++it32) {
+                const bool odd = (it32 & 1u) != 0u;
+                if (!odd) gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);
+                iterate(it32, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0]);
             }
         }
 
