@@ -30,6 +30,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         "r"(phase)
         : "memory");
 }
+// The same wait for a thread that has nothing else to do (a producer lane): back off between polls so the
+// spin does not take issue slots from the warps doing the arithmetic on the same scheduler.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t phase, uint32_t ns = 64) {
+    const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(phase)
+            : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
 // 1-D bulk copy global -> shared through the TMA unit (UBLKCP in SASS); bytes % 16 == 0.
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile(
