@@ -349,6 +349,10 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         a.noise_mode = p->noise_mode;
         a.key0 = static_cast<uint32_t>(p->seed);
         a.key1 = static_cast<uint32_t>(p->seed >> 32);
+        for (int r = 0; r < 10; ++r) {
+            a.keys.k0[r] = a.key0 + static_cast<uint32_t>(r) * kPhiloxW0;
+            a.keys.k1[r] = a.key1 + static_cast<uint32_t>(r) * kPhiloxW1;
+        }
         a.noise = p->noise ? static_cast<const unsigned char*>(p->noise) + static_cast<size_t>(c0) * sz : nullptr;
         a.ld_noise = p->ld_noise;
         a.nq = p->nq;

@@ -56,6 +56,7 @@ struct PredictArgs {
     // noise
     int noise_mode;           // 0 none, 1 philox, 2 external
     uint32_t key0, key1;
+    PhiloxKeys keys;          // round keys of (key0, key1): constant-bank operands of the Philox rounds
     const void* noise;        // [n_draws][ld_noise] real
     long long ld_noise;
     // windows / results, indexed [n * nq + j]
@@ -169,14 +170,14 @@ __device__ __forceinline__ void lane_init(const PredictArgs& a, const LaneCtx& c
 }
 
 // x[0..3] are draws s .. s+3 of nucleus c.n (FLT_MAX = no such draw)
-template <typename real, int NQ>
+template <typename real, int NQ, bool FULL = false>
 __device__ __forceinline__ void consume4(const PredictArgs& a, const LaneCtx& c, LaneAcc<real, NQ>& st,
                                          const real (&x)[4], long long s, real tc, real ctr) {
     using M = Math<real>;
     if (a.first) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const bool valid = x[r] < real(FLT_MAX);
+            const bool valid = FULL || x[r] < real(FLT_MAX);      // FULL: all four draws exist, no padding marks
             const real dv = valid ? x[r] - ctr : real(0);
             st.sx += dv;
             st.sxx = M::fma(dv, dv, st.sxx);

@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(kTcThreads + 32, 1) predict_pass_tc_kernel(con
             const uint32_t tcol = tmem_base + (static_cast<uint32_t>(32 * quarter) << 16) +
                                   static_cast<uint32_t>(st * kTcTile + 32 * colgrp);
             const long long s0 = s_begin + static_cast<long long>(t) * kTcTile + 32 * colgrp;
+            const int rem = static_cast<int>(min(s_end - s0, static_cast<long long>(32)));   // draws of this warp's columns
             const float* sig =
                 reinterpret_cast<const float*>(img + (tile0 + t) * IM::kStride + IM::kTileBytes) + 32 * colgrp;
             // eight draws at a time, rolled: the loop body stays small enough for the instruction cache
@@ -294,8 +295,26 @@ __global__ void __launch_bounds__(kTcThreads + 32, 1) predict_pass_tc_kernel(con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[st]);
                 }
-                if (s0 + g >= s_end) continue;                              // warp-uniform
-                // two Philox calls side by side: independent chains for the scheduler to interleave
+                if (g >= rem) continue;                                     // warp-uniform
+                if (g + 8 <= rem && a.noise_mode == 1) {
+                    // the common case: eight real draws.  Two Philox calls side by side (independent chains
+                    // for the scheduler to interleave), Box-Muller and x = xs + sigma z on packed fp32 pairs.
+                    const uint32_t blk = static_cast<uint32_t>((s0 + g) >> 2);
+                    const Philox4 ra = philox4x32_10(blk, nglob, 0u, kTagNoise, a.keys);
+                    const Philox4 rb = philox4x32_10(blk + 1u, nglob, 0u, kTagNoise, a.keys);
+                    const float4 s_a = *reinterpret_cast<const float4*>(sig + g);
+                    const float4 s_b = *reinterpret_cast<const float4*>(sig + g + 4);
+                    float x[8];
+                    unpack2(fma2(pack2(s_a.x, s_a.y), Math<float>::box_muller2(ra.x, ra.y), pack2(xs[0], xs[1])), x[0], x[1]);
+                    unpack2(fma2(pack2(s_a.z, s_a.w), Math<float>::box_muller2(ra.z, ra.w), pack2(xs[2], xs[3])), x[2], x[3]);
+                    unpack2(fma2(pack2(s_b.x, s_b.y), Math<float>::box_muller2(rb.x, rb.y), pack2(xs[4], xs[5])), x[4], x[5]);
+                    unpack2(fma2(pack2(s_b.z, s_b.w), Math<float>::box_muller2(rb.z, rb.w), pack2(xs[6], xs[7])), x[6], x[7]);
+                    const float xa[4] = {x[0], x[1], x[2], x[3]}, xb[4] = {x[4], x[5], x[6], x[7]};
+                    consume4<float, NQ, true>(a, c, acc, xa, s0 + g, tc, ctr);
+                    consume4<float, NQ, true>(a, c, acc, xb, s0 + g + 4, tc, ctr);
+                    continue;
+                }
+                // tail of the draw range, or a pass without noise
                 float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 float sg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (a.noise_mode == 1) {
@@ -305,8 +324,8 @@ __global__ void __launch_bounds__(kTcThreads + 32, 1) predict_pass_tc_kernel(con
                     sg[4] = s_b.x; sg[5] = s_b.y; sg[6] = s_b.z; sg[7] = s_b.w;
                     float za[4], zb[4];
                     const uint32_t blk = static_cast<uint32_t>((s0 + g) >> 2);
-                    normals4<float>(blk, nglob, 0u, kTagNoise, a.key0, a.key1, za);
-                    normals4<float>(blk + 1u, nglob, 0u, kTagNoise, a.key0, a.key1, zb);
+                    normals4_k<float>(blk, nglob, 0u, kTagNoise, a.keys, za);
+                    normals4_k<float>(blk + 1u, nglob, 0u, kTagNoise, a.keys, zb);
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         z[r] = za[r];
@@ -315,15 +334,14 @@ __global__ void __launch_bounds__(kTcThreads + 32, 1) predict_pass_tc_kernel(con
                 }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const long long s = s0 + g + 4 * h;
-                    if (s < s_end) {
+                    if (g + 4 * h < rem) {
                         float x[4];
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
                             x[r] = fmaf(sg[4 * h + r], z[4 * h + r], xs[4 * h + r]);
-                            if (s + r >= s_end) x[r] = FLT_MAX;
+                            if (g + 4 * h + r >= rem) x[r] = FLT_MAX;
                         }
-                        consume4<float, NQ>(a, c, acc, x, s, tc, ctr);
+                        consume4<float, NQ>(a, c, acc, x, s0 + g + 4 * h, tc, ctr);
                     }
                 }
             }
