@@ -115,6 +115,53 @@ __global__ void probe_single(long long iters, float* sink) {
     if (s == 0x12345678u) sink[0] = static_cast<float>(s);
 }
 
+// Mixed streams: per chain and iteration W x IMAD.WIDE, F x FFMA, F2 x FFMA2 (packed fp32 pair), M x MUFU,
+// L x LOP3, all independent across chains.  Shows which instruction classes share a pipe on this part
+// (e.g. whether FFMA keeps flowing while IMAD.WIDE holds the heavy half of the FMA pipe).
+template <int W, int F, int F2, int M, int L>
+__global__ void probe_mix(long long iters, float* sink) {
+    unsigned int a[kChains], b[kChains];
+    float f[kChains], g[kChains];
+    unsigned long long h[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        a[i] = threadIdx.x * 2654435761u + i;
+        b[i] = a[i] ^ 0x9E3779B9u;
+        f[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+        g[i] = 0.5f + 1e-3f * (threadIdx.x + i);
+        h[i] = (static_cast<unsigned long long>(__float_as_uint(f[i])) << 32) | __float_as_uint(g[i]);
+    }
+    const float m = 0.999999f, c = 1e-7f;
+    const unsigned long long m2 = (static_cast<unsigned long long>(__float_as_uint(m)) << 32) | __float_as_uint(m);
+    const unsigned long long c2 = (static_cast<unsigned long long>(__float_as_uint(c)) << 32) | __float_as_uint(c);
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+#pragma unroll
+            for (int r = 0; r < W; ++r) {
+                unsigned long long p;
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a[i]), "r"(0xD2511F53u));
+                a[i] = static_cast<unsigned int>(p >> 32);
+                b[i] = static_cast<unsigned int>(p);
+            }
+#pragma unroll
+            for (int r = 0; r < F; ++r) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(m), "f"(c));
+#pragma unroll
+            for (int r = 0; r < F2; ++r) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(h[i]) : "l"(m2), "l"(c2));
+#pragma unroll
+            for (int r = 0; r < M; ++r) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(g[i]));
+#pragma unroll
+            for (int r = 0; r < L; ++r)
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(a[(i + 1) % kChains]), "r"(0x9E3779B9u));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i)
+        s += f[i] + g[i] + static_cast<float>((a[i] ^ b[i]) & 1u) + static_cast<float>(h[i] & 1ull);
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -127,12 +174,20 @@ int bmc_probe_ops_per_iteration(int kind) {
         case 2: return 2 * kChains;      // IMAD.WIDE + LOP3
         case 3: return 2 * kChains;      // FFMA + LOP3
         case 4: case 5: case 6: case 7: return kChains;   // IMAD.WIDE(+IADD) / IMAD.HI / IMAD / LOP3 alone
+        case 8: return kChains;          // FFMA2 alone (one packed instruction = two fp32 FMAs)
+        case 9: return kChains;          // IMAD.WIDE alone
+        case 10: return 2 * kChains;     // IMAD.WIDE + FFMA
+        case 11: return 3 * kChains;     // IMAD.WIDE + 2 FFMA
+        case 12: return 2 * kChains;     // IMAD.WIDE + FFMA2
+        case 13: return 5 * kChains;     // MUFU + 4 FFMA
+        case 14: return 3 * kChains;     // MUFU + 2 IMAD.WIDE
+        case 15: return 2 * kChains;     // FFMA2 + FFMA
         default: return 0;
     }
 }
 
 int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, void* stream) {
-    BMC_REQUIRE(kind >= 0 && kind <= 7 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink,
+    BMC_REQUIRE(kind >= 0 && kind <= 15 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink,
                 "bmc_probe: bad arguments");
     cudaStream_t st = bmc::as_stream(stream);
     switch (kind) {
@@ -143,7 +198,15 @@ int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, voi
         case 4: probe_single<0><<<blocks, threads, 0, st>>>(iters, sink); break;
         case 5: probe_single<1><<<blocks, threads, 0, st>>>(iters, sink); break;
         case 6: probe_single<2><<<blocks, threads, 0, st>>>(iters, sink); break;
-        default: probe_single<3><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 7: probe_single<3><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 8: probe_mix<0, 0, 1, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 9: probe_mix<1, 0, 0, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 10: probe_mix<1, 1, 0, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 11: probe_mix<1, 2, 0, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 12: probe_mix<1, 0, 1, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 13: probe_mix<0, 4, 0, 1, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 14: probe_mix<2, 0, 0, 1, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        default: probe_mix<0, 1, 1, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
     }
     BMC_LAUNCH_CHECK();
     return BMC_OK;
