@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         // iterations 2m and 2m+1 share one Gamma proposal block.  fp32 walks them in pairs where the segment
         // allows: the Philox rounds of 2m+1 then sit in the same basic block as the MUFU work of 2m and
         // overlap with it (9.98 -> 9.32 ms); fp64 has no registers to spare for that and is faster one by one.
-        if constexpr (sizeof(real) == 4) {
+        if constexpr (sizeof(real) == 4 && KP <= 16) {
             if ((it32 & 1u) != 0u) {
                 iterate(it32, gp.x[1], gp.u[1]);
                 ++it32;
@@ -365,12 +365,12 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
 #pragma unroll
             for (int b = 0; b < (KP + 3) / 4; ++b) {
                 real z[4];
-                normals4<real>(it32, static_cast<uint32_t>(b), chain, kTagGibbs, a.key0, a.key1, z);
+                normals4_k<real>(it32, static_cast<uint32_t>(b), chain, kTagGibbs, a.keys, z);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     if (4 * b + q < KP) row[4 * b + q] = z[q];
             }
-            row[KP] = gamma_unit_scale<real>(gc, it32, chain, kTagGibbs, a.key0, a.key1);
+            row[KP] = gamma_unit_scale<real>(gc, it32, chain, kTagGibbs, a.keys, a.key0, a.key1);
         }
         __syncwarp();
         // ---- phase 2: the state updates, in order (:41-52)
@@ -467,6 +467,7 @@ struct SimplexArgs {
     int k, m;
     double rss_min, shape, prior_scale;
     uint32_t key0, key1;
+    PhiloxKeys keys;        // round keys of (key0, key1)
     unsigned long long chain0;
     long long n_chains;
     long long burn, iterations;
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(128) gibbs_simplex_kernel(const SimplexArgs a)
 #pragma unroll
         for (int j = 0; j < (KP + 3) / 4; ++j) {
             real z[4];
-            normals4<real>(it32, static_cast<uint32_t>(j), chain, kTagSimplex, a.key0, a.key1, z);
+            normals4_k<real>(it32, static_cast<uint32_t>(j), chain, kTagSimplex, a.keys, z);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 if (4 * j + q < KP) delta[4 * j + q] = step[4 * j + q] * z[q];           // :98 / :121
@@ -580,7 +581,7 @@ __global__ void __launch_bounds__(128) gibbs_simplex_kernel(const SimplexArgs a)
             gdelta[r] = s;
             diff = M::fma(delta[r], M::fma(real(2), gdc[r], s), diff);
         }
-        const real u = M::u01(philox4x32_10(it32, kBlockUniform, chain, kTagSimplex, a.key0, a.key1).x);
+        const real u = M::u01(philox4x32_10(it32, kBlockUniform, chain, kTagSimplex, a.keys).x);
         // min(1, exp((ll' - ll)/s2)) with ll = -RSS: note no factor 1/2 (:108 / :130)
         const real alpha = M::exp(M::div(-diff, s2));
         const bool accept = feasible && (u < fmin(real(1), alpha));
@@ -594,7 +595,7 @@ __global__ void __launch_bounds__(128) gibbs_simplex_kernel(const SimplexArgs a)
             n_acc += it >= a.burn ? 1 : 0;
         }
         const real scale = real(0.5) * (prior_scale + rss);                              // :116 / :139
-        const real gm = gamma_unit_scale<real>(gc, it32, chain, kTagSimplex, a.key0, a.key1);
+        const real gm = gamma_unit_scale<real>(gc, it32, chain, kTagSimplex, a.keys, a.key0, a.key1);
         s2 = M::div(scale, gm);                                                          // no floor (:117)
         if (it < a.burn) continue;
         const real sig = M::sqrt(s2);
@@ -780,13 +781,13 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group_kernel(const SimplexA
 #pragma unroll
             for (int b = 0; b < (KP + 3) / 4; ++b) {
                 real z[4];
-                normals4<real>(it32, static_cast<uint32_t>(b), chain, kTagSimplex, a.key0, a.key1, z);
+                normals4_k<real>(it32, static_cast<uint32_t>(b), chain, kTagSimplex, a.keys, z);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     if (4 * b + q < KP) row[4 * b + q] = z[q];
             }
-            row[KP] = M::u01(philox4x32_10(it32, kBlockUniform, chain, kTagSimplex, a.key0, a.key1).x);
-            row[KP + 1] = gamma_unit_scale<real>(gc, it32, chain, kTagSimplex, a.key0, a.key1);
+            row[KP] = M::u01(philox4x32_10(it32, kBlockUniform, chain, kTagSimplex, a.keys).x);
+            row[KP + 1] = gamma_unit_scale<real>(gc, it32, chain, kTagSimplex, a.keys, a.key0, a.key1);
         }
         __syncwarp();
         // ---- phase 2: the state updates, in order

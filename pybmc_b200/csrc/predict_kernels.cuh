@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kPredWarps * 32) predict_pass_kernel(const Pre
             const long long s = s0 + g;
             if (a.noise_mode == 1) {
                 real z[4];
-                normals4<real>(static_cast<uint32_t>(s >> 2), nglob, 0u, kTagNoise, a.key0, a.key1, z);
+                normals4_k<real>(static_cast<uint32_t>(s >> 2), nglob, 0u, kTagNoise, a.keys, z);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) x[r] = M::fma(sigma[r], z[r], x[r]);
             } else if (a.noise_mode == 2 && live) {

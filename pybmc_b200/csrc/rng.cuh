@@ -306,6 +306,13 @@ __device__ __forceinline__ real gamma_from_first(const GammaConst<real>& g, real
 // stand-alone draw for iteration `it` (kernels that do not walk the iterations in order)
 template <typename real>
 __device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
+                                                 uint32_t tag, const PhiloxKeys& ks, uint32_t k0, uint32_t k1) {
+    const GammaPair<real> p = gamma_pair<real>(it & ~1u, chain, tag, ks);
+    const int odd = static_cast<int>(it & 1u);
+    return gamma_from_first<real>(g, odd ? p.x[1] : p.x[0], odd ? p.u[1] : p.u[0], it, chain, tag, k0, k1);
+}
+template <typename real>
+__device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
                                                  uint32_t tag, uint32_t k0, uint32_t k1) {
     const GammaPair<real> p = gamma_pair<real>(it & ~1u, chain, tag, philox_keys(k0, k1));
     const int odd = static_cast<int>(it & 1u);

@@ -126,6 +126,10 @@ int bmc_gibbs_simplex_run(int dtype, const bmc_simplex_problem* p, uint64_t seed
     a.gamma_boost = a.shape < 1.0;
     a.key0 = static_cast<uint32_t>(seed);
     a.key1 = static_cast<uint32_t>(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        a.keys.k0[r] = a.key0 + static_cast<uint32_t>(r) * kPhiloxW0;
+        a.keys.k1[r] = a.key1 + static_cast<uint32_t>(r) * kPhiloxW1;
+    }
     a.chain0 = chain0;
     a.n_chains = n_chains;
     a.burn = burn;
