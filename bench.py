@@ -326,16 +326,24 @@ def run_native(args):
     pipe_peaks = measure_pipe_peaks(torch, dev)
     issue_peak = max(pipe_peaks["issue"]["Gwarp_inst_per_s"], pipe_peaks["ffma"]["Gwarp_inst_per_s"])
     _PEAKS["issue"] = issue_peak
+    fma = fma_pipe_view(per_gpu_rate, pipe_peaks) or {}
     line["roofline"] = {
         "kernel": "gibbs_conjugate_kernel<float,8,2>",
-        "bound": "issue", "unit": "Gwarp-inst/s",
-        "achieved": (inst * per_gpu_rate / 32 / 1e9) if inst else None,
-        "peak": issue_peak, "frac": (inst * per_gpu_rate / 32 / 1e9 / issue_peak) if inst else None,
-        "peak_source": "measured in this run by bmc_probe (independent FFMA + LOP3 streams, all SMs); nominal "
+        "bound": "fma-pipe", "unit": "Gwarp-inst/s (FFMA slots)",
+        "achieved": fma.get("achieved"), "peak": fma.get("peak"), "frac": fma.get("frac"),
+        "peak_source": "FFMA rate measured in this run by bmc_probe (independent streams, all SMs); nominal "
                        "148 SMs x 4 schedulers x sampled SM clock = %.0f" % nominal_issue,
+        "work": "FMA-pipe instructions of one chain-iteration priced in FFMA slots (IMAD.WIDE and packed fp32 "
+                "cost more than one, measured): SURVEY.md section 8d counts the same items -- 2.5 Philox calls, "
+                "9 normals, the K-component update, the moment sums",
+        "fma_pipe": fma,
+        "issue": {"bound": "issue", "unit": "Gwarp-inst/s",
+                  "achieved": (inst * per_gpu_rate / 32 / 1e9) if inst else None, "peak": issue_peak,
+                  "frac": (inst * per_gpu_rate / 32 / 1e9 / issue_peak) if inst else None,
+                  "warp_inst_per_chain_iter": inst,
+                  "note": "all executed warp-instructions against the measured issue peak; fell from 0.63 as "
+                          "instructions were removed (427 -> 261 per chain-iteration) faster than time"},
         "pipe_peaks_measured": pipe_peaks,
-        "warp_inst_per_chain_iter": inst,
-        "fma_pipe": fma_pipe_view(per_gpu_rate, sm_mhz),
         "traffic": load_dram_bytes(),
         "hbm": {"bound": "hbm", "achieved": alg_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / kernel_s / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs"
@@ -369,7 +377,8 @@ def measure_pipe_peaks(torch, dev):
     blocks, threads, iters = 148 * 8, 256, 20000
     out = {}
     for kind, name in ((0, "ffma"), (1, "mufu"), (2, "philox_mix"), (3, "issue"), (4, "imad_wide_plus_iadd"),
-                       (5, "imad_hi"), (6, "imad"), (7, "lop3")):
+                       (5, "imad_hi"), (6, "imad"), (7, "lop3"), (8, "ffma2"), (9, "imad_wide"),
+                       (11, "imad_wide_plus_2ffma")):
         ops = lib.bmc_probe_ops_per_iteration(kind)
         best = None
         for _ in range(3):
@@ -411,17 +420,25 @@ def predict_roofline(torch, dev, units_per_s_per_gpu, ms_step):
             "note": "whole step (pass + select + window set-up) against the pass kernel's instruction count"}
 
 
-def fma_pipe_view(rate_per_gpu, sm_mhz):
-    """The busiest pipe of the sampler is the FMA pipe: Philox's 32x32->64 multiplies issue at a quarter
-    of the FFMA rate on B200 (bmc_probe: IMAD.WIDE 0.23, IMAD 0.50, LOP3 0.50, MUFU 0.125 of one
-    warp-instruction per clock and scheduler).  Fraction = pipe cycles the opcode mix needs / cycles spent."""
+def fma_pipe_view(rate_per_gpu, pipe_peaks):
+    """The sampler's bounding unit is the FMA pipe.  bmc_probe shows that on B200 a 32x32->64 multiply
+    (IMAD.WIDE, two per Philox round) holds the whole pipe for ~4 cycles -- no FFMA flows beside it
+    (IMAD.WIDE + 2 FFMA = 6.1 cycles) -- and that a packed FFMA2 is two FFMA slots.  Work = the kernel's
+    FMA-pipe instructions per warp-iteration (ncu opcode mix, profiles/kernel_constants.json), each class
+    priced in FFMA slots by the rates measured in this run; peak = the measured FFMA rate."""
     try:
-        need = float(json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))[
-            "gibbs_conjugate_f32_k8_full"]["fma_pipe_cycles_per_warp_iter"])
+        mix = json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))[
+            "gibbs_conjugate_f32_k8_full"]["fma_pipe_mix"]
     except (OSError, KeyError, ValueError):
         return None
-    spent = 148 * 4 * sm_mhz * 1e6 / (rate_per_gpu / 32)        # scheduler-cycles per warp-iteration
-    return {"cycles_needed_per_warp_iter": need, "cycles_spent_per_warp_iter": spent, "frac": need / spent}
+    ffma = pipe_peaks["ffma"]["Gwarp_inst_per_s"]
+    price = {"fp32": 1.0, "fp32x2": ffma / pipe_peaks["ffma2"]["Gwarp_inst_per_s"],
+             "imad": ffma / pipe_peaks["imad"]["Gwarp_inst_per_s"],
+             "imad_wide": ffma / pipe_peaks["imad_wide"]["Gwarp_inst_per_s"]}
+    slots = sum(float(mix[k]) * price[k] for k in price)                  # FFMA slots per warp-iteration
+    achieved = slots * rate_per_gpu / 32 / 1e9
+    return {"achieved": achieved, "peak": ffma, "frac": achieved / ffma, "ffma_slots_per_warp_iter": slots,
+            "price_in_ffma_slots": price, "mix_per_warp_iter": mix}
 
 
 def load_inst_per_iter():
