@@ -208,7 +208,10 @@ int bmc_nearest_class(const double* points, int64_t n, const double* refs, int64
 
 /* ---- peak probes for the pipe rooflines: register-only kernels measuring what the
  *      box sustains on the FP32 FMA pipe (kind 0), the MUFU pipe (1), the Philox integer mix (2) and
- *      dual-pipe issue (3).  `iters` loop iterations per thread, each issuing
+ *      dual-pipe issue (3); single-instruction streams IMAD.WIDE+IADD / IMAD.HI / IMAD / LOP3 (4-7), packed
+ *      FFMA2 (8), IMAD.WIDE alone (9), and the mixes that show which classes share a pipe: IMAD.WIDE + FFMA
+ *      (10), + 2 FFMA (11), + FFMA2 (12), MUFU + 4 FFMA (13), MUFU + 2 IMAD.WIDE (14), FFMA2 + FFMA (15).
+ *      `iters` loop iterations per thread, each issuing
  *      bmc_probe_ops_per_iteration(kind) thread-level operations; `sink` is a dev float[1]. */
 int bmc_probe_ops_per_iteration(int kind);
 int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, void* stream);
