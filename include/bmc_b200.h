@@ -200,6 +200,11 @@ int bmc_column_moments(const double* matrix, int64_t s_rows, int64_t n_cols, int
 int bmc_coverage_levels(const int64_t* c_lt, const int64_t* c_le, int64_t n_points, const int64_t* lo_idx,
                         const int64_t* hi_idx, int n_levels, int64_t* covered, void* stream);
 
+/* A/B switch of the simplex sampler's few-chains kernel for at most 16 models (state-independent parts of
+ * a proposal precomputed 32 iterations at a time; gibbs_kernels.cuh).  Same stream and decisions either way.
+ * Returns the previous setting; default on. */
+int bmc_simplex_set_group16(int enabled);
+
 /* ---- data split by distance: Dataset.separate_points_distance_allSets, pybmc/data.py:194-245 ---------
  * cls[i] = 0 if a reference point lies within d1 of point i (Euclidean, <=), 1 if one lies within d2 but
  * none within d1, 2 otherwise.  points dev [n][dim], refs dev [r][dim] (fp64), cls dev int32 [n]. */

@@ -64,6 +64,7 @@ SIGNATURES = {
     "bmc_predict_workspace_bytes": (_sz, [_int, _i64, _int, _i64]),
     "bmc_predict_theta_stride": (_int, [_int]),
     "bmc_predict_set_tensor_path": (None, [_int]),
+    "bmc_simplex_set_group16": (_int, [_int]),
     "bmc_predict_fused": (_int, [_int, C.POINTER(PredictProblem), _p, _p, _p, _p, _p, _p, _i64, _p, _sz,
                                  C.POINTER(_int), _p]),
     "bmc_coverage_counts": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),

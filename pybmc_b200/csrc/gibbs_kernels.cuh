@@ -861,4 +861,254 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group_kernel(const SimplexA
     if (a.accepted && g == 0 && chain_ok) a.accepted[cid] = n_acc;
 }
 
+// --------------------------------------------------------------------------------------
+// Simplex sampler, eight lanes per chain, at most 16 models (BASELINE configs[1]: 15 models, K = 3).
+// Everything about a proposal that does not depend on the chain's state is linear in the proposal step
+// delta = S * stepsize * z and is worked out in the parallel phase, 32 iterations at a time:
+//     dw = delta' Vt_hat         (the change of the 16 model weights, :99)
+//     G delta, delta' G delta    (the pieces of RSS' - RSS = delta' G (2 dc + delta), :104-108)
+// next to the Metropolis uniform and the Gamma variate.  The serial phase then carries, replicated in the
+// eight lanes of the group, dc = b - b_ols, G dc, RSS and sigma^2, and in lane g the weights of models g
+// and g + 8: an iteration is a K-term dot product, two adds, a vote ("any weight negative", :102), one
+// exp and a handful of selects -- no shuffles and a dependency chain of ~100 cycles instead of ~650.
+// Same random stream and the same decisions as the other simplex kernels (the weights and G dc are carried
+// as running sums, as RSS always was; they are rebuilt from dc at the start of every batch of 32).
+constexpr int kSimplexModels16 = 16;
+
+template <int KP>
+struct SimplexRow16 {
+    static constexpr int kDelta = 0, kGDelta = KP, kDw = 2 * KP, kScal = 2 * KP + kSimplexModels16;   // dgd, u, gamma
+    static constexpr int kRow = 2 * KP + kSimplexModels16 + 4;
+};
+
+template <typename real, int KP, int MODE>
+__global__ void __launch_bounds__(128) gibbs_simplex_group16_kernel(const SimplexArgs a) {
+    using M = Math<real>;
+    using R = SimplexRow16<KP>;
+    constexpr int G = kSimplexGroup, MW = kSimplexModels16;
+    constexpr int D = KP + 1;
+    constexpr int WPB = 4, CPW = 32 / G;
+    constexpr int ROW = R::kRow;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real* const vt_s = reinterpret_cast<real*>(smem_raw);                 // [KP][16], zero padded
+    real* const gram_s = vt_s + KP * MW;                                  // [KP][KP], zero padded
+    real* const draws_s = gram_s + KP * KP;                               // [WPB][CPW][32][ROW]
+    for (int i = threadIdx.x; i < KP * MW; i += blockDim.x) {
+        const int k = i / MW, m = i % MW;
+        vt_s[i] = (k < a.k && m < a.m) ? static_cast<real>(a.vt[k * a.m + m]) : real(0);
+    }
+    for (int i = threadIdx.x; i < KP * KP; i += blockDim.x) {
+        const int r = i / KP, c = i % KP;
+        gram_s[i] = (r < a.k && c < a.k) ? static_cast<real>(a.gram[r * a.k + c]) : real(0);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane & (G - 1), grp = lane / G;
+    const long long cid_raw = (static_cast<long long>(blockIdx.x) * WPB + warp) * CPW + grp;
+    const bool chain_ok = cid_raw < a.n_chains;
+    if (!__any_sync(0xffffffffu, chain_ok)) return;                       // whole warp beyond the last chain
+    const long long cid = chain_ok ? cid_raw : a.n_chains - 1;            // idle groups shadow a real chain
+    const uint32_t chain = static_cast<uint32_t>(a.chain0 + static_cast<unsigned long long>(cid));
+    real* const mine = draws_s + (static_cast<size_t>(warp) * CPW + grp) * 32 * ROW;
+
+    real step[KP], b_ols[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        step[k] = k < a.k ? static_cast<real>(a.step[k]) : real(0);
+        b_ols[k] = k < a.k ? static_cast<real>(a.b_ols[k]) : real(0);
+    }
+    const bool comp = g < a.k;
+    const real b_ols_own = comp ? static_cast<real>(a.b_ols[g]) : real(0);
+    const real bias0 = static_cast<real>(1.0 / static_cast<double>(a.m));  // :78
+    const real prior_scale = run_consts<real>(a).prior_scale;
+    const real sig_ref = run_consts<real>(a).sigma_ref;
+    const GammaConst<real> gc = gamma_const_of(run_consts<real>(a), a.gamma_boost);
+    const bool vok0 = g < a.m, vok1 = g + G < a.m;
+    const unsigned int grp_shift = static_cast<unsigned int>(G * grp);
+
+    // state, replicated in the group: dc = b - b_ols (b starts at 0, :82), G dc, RSS, sigma^2
+    real dc[KP], gdc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) dc[k] = -b_ols[k];
+    real dc_own = -b_ols_own;
+    real w0 = bias0, w1 = bias0, rss = real(0);
+    auto rebuild = [&](bool with_rss) {
+        // G dc and the weights from dc itself (bounds the drift of the running sums)
+        real acc = real(0);
+#pragma unroll
+        for (int r = 0; r < KP; ++r) {
+            real t = real(0);
+#pragma unroll
+            for (int c = 0; c < KP; ++c) t = M::fma(gram_s[r * KP + c], dc[c], t);
+            gdc[r] = t;
+            acc = M::fma(t, dc[r], acc);
+        }
+        if (with_rss) rss = acc + run_consts<real>(a).rss_min;
+        real a0 = bias0, a1 = bias0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const real bk = b_ols[k] + dc[k];
+            a0 = M::fma(bk, vt_s[k * MW + g], a0);
+            a1 = M::fma(bk, vt_s[k * MW + g + G], a1);
+        }
+        w0 = a0;
+        w1 = a1;
+    };
+    rebuild(true);
+    real s2 = run_consts<real>(a).sigma2_init;                           // :86
+
+    real acc1 = real(0), accs = real(0), acce = real(0), accee = real(0);
+    real acc2[KP];
+#pragma unroll
+    for (int c = 0; c < KP; ++c) acc2[c] = real(0);
+    int n_acc = 0;
+    real* const out = static_cast<real*>(a.samples);
+
+    // one state update (:98-117 / :121-140)
+    auto update = [&](const real* row, bool count_accept) {
+        real delta[KP], gdelta[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            delta[k] = row[R::kDelta + k];
+            gdelta[k] = row[R::kGDelta + k];
+        }
+        const real delta_own = g < KP ? row[R::kDelta + (g < KP ? g : 0)] : real(0);
+        const real dgd = row[R::kScal], u = row[R::kScal + 1], gm = row[R::kScal + 2];
+        const real wn0 = w0 + row[R::kDw + g], wn1 = w1 + row[R::kDw + g + G];
+        const bool neg = (vok0 && wn0 < real(0)) || (vok1 && wn1 < real(0));      // :102
+        const unsigned int any_neg = (__ballot_sync(0xffffffffu, neg) >> grp_shift) & 0xffu;
+        real t0 = real(0), t1 = real(0);
+#pragma unroll
+        for (int k = 0; k < KP; k += 2) {
+            t0 = M::fma(delta[k], gdc[k], t0);
+            if (k + 1 < KP) t1 = M::fma(delta[k + 1], gdc[k + 1], t1);
+        }
+        const real diff = M::fma(real(2), t0 + t1, dgd);                  // RSS' - RSS = delta'G(2 dc + delta)
+        const real alpha = M::exp(M::div(-diff, s2));                     // no factor 1/2 (:108 / :130)
+        const bool accept = any_neg == 0u && u < fmin(real(1), alpha);    // :102, :110
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            dc[k] = accept ? dc[k] + delta[k] : dc[k];
+            gdc[k] = accept ? gdc[k] + gdelta[k] : gdc[k];
+        }
+        dc_own = accept ? dc_own + delta_own : dc_own;
+        w0 = accept ? wn0 : w0;
+        w1 = accept ? wn1 : w1;
+        rss = accept ? rss + diff : rss;
+        n_acc += (accept && count_accept) ? 1 : 0;
+        s2 = M::div(real(0.5) * (prior_scale + rss), gm);                 // :116-117, no floor
+    };
+
+    const int burn = static_cast<int>(a.burn), total = static_cast<int>(a.burn + a.iterations);
+    int next_store = a.samples ? burn : -1;
+    int slot = 0;
+    for (int base = 0; base < total; base += 32) {
+        // ---- phase 1: everything state-independent of iterations base .. base+31 of this group's chain
+#pragma unroll 1
+        for (int t = 0; t < 32 / G; ++t) {
+            const int j = g + G * t;
+            const uint32_t it32 = static_cast<uint32_t>(base + j);
+            real* row = mine + j * ROW;
+            real delta[KP];
+#pragma unroll
+            for (int b = 0; b < (KP + 3) / 4; ++b) {
+                real z[4];
+                normals4_k<real>(it32, static_cast<uint32_t>(b), chain, kTagSimplex, a.keys, z);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (4 * b + q < KP) delta[4 * b + q] = step[4 * b + q] * z[q];            // :98 / :121
+            }
+            real dgd = real(0);
+#pragma unroll
+            for (int r = 0; r < KP; ++r) {
+                real gd = real(0);
+#pragma unroll
+                for (int c = 0; c < KP; ++c) gd = M::fma(gram_s[r * KP + c], delta[c], gd);
+                row[R::kDelta + r] = delta[r];
+                row[R::kGDelta + r] = gd;
+                dgd = M::fma(delta[r], gd, dgd);
+            }
+#pragma unroll
+            for (int m = 0; m < MW; ++m) {
+                real dw = real(0);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) dw = M::fma(delta[k], vt_s[k * MW + m], dw);
+                row[R::kDw + m] = dw;
+            }
+            row[R::kScal] = dgd;
+            row[R::kScal + 1] = M::u01(philox4x32_10(it32, kBlockUniform, chain, kTagSimplex, a.keys).x);
+            row[R::kScal + 2] = gamma_unit_scale<real>(gc, it32, chain, kTagSimplex, a.keys, a.key0, a.key1);
+        }
+        __syncwarp();
+        if (base > 0) rebuild(false);
+        // ---- phase 2: the state updates, in order
+        const int n_here = min(32, total - base);
+        if (base + n_here <= burn) {
+            for (int j = 0; j < n_here; ++j) update(mine + j * ROW, false);   // burn-in: nothing recorded
+        } else {
+            for (int j = 0; j < n_here; ++j) {
+                const int it = base + j;
+                update(mine + j * ROW, it >= burn);
+                if (it < burn) continue;
+                const real sig = M::sqrt(s2);
+                if (MODE != 0) {
+                    const real es = sig - sig_ref;
+                    acc1 += dc_own;
+                    accs = M::fma(dc_own, es, accs);
+                    acce += es;
+                    accee = M::fma(es, es, accee);
+                    if (MODE == 1) {
+                        acc2[0] = M::fma(dc_own, dc_own, acc2[0]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < KP; ++c) acc2[c] = M::fma(dc_own, dc[c], acc2[c]);
+                    }
+                    const int done = it - burn + 1;
+                    if ((done % kFlushEvery) == 0 || it + 1 == total) {
+                        auto row2 = [&](int r, int c) { return D + r * D - r * (r - 1) / 2 + (c - r); };
+                        auto flush = [&](int row_out, real& v) {
+                            if (chain_ok) {
+                                double* p = a.chain_stats + static_cast<long long>(row_out) * a.n_chains + cid;
+                                *p += static_cast<double>(v);
+                            }
+                            v = real(0);
+                        };
+                        if (g < KP) {
+                            flush(g, acc1);
+                            if (MODE == 1) {
+                                flush(D + g, acc2[0]);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < KP; ++c) {
+                                    if (c >= g) flush(row2(g, c), acc2[c]);
+                                    else acc2[c] = real(0);
+                                }
+                                flush(row2(g, KP), accs);
+                            }
+                        }
+                        if (g == 0) {
+                            flush(KP, acce);
+                            flush(MODE == 1 ? D + KP : row2(KP, KP), accee);
+                        }
+                        acc1 = accs = acce = accee = real(0);
+#pragma unroll
+                        for (int c = 0; c < KP; ++c) acc2[c] = real(0);
+                    }
+                }
+                if (it == next_store) {
+                    if (chain_ok) {
+                        real* dst = out + static_cast<long long>(slot) * (a.k + 1) * a.n_chains + cid;
+                        if (g < a.k) dst[static_cast<long long>(g) * a.n_chains] = b_ols_own + dc_own;
+                        if (g == 0) dst[static_cast<long long>(a.k) * a.n_chains] = sig;
+                    }
+                    ++slot;
+                    next_store += static_cast<int>(a.thin);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (a.accepted && chain_ok && g == 0) a.accepted[cid] = n_acc;
+}
+
 }  // namespace bmc

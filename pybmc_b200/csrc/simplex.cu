@@ -65,6 +65,31 @@ int launch_simplex_group(const SimplexArgs& a, int stats_mode, cudaStream_t stre
     return BMC_OK;
 }
 
+// at most 16 models: the group kernel that precomputes the weight changes (gibbs_simplex_group16_kernel)
+template <typename real, int KP>
+int launch_simplex_group16(const SimplexArgs& a, int stats_mode, cudaStream_t stream) {
+    const int wpb = 4, cpw = 32 / kSimplexGroup;
+    const unsigned blocks = static_cast<unsigned>((a.n_chains + wpb * cpw - 1) / (wpb * cpw));
+    const size_t smem = sizeof(real) * (static_cast<size_t>(KP) * kSimplexModels16 + static_cast<size_t>(KP) * KP +
+                                        static_cast<size_t>(wpb) * cpw * 32 * SimplexRow16<KP>::kRow);
+    if (smem > 200 * 1024) return 1;
+#define BMC_SIMPLEX_GROUP16(MODE)                                                                             \
+    do {                                                                                                      \
+        auto kern = gibbs_simplex_group16_kernel<real, KP, MODE>;                                             \
+        if (smem > 32 * 1024)                                                                                 \
+            BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        kern<<<blocks, wpb * 32, smem, stream>>>(a);                                                          \
+    } while (0)
+    if (stats_mode == BMC_STATS_NONE) BMC_SIMPLEX_GROUP16(0);
+    else if (stats_mode == BMC_STATS_DIAG) BMC_SIMPLEX_GROUP16(1);
+    else BMC_SIMPLEX_GROUP16(2);
+#undef BMC_SIMPLEX_GROUP16
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+int g_simplex_group16 = 1;      // bmc_simplex_set_group16(): A/B switch, default on
+
 // below this many chains a thread-per-chain launch cannot fill the machine (148 SMs x 4 schedulers x
 // a few warps each): give every chain eight lanes instead.  Measured crossover on B200
 // (profiles/layout_sweep.py): 16,384 chains (4.08 vs 4.03 ms); 32,768: 4.8 vs 7.8 ms; 4096: 4.1 vs 1.7 ms.
@@ -72,6 +97,11 @@ constexpr long long kGroupPerChainBelow = 16384;
 
 template <typename real>
 int dispatch_simplex(const SimplexArgs& a, int stats_mode, int threads, cudaStream_t stream) {
+    if (a.n_chains < kGroupPerChainBelow && a.k <= 8 && a.m <= kSimplexModels16 && g_simplex_group16) {
+        const int rc = a.k <= 4 ? launch_simplex_group16<real, 4>(a, stats_mode, stream)
+                                : launch_simplex_group16<real, 8>(a, stats_mode, stream);
+        if (rc <= 0) return rc;
+    }
     if (a.n_chains < kGroupPerChainBelow && a.k <= 8) {
         const int rc = a.k <= 4 ? launch_simplex_group<real, 4>(a, stats_mode, stream)
                                 : launch_simplex_group<real, 8>(a, stats_mode, stream);
@@ -87,6 +117,12 @@ int dispatch_simplex(const SimplexArgs& a, int stats_mode, int threads, cudaStre
 }  // namespace
 
 extern "C" {
+
+int bmc_simplex_set_group16(int enabled) {
+    const int before = g_simplex_group16;
+    g_simplex_group16 = enabled != 0;
+    return before;
+}
 
 int bmc_gibbs_simplex_run(int dtype, const bmc_simplex_problem* p, uint64_t seed, uint64_t chain0,
                           int64_t n_chains, int64_t burn, int64_t iterations, int64_t thin, int64_t n_kept,

@@ -329,3 +329,26 @@ def test_simplex_posterior_matches_reference_sampler_statistically():
         assert np.all(w > -1e-6) and abs(w.sum() - 1.0) < 1e-8
         acc_ref = np.mean([np.mean(np.any(np.diff(s[:, :3], axis=0) != 0, axis=1)) for s in runs])
         assert abs(res.acceptance.mean() - acc_ref) < 0.03
+
+
+def test_simplex_few_model_kernel_matches_general_group_kernel():
+    """At most 16 models: the group kernel that precomputes the weight changes of 32 iterations at a time
+    walks the same chains as the general one (running sums instead of per-iteration dot products: fp64
+    round-off apart), in both precisions' moment sums and acceptance counts."""
+    import pybmc_b200 as pb
+    from pybmc_b200 import _lib
+    lib = _lib.load()
+    y, X, Vt, S = _simplex_case()
+    out = {}
+    for fast in (1, 0):
+        before = lib.bmc_simplex_set_group16(fast)
+        try:
+            out[fast] = pb.run_gibbs_simplex(y, X, Vt, S, 500, [1.0, 0.02], burn=70, stepsize=0.02, n_chains=37,
+                                             seed=5, thin=3, stats="full")
+        finally:
+            lib.bmc_simplex_set_group16(before)
+    a, b = out[1], out[0]
+    np.testing.assert_allclose(a.samples, b.samples, rtol=1e-9, atol=1e-12)
+    assert np.array_equal(a.acceptance, b.acceptance)
+    np.testing.assert_allclose(a.mean, b.mean, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(a.cov, b.cov, rtol=1e-7, atol=1e-12)
