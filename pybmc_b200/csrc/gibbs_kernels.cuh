@@ -975,7 +975,7 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group16_kernel(const Simple
         const real delta_own = g < KP ? row[R::kDelta + (g < KP ? g : 0)] : real(0);
         const real dgd = row[R::kScal], u = row[R::kScal + 1], gm = row[R::kScal + 2];
         const real wn0 = w0 + row[R::kDw + g], wn1 = w1 + row[R::kDw + g + G];
-        const bool neg = (vok0 && wn0 < real(0)) || (vok1 && wn1 < real(0));      // :102
+        const bool neg = (vok0 & (wn0 < real(0))) | (vok1 & (wn1 < real(0)));     // :102
         const unsigned int any_neg = (__ballot_sync(0xffffffffu, neg) >> grp_shift) & 0xffu;
         real t0 = real(0), t1 = real(0);
 #pragma unroll
@@ -985,7 +985,7 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group16_kernel(const Simple
         }
         const real diff = M::fma(real(2), t0 + t1, dgd);                  // RSS' - RSS = delta'G(2 dc + delta)
         const real alpha = M::exp(M::div(-diff, s2));                     // no factor 1/2 (:108 / :130)
-        const bool accept = any_neg == 0u && u < fmin(real(1), alpha);    // :102, :110
+        const bool accept = (any_neg == 0u) & (u < fmin(real(1), alpha)); // :102, :110
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             dc[k] = accept ? dc[k] + delta[k] : dc[k];

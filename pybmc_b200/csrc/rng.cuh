@@ -133,7 +133,13 @@ struct Math<float> {
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(x));
         return l2 * 0.6931471805599453f;
     }
-    static __device__ __forceinline__ float exp(float x) { return __expf(x); }
+    // e^x = 2^(x log2 e) on the MUFU pipe; results below 2^-126 flush to zero (they are compared with a
+    // uniform that is never below 2^-33)
+    static __device__ __forceinline__ float exp(float x) {
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+        return r;
+    }
     static __device__ __forceinline__ float sqrt(float x) {
         float r;
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -149,7 +155,8 @@ struct Math<float> {
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
         return r;
     }
-    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    // a / b for a normal divisor: what div.approx does, minus its range fix-up instructions
+    static __device__ __forceinline__ float div(float a, float b) { return a * rcp(b); }
     static __device__ __forceinline__ float pow(float a, float b) { return powf(a, b); }
     static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
 };

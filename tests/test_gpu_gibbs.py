@@ -331,24 +331,39 @@ def test_simplex_posterior_matches_reference_sampler_statistically():
         assert abs(res.acceptance.mean() - acc_ref) < 0.03
 
 
-def test_simplex_few_model_kernel_matches_general_group_kernel():
-    """At most 16 models: the group kernel that precomputes the weight changes of 32 iterations at a time
-    walks the same chains as the general one (running sums instead of per-iteration dot products: fp64
-    round-off apart), in both precisions' moment sums and acceptance counts."""
+def test_simplex_few_model_kernels_match_general_group_kernel():
+    """At most 16 models: the kernel that precomputes the weight changes of 32 iterations at a time (the
+    default) walks the same chains as the general eight-lanes-per-chain kernel -- running sums instead of
+    per-iteration dot products, so fp64 round-off apart -- with the same moment sums and acceptance counts;
+    chain counts that leave groups of the last warp idle, burn-in that ends inside a batch, thinning."""
     import pybmc_b200 as pb
     from pybmc_b200 import _lib
     lib = _lib.load()
     y, X, Vt, S = _simplex_case()
-    out = {}
-    for fast in (1, 0):
-        before = lib.bmc_simplex_set_group16(fast)
+    for n_chains, T, burn, thin in ((37, 500, 70, 3), (1, 203, 0, 1), (64, 61, 11, 7)):
+        out = {}
+        for mode in (1, 0):
+            before = lib.bmc_simplex_set_group16(mode)
+            try:
+                out[mode] = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02,
+                                                 n_chains=n_chains, seed=5, thin=thin, stats="full")
+            finally:
+                lib.bmc_simplex_set_group16(before)
+        b = out[0]
+        for mode in (1,):
+            a = out[mode]
+            np.testing.assert_allclose(a.samples, b.samples, rtol=1e-9, atol=1e-12)
+            assert np.array_equal(a.acceptance, b.acceptance)
+            np.testing.assert_allclose(a.mean, b.mean, rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(a.cov, b.cov, rtol=1e-7, atol=1e-12)
+    f32 = {}
+    for mode in (1, 0):
+        before = lib.bmc_simplex_set_group16(mode)
         try:
-            out[fast] = pb.run_gibbs_simplex(y, X, Vt, S, 500, [1.0, 0.02], burn=70, stepsize=0.02, n_chains=37,
-                                             seed=5, thin=3, stats="full")
+            f32[mode] = pb.run_gibbs_simplex(y, X, Vt, S, 4000, [1.0, 0.02], burn=500, stepsize=0.02, n_chains=512,
+                                             seed=9, dtype="float32", keep_samples=False, stats="full")
         finally:
             lib.bmc_simplex_set_group16(before)
-    a, b = out[1], out[0]
-    np.testing.assert_allclose(a.samples, b.samples, rtol=1e-9, atol=1e-12)
-    assert np.array_equal(a.acceptance, b.acceptance)
-    np.testing.assert_allclose(a.mean, b.mean, rtol=1e-9, atol=1e-12)
-    np.testing.assert_allclose(a.cov, b.cov, rtol=1e-7, atol=1e-12)
+    # fp32: same law (chains may part ways after a borderline decision); moments of 2e6 draws agree
+    np.testing.assert_allclose(f32[1].mean, f32[0].mean, rtol=2e-3, atol=2e-4)
+    assert abs(f32[1].acceptance.mean() - f32[0].acceptance.mean()) < 5e-3
