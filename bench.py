@@ -545,6 +545,33 @@ def extras_predict(out, args, torch, dev, world, rank, timed, barrier, flush, hb
                                     "counts, no S x N matrix, nuclei sharded over ranks"}
     del prob, ws
 
+    # the same step end to end through the public call: host arrays in (this rank's predictions, truth, all
+    # posterior rows), host results out (mean, variance, percentiles, order counts)
+    from pybmc_b200.sampling_utils import predictive_summary
+    p_h, t_h = np.ascontiguousarray(preds[lo:hi]), np.ascontiguousarray(truth[lo:hi])
+
+    def pred_e2e():
+        return predictive_summary(p_h, theta, vt, truth=t_h, percentiles=q, seed=SEED, dtype="float32",
+                                  subsample=False, device=dev, point0=lo)
+    for _ in range(2):
+        r = pred_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = pred_e2e()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    out["predict_f32"]["e2e"] = {
+        "value": n_total * n_draws / e2e_s, "unit": "samples*points/s", "ms_per_step": 1e3 * e2e_s,
+        "h2d_bytes_per_step": int(p_h.nbytes + t_h.nbytes + theta.nbytes + vt.nbytes),
+        "d2h_bytes_per_step": int((hi - lo) * 8 * (2 + len(q) + 2))}
+    del r
+
     # an HBM-bound kernel of the path: order counts of a materialised matrix (coverage())
     if rank == 0 and not only_predict:
         s_rows, n_cols = 10000, 65536
