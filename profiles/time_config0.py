@@ -22,6 +22,7 @@ with contextlib.redirect_stdout(io.StringIO()):
     res["train_50k_1chain_f32"] = t(lambda: bmc.train({"iterations": 50000, "dtype": "float32"}))[0]
     res["train_50k_64chains_f64"] = t(lambda: bmc.train({"iterations": 50000, "n_chains": 64, "thin": 64}))[0]
     bmc.train({"iterations": 50000})
+    res["predict2_first_call"] = t(lambda: bmc.predict2("BE"))[0]
     res["predict2"] = t(lambda: bmc.predict2("BE"))[0]
     res["predict2_nodraws"] = t(lambda: bmc.predict2("BE", return_draws=False))[0]
     res["evaluate"] = t(lambda: bmc.evaluate())[0]

@@ -240,7 +240,9 @@ class ConjugateSampler:
         comp = list(range(k)) + [kp]
         jac_d = torch.from_numpy(jac).to(cstats.device)
         base_d = torch.from_numpy(base).to(cstats.device)
-        chain_mean_d = base_d[None, :] + (cstats[comp, :].t() / float(iterations)) @ jac_d.t()
+        # [C, K+1] x [K+1, K+1] as a broadcast product: element-wise kernels only, no cuBLAS handle for this
+        chain_mean_d = base_d[None, :] + ((cstats[comp, :].t() / float(iterations))[:, None, :]
+                                          * jac_d[None, :, :]).sum(dim=2)
         self.last_rhat, self.last_ess = _chain_diagnostics(cstats, comp, _stat_layout(k, kp, mode)[2], jac_d,
                                                            chain_mean_d, iterations)
         return mean, cov, D.to_host(chain_mean_d)

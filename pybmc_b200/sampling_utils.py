@@ -220,8 +220,16 @@ class PredictiveProblem:
             raise ValueError(f"samples must be [S, {self.k + 1}], got {tuple(th.shape)}")
         self.n_draws = th.shape[0]
         self.theta_mean = th.mean(dim=0).contiguous()
-        cen = th - self.theta_mean
-        self.theta_cov = (cen.t() @ cen / max(self.n_draws, 1)).contiguous()
+        cen = (th - self.theta_mean).contiguous()
+        # covariance of the draws by the library's own Gram kernel (no cuBLAS handle for a (K+1)^2 result)
+        lib = _lib.load()
+        cov = torch.zeros((self.k + 1, self.k + 1), dtype=torch.float64, device=self.dev)
+        if self.n_draws > 0:
+            ws = torch.empty(max(int(lib.bmc_gram_workspace_bytes(self.n_draws, self.k + 1)), 8), dtype=torch.uint8,
+                             device=self.dev)
+            _lib.check(lib.bmc_gram(D.ptr(cen), self.n_draws, self.k + 1, cen.stride(0), None, None, D.ptr(cov),
+                                    D.ptr(ws), ws.numel(), D.stream_ptr(self.dev)), "bmc_gram")
+        self.theta_cov = (cov / max(self.n_draws, 1)).contiguous()
         # rows padded for 16-byte broadcast loads: beta | zeros | sigma at column stride-4 | zeros
         stride = _lib.load().bmc_predict_theta_stride(self.k)
         padded = torch.zeros((self.n_draws, stride), dtype=tdt, device=self.dev)
