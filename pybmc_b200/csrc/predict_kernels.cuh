@@ -588,12 +588,34 @@ __global__ void __launch_bounds__(256) predict_select_kernel(const SelectArgs a)
     real stored_value = real(0), v_first = real(0), v_second = real(0);
     if (inside && storable && cw <= kStageCap) {
         // gather the slots' candidates once; the radix passes then run out of shared memory
+        // four slots at a time, up to four values per lane and slot: sixteen independent loads in flight
+        // instead of one slot's at a time (this gather is latency-bound: 33 % long-scoreboard stalls)
         int off = 0;
-        for (int sl = 0; sl < a.n_slots; ++sl) {
-            const int c = static_cast<int>(slot_cnt[sl]);
-            const real* seg = src + static_cast<long long>(sl) * a.seg_len;
-            for (int i = lane; i < c; i += 32) stage[off + i] = seg[i];
-            off += c;
+        for (int sl = 0; sl < a.n_slots; sl += 4) {
+            int c[4];
+            real v[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = sl + q < a.n_slots ? static_cast<int>(slot_cnt[sl + q]) : 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const real* seg = src + static_cast<long long>(sl + q) * a.seg_len;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int i = lane + 32 * t;
+                    v[q][t] = i < c[q] ? seg[i] : real(0);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const real* seg = src + static_cast<long long>(sl + q) * a.seg_len;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int i = lane + 32 * t;
+                    if (i < c[q]) stage[off + i] = v[q][t];
+                }
+                for (int i = lane + 128; i < c[q]; i += 32) stage[off + i] = seg[i];
+                off += c[q];
+            }
         }
         if (lane == 0) staged_cnt[warp] = static_cast<unsigned int>(off);
         __syncwarp();

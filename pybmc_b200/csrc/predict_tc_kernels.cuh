@@ -165,10 +165,10 @@ template <int KP, int NQ>
 __global__ void __launch_bounds__(kTcThreads + 32, 1) predict_pass_tc_kernel(const PredictArgs a,
                                                                              const unsigned char* __restrict__ img) {
     using IM = TcImage<KP>;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* const a_hi = smem_raw;
-    unsigned char* const a_lo = smem_raw + IM::kOperandBytes;
-    unsigned char* const stage0 = smem_raw + 2 * IM::kOperandBytes;
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    unsigned char* const a_hi = tc_smem_raw;
+    unsigned char* const a_lo = tc_smem_raw + IM::kOperandBytes;
+    unsigned char* const stage0 = tc_smem_raw + 2 * IM::kOperandBytes;
     __shared__ __align__(8) uint64_t full_bar[2], done_bar[2], empty_bar[2];
     __shared__ uint32_t tmem_slot;
 
