@@ -4,6 +4,8 @@
 //   gibbs_conjugate_group_kernel  eight lanes (or a warp) per chain  same loop, for fewer than 16,384 (1,536) chains
 //   gibbs_simplex_kernel          one chain per thread   pybmc/inference_utils.py:97-141 (gibbs_sampler_simplex)
 //   gibbs_simplex_group_kernel    eight lanes per chain  same loops, for fewer than 16,384 chains
+//   gibbs_simplex_group16_kernel  eight lanes per chain, at most 16 models: the state-independent parts of a
+//                                 proposal (weight changes, G delta) precomputed 32 iterations at a time
 //
 // The reference recomputes X'y, the residual y - X b and a K-by-K inverse in every
 // iteration.  Both are functions of b through K-sized statistics only:
