@@ -367,3 +367,32 @@ def test_simplex_few_model_kernels_match_general_group_kernel():
     # fp32: same law (chains may part ways after a borderline decision); moments of 2e6 draws agree
     np.testing.assert_allclose(f32[1].mean, f32[0].mean, rtol=2e-3, atol=2e-4)
     assert abs(f32[1].acceptance.mean() - f32[0].acceptance.mean()) < 5e-3
+
+
+def test_conjugate_layouts_agree_in_fp32():
+    """The fp32 thread-per-chain kernel (packed FFMA2 arithmetic, iterations in pairs, segmented loop, packed
+    moment pairs) against the fp32 group kernels (scalar arithmetic) on the same stream, and its device moment
+    sums -- every entry of the packed layout -- against the samples it wrote; kept draws at odd and even
+    iterations, a keep point inside a pair, flush boundaries inside the run."""
+    import pybmc_b200 as pb
+    for name in ("ensemble_default", "wide_k8"):
+        y, X, prior = CASES[name]()
+        width = np.asarray(X).shape[1] + 1
+        T = 150
+        many = pb.run_gibbs(y, X, T, prior, n_chains=16384, seed=13, stats="full", dtype="float32")
+        few = pb.run_gibbs(y, X, T, prior, n_chains=6, seed=13, stats="full", dtype="float32")
+        mid = pb.run_gibbs(y, X, T, prior, n_chains=2000, seed=13, stats="full", dtype="float32")
+        a = many.samples.reshape(16384, T, width)[:6].astype(np.float64)
+        b = few.samples.reshape(6, T, width).astype(np.float64)
+        c = mid.samples.reshape(2000, T, width)[:6].astype(np.float64)
+        scale = np.abs(b).max(axis=(0, 1))
+        assert np.max(np.abs(a - b) / scale) < 2e-5 and np.max(np.abs(c - b) / scale) < 2e-5
+        smp = many.samples.astype(np.float64)
+        np.testing.assert_allclose(many.mean, smp.mean(axis=0), rtol=2e-5, atol=2e-6 * scale.max())
+        want = np.cov(smp.T, ddof=0)
+        assert np.max(np.abs(many.cov - want)) < 2e-3 * np.abs(want).max()
+        thin = pb.run_gibbs(y, X, T, prior, n_chains=16384, seed=13, stats="diag", dtype="float32", thin=7, discard=5)
+        kept = thin.samples.reshape(16384, -1, width)
+        full = many.samples.reshape(16384, T, width)
+        assert np.array_equal(kept, full[:, 5::7])
+        np.testing.assert_allclose(thin.mean, many.mean, rtol=1e-6, atol=1e-7 * scale.max())
