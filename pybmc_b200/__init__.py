@@ -27,3 +27,21 @@ __all__ = [
     "coverage",
     "rndm_m_random_calculator",
 ]
+
+
+def install_as_pybmc():
+    """Make ``import pybmc`` (and ``pybmc.bmc``, ``pybmc.data``, ``pybmc.inference_utils``,
+    ``pybmc.sampling_utils``) resolve to this package for the rest of the process, so that scripts written
+    against upstream run unchanged: call it once before they import ``pybmc``.  Refuses to shadow an upstream
+    ``pybmc`` that is already imported."""
+    import sys
+    from . import bmc, data, inference_utils, sampling_utils
+    this = sys.modules[__name__]
+    loaded = sys.modules.get("pybmc")
+    if loaded is not None and loaded is not this:
+        raise RuntimeError("another 'pybmc' is already imported; call install_as_pybmc() before importing it")
+    sys.modules["pybmc"] = this
+    for name, module in (("bmc", bmc), ("data", data), ("inference_utils", inference_utils),
+                         ("sampling_utils", sampling_utils)):
+        sys.modules["pybmc." + name] = module
+    return this

@@ -155,3 +155,29 @@ def test_chain_diagnostics_on_ar1_chains():
     assert np.all(np.abs(ess / want - 1.0) < 0.2), (ess, want)        # sd of the estimate ~ sqrt(2/chains) = 6 %
     one = _chain_diagnostics(cs[:, :1], comp, second, torch.eye(3, dtype=torch.float64), chain_mean[:1], n)
     assert one == (None, None)
+
+
+def test_install_as_pybmc_makes_upstream_imports_resolve_here():
+    """Scripts written against upstream (docs/usage.md:10-12) run unchanged after one call; an upstream
+    package that is already imported is not shadowed."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import pybmc_b200; pybmc_b200.install_as_pybmc()\n"
+        "from pybmc.data import Dataset\n"
+        "from pybmc.bmc import BayesianModelCombination\n"
+        "from pybmc.inference_utils import gibbs_sampler, gibbs_sampler_simplex, USVt_hat_extraction\n"
+        "from pybmc.sampling_utils import coverage, rndm_m_random_calculator\n"
+        "import pybmc\n"
+        "assert pybmc is pybmc_b200 and pybmc.Dataset is Dataset is pybmc_b200.Dataset\n"
+        "assert BayesianModelCombination is pybmc_b200.BayesianModelCombination\n"
+        "assert gibbs_sampler is pybmc_b200.gibbs_sampler and coverage is pybmc_b200.coverage\n"
+        "import types; sys.modules['pybmc'] = types.ModuleType('pybmc')\n"
+        "try:\n"
+        "    pybmc_b200.install_as_pybmc()\n"
+        "except RuntimeError:\n"
+        "    print('refused')\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "refused"
