@@ -468,8 +468,46 @@ def extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ran
     extras_predict(out, args, torch, dev, world, rank, timed, barrier, flush, hbm_peak, steps, only_predict)
     if not only_predict:
         extras_config5(out, torch, dev, world, rank, timed, pb, steps, hbm_peak)
+        if rank == 0:
+            extras_config0(out, torch, pb, dev)
     barrier()
     return out
+
+
+def extras_config0(out, torch, pb, dev):
+    """BASELINE configs[0], the reference's own workflow through the drop-in class (surrogate for the absent
+    selected_data.h5: 629 nuclei x 15 models, 377 training rows, K = 3): wall-clock of each public call,
+    second call of a process (the first also pays one-time CUDA / cuSOLVER initialisation)."""
+    import contextlib
+    import io
+    import pandas as pd
+    preds, truth = config1_ensemble()
+    models = [f"m{i}" for i in range(preds.shape[1])]
+    df = pd.DataFrame(preds, columns=models)
+    df["N"] = np.arange(len(truth))
+    df["Z"] = np.arange(len(truth)) // 3
+    df["truth"] = truth
+    train = df.iloc[np.random.default_rng(1).permutation(len(df))[:377]]
+    bmc = pb.BayesianModelCombination(models, {"BE": df}, "truth")
+
+    def wall(fn):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize(dev)
+        return 1e3 * (time.perf_counter() - t0)
+    calls = (("orthogonalize", lambda: bmc.orthogonalize("BE", train, 3)),
+             ("train_50000_iterations", lambda: bmc.train({"iterations": 50000})),
+             ("predict2", lambda: bmc.predict2("BE")),
+             ("evaluate", lambda: bmc.evaluate()))
+    ms = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(2):
+            for name, fn in calls:
+                ms[name] = wall(fn)
+    out["config0_workflow_ms"] = dict(ms, config="configs[0] surrogate: 629 x 15, K=3, one fp64 chain of 50,000 iterations, "
+                                                 "10,000 draws materialised by predict2, 21 coverage levels; reference "
+                                                 "(NumPy, one core): ~7000 / 840 / 2500 ms for train / predict2 / evaluate")
 
 
 def extras_samplers(out, timed, sampler, pb, dev, world, rank, steps):
