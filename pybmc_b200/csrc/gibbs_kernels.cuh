@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
     constexpr int G = GEN;
     constexpr int D = KP + 1;
     constexpr int WPB = 4, CPW = 32 / G;
-    constexpr int ROW = KP + 1;                                           // z[KP], gamma
+    constexpr int ROW = KP + 1;                                           // z[KP], 1 / gamma
     __shared__ real draws_s[WPB * CPW * 32 * ROW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane & (G - 1), grp = lane / G;
@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
                 for (int q = 0; q < 4; ++q)
                     if (4 * b + q < KP) row[4 * b + q] = z[q];
             }
-            row[KP] = gamma_unit_scale<real>(gc, it32, chain, kTagGibbs, a.keys, a.key0, a.key1);
+            // the reciprocal is taken here, in the parallel phase (a full division in fp64)
+            row[KP] = M::rcp(gamma_unit_scale<real>(gc, it32, chain, kTagGibbs, a.keys, a.key0, a.key1));
         }
         __syncwarp();
         // ---- phase 2: the state updates, in order (:41-52)
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
             const int it = base + j;
             const real* row = mine + j * ROW;
             const real z = g < KP ? row[g] : real(0);
-            const real inv_gm = M::rcp(row[KP]);                         // off the dependency chain
+            const real inv_gm = row[KP];
             const real sd = sig * M::rsqrt(d + s2);                      // 1/sqrt(d/s2 + 1)
             const real e = sd * M::fma(pull, sd, z);                      // pull/p + z/sqrt(p)
             real rss = (d * e) * e;
