@@ -2,16 +2,26 @@
 """Benchmark of the pyBMC inference hot path on B200 (driver contract: see README / DESIGN.md).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                    [--metric gibbs|predict] [--dtype f32|f64]
 
-Headline workload = BASELINE.json configs[2]: synthetic ensemble of 16 models x 3000 points,
-K = 8 SVD components, 65,536 conjugate-Gibbs chains x 10,000 iterations per GPU (chains shard
-across ranks with no data-path collective: weak scaling).  A "step" is one full run of those chains.
+BASELINE.json quotes two metrics; both are first-class here, in both arms:
 
-  value  chain-iterations / s, whole job, problem constants resident in HBM (CUDA events)
-  e2e    the same metric through the public API `pybmc_b200.run_gibbs` with host NumPy inputs:
-         H2D of (y, X), sufficient statistics, sampler, D2H of moments + the kept samples
-  extra  the other metric of BASELINE.json (posterior-pred samples x points / s, configs[3]),
-         the simplex sampler (configs[1]), the fp64 sampler and an HBM-bound kernel of the path
+  gibbs    chain-iterations / s on BASELINE configs[2]: synthetic ensemble of 16 models x 3000 points, K = 8 SVD
+           components, 65,536 conjugate-Gibbs chains x 10,000 iterations PER GPU (chains shard over ranks through
+           pybmc_b200.parallel.sharded_gibbs, no data-path collective: weak scaling).  One step = one full run.
+           Measured in fp32 (the default headline, admitted by BASELINE.json's 1e-5 / 3-MCSE tolerances) AND in
+           fp64 (the reference's own arithmetic type) at the same full size: the fp64 numbers are the top-level
+           object "f64" of the default line, or the whole line with --dtype f64.
+  predict  posterior-pred samples x points / s on BASELINE configs[3]: 1e5 nuclei x 1e5 posterior draws x K = 16,
+           mean / variance / 5 percentiles / coverage counts, the S x N matrix never stored; nuclei shard over
+           ranks.  Top-level object "predict" of the default line, or the whole line with --metric predict.
+
+Per metric:  value  device-timed (CUDA events), inputs resident in HBM;
+             e2e    the same metric through the public API with HOST arrays in and host results out;
+             roofline  live rate against the measured pipe peaks + the hardware counters of the committed ncu
+                       capture of the same kernel (profiles/kernel_constants.json, regenerated from the .ncu-rep);
+             cpu_baseline  the reference algorithm (oracle port) on the host cores (N = 1, rank 0).
+`--impl reference` times the reference's CPU path for the same metric(s) on all host cores.
 
 One JSON line on stdout (rank 0).
 """
@@ -30,10 +40,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "gibbs_chain_iters_per_sec"
 UNIT = "chain-iters/s"
+PRED_METRIC = "posterior_pred_samples_x_points_per_sec"
+PRED_UNIT = "samples*points/s"
 CHAINS_PER_GPU = 65536
 ITERATIONS = 10000
 KEEP_PER_CHAIN = 10
+HIST_EVERY = 64           # marginal histograms of (b, sigma): every 64th state (the kernels' flush points)
 SEED = 0xB200 + 3
+PRED_POINTS, PRED_DRAWS, PRED_K = 100_000, 100_000, 16
+PRED_Q = [2.5, 16.0, 50.0, 84.0, 97.5]
+
 
 # ------------------------------------------------------------------------------------------------
 # synthetic inputs
@@ -79,6 +95,24 @@ def config4_inputs(n_points, n_draws, k=16):
     return preds, vt, theta, truth
 
 
+def config5_rows(lo, hi, m=256, k=64):
+    """Rows [lo, hi) of BASELINE configs[4]'s table (1e5 points x 256 models, 64 latent factors with a graded
+    spectrum 1 .. 1e-2 + noise), generated per row so that every rank can build exactly its own block."""
+    mix = np.random.default_rng(1005).normal(size=(k, m))
+    spec = np.logspace(0, -2, k)
+    out = np.empty((hi - lo, m))
+    truth = np.empty(hi - lo)
+    step = 8192
+    for a in range(lo, hi, step):
+        b = min(hi, a + step)
+        rng = np.random.default_rng([1005, a])
+        base = rng.uniform(100, 2000, b - a)
+        latent = rng.normal(size=(b - a, k)) * spec
+        out[a - lo:b - lo] = base[:, None] + 30.0 * latent @ mix + rng.normal(0, 0.05, (b - a, m))
+        truth[a - lo:b - lo] = base + 30.0 * latent @ mix[:, 0] * 0.5 + rng.normal(0, 0.15, b - a)
+    return out, truth
+
+
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons while the timed region runs."""
@@ -97,6 +131,7 @@ class ClockSampler:
             threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
         except OSError:
             self.proc = None
+        return self
 
     def stop(self):
         if self.proc is None:
@@ -118,10 +153,6 @@ class ClockSampler:
         busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
-
-
-def flush_l2(torch, buf):
-    buf.add_(1)          # 512 MiB read + write > 126 MB L2
 
 
 # ------------------------------------------------------------------------------------------------
@@ -153,6 +184,66 @@ def cpu_sampler_rate(iters_per_chain, pool, cores, problem):
     return cores * iters_per_chain / dt, dt
 
 
+def _cpu_predict(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    preds, theta, vt, truth, seed = args
+    from oracle import bmc_oracle as oc
+    rndm_m, _ = oc.predictive_draws(preds, theta, vt, np.random.default_rng(seed))       # sampling_utils.py:40-84
+    # the reference re-sorts every column for each of the 21 levels (pybmc/sampling_utils.py:24-28); the
+    # port sorts once, so this baseline is faster than the reference itself
+    oc.coverage_levels(np.arange(0, 101, 5), rndm_m, truth)                              # sampling_utils.py:4-37
+    return rndm_m.shape[0] * rndm_m.shape[1]
+
+
+CPU_PRED_POINTS, CPU_PRED_DRAWS = 629, 10000      # the reference's own sizes: S = 10^4 is hard-coded upstream (:57)
+
+
+def cpu_predict_rate(pool, cores, inputs, seed0=50):
+    preds, vt, theta, truth = inputs
+    t0 = time.perf_counter()
+    units = sum(pool.map(_cpu_predict, [(preds, theta, vt, truth, seed0 + c) for c in range(cores)]))
+    dt = time.perf_counter() - t0
+    return units / dt, dt
+
+
+def gibbs_sample_text(cores, iters):
+    return (f"{cores} chains x {iters} iterations of the same 3000 x 8 problem per step, one process per host core "
+            f"(oracle port of pybmc/inference_utils.py:4-56 on NumPy's generators; {cores * iters / (CHAINS_PER_GPU * ITERATIONS):.1e} "
+            "of one GPU step's chain-iterations: a RATE extrapolation, and conservative -- the port runs ~1.8x the "
+            "iterations/s/core of the live reference (no multivariate_normal SVD check, BASELINE.md))")
+
+
+def predict_sample_text(cores, dt):
+    return (f"{cores} x ({CPU_PRED_POINTS} points x {CPU_PRED_DRAWS} draws x K={PRED_K}: predictive matrix, 3 percentiles, 21 "
+            f"coverage levels -- oracle port of pybmc/sampling_utils.py:40-84 + :4-37), one process per core, {dt:.1f} s; "
+            "rate extrapolation (the reference cannot hold a 1e5 x 1e5 matrix: 80 GB), conservative (the port sorts "
+            "each column once, the reference 21 times)")
+
+
+def pred_config(n_gpus):
+    return {"workload": "BASELINE configs[3]: synthetic posterior prediction, 1e5 nuclei x 1e5 posterior draws x K=16, fused "
+                        "mean / variance / 5 percentiles / coverage counts, no materialised S x N matrix",
+            "n_points": PRED_POINTS, "n_draws": PRED_DRAWS, "components": PRED_K, "percentiles": PRED_Q,
+            "sharding": f"nuclei over {n_gpus} GPU(s); e2e: rank 0 uploads the posterior rows once, NCCL broadcast, one "
+                        "all-gather of the packed per-nucleus outputs",
+            "l2": "512 MiB buffer rewritten between timed steps"}
+
+
+def workload_config(n_gpus, dtype="f32"):
+    return {"workload": "BASELINE configs[2]: synthetic ensemble 16 models x 3000 points, K=8 SVD components, "
+                        "conjugate Gibbs, 65536 chains x 10000 iterations per GPU",
+            "n_points": 3000, "n_models": 16, "components": 8, "chains_per_gpu": CHAINS_PER_GPU,
+            "chains_total": CHAINS_PER_GPU * n_gpus, "iterations": ITERATIONS, "kept_per_chain": KEEP_PER_CHAIN,
+            "arithmetic": dtype,
+            "moments": "all first and cross second moments per chain, summed in the kernel's arithmetic type over 64 "
+                       "iterations, then added to fp64 rows in HBM",
+            "histograms": f"marginal histograms of (b, sigma), 512 bins, every {HIST_EVERY}th state",
+            "sharding": f"chains over {n_gpus} GPU(s) via pybmc_b200.parallel.sharded_gibbs, no data-path collective; "
+                        "per step one all-reduce of the 54 moment sums + count (fp64) and one of the 9 x 512 "
+                        "histogram counts (int64)",
+            "l2": "512 MiB buffer rewritten between timed steps (working set is K-sized, not L2-resident data)"}
+
+
 def run_reference(args):
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
@@ -161,6 +252,7 @@ def run_reference(args):
     os.environ["OMP_NUM_THREADS"] = "1"
     cores = os.cpu_count() or 1
     problem = cpu_problem()
+    pred_inputs = config4_inputs(CPU_PRED_POINTS, CPU_PRED_DRAWS + 2000)
     iters = 1500
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(args.warmup):
@@ -169,216 +261,138 @@ def run_reference(args):
         for _ in range(args.steps):
             _, dt = cpu_sampler_rate(iters, pool, cores, problem)
             times.append(dt)
+        p_times = []
+        for i in range(max(1, min(args.steps, 3))):
+            _, dt = cpu_predict_rate(pool, cores, pred_inputs, 50 + 100 * i)
+            p_times.append(dt)
     total = float(np.sum(times))
     value = cores * iters * args.steps / total
-    sample = f"{cores} chains x {iters} iterations per step on {cores} host processes (oracle port, NumPy RNG)"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+    p_total = float(np.sum(p_times))
+    p_units = cores * CPU_PRED_POINTS * CPU_PRED_DRAWS * len(p_times)
+    p_value = p_units / p_total
+    gibbs = {"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": 1e3 * total / args.steps,
+             "higher_is_better": True, "dtype": "f64", "config": workload_config(args.gpus, "f64"),
+             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                              "sample": gibbs_sample_text(cores, iters)},
+             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    predict = {"metric": PRED_METRIC, "value": p_value, "unit": PRED_UNIT, "ms_per_step": 1e3 * p_total / len(p_times),
+               "higher_is_better": True, "dtype": "f64", "config": pred_config(args.gpus),
+               "cpu_baseline": {"value": p_value, "unit": PRED_UNIT, "cores": cores, "kind": "port",
+                                "sample": predict_sample_text(cores, p_total / len(p_times))},
+               "e2e": {"value": p_value, "unit": PRED_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    main_, other = (predict, gibbs) if args.metric == "predict" else (gibbs, predict)
+    line = {"impl": "reference", **main_, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "scaling": "weak", "vs_baseline": None, "data": "synthetic", "gpu_launches": 0}
+    if args.metric == "predict":
+        line["gibbs"] = other
+    else:
+        line["predict"] = other
+        line["f64"] = {k: gibbs[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "e2e", "cpu_baseline")}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
-    return {"workload": "BASELINE configs[2]: synthetic ensemble 16 models x 3000 points, K=8 SVD components, "
-                        "conjugate Gibbs, 65536 chains x 10000 iterations per GPU",
-            "n_points": 3000, "n_models": 16, "components": 8, "chains_per_gpu": CHAINS_PER_GPU,
-            "chains_total": CHAINS_PER_GPU * n_gpus, "iterations": ITERATIONS, "kept_per_chain": KEEP_PER_CHAIN,
-            "moments": "full cross moments in fp64", "sharding": f"chains over {n_gpus} GPU(s), no data-path collective; "
-            "one all-reduce of the 54 moment sums per step",
-            "l2": "512 MiB buffer rewritten between timed steps (working set is K-sized, not L2-resident data)"}
-
-
 # ------------------------------------------------------------------------------------------------
-def run_native(args):
-    import torch
-    import torch.distributed as dist
-    import pybmc_b200 as pb
-    from pybmc_b200 import _lib
-    from pybmc_b200.inference_utils import ConjugateSampler
+# native arm
+# ------------------------------------------------------------------------------------------------
+class Bench:
+    """Shared plumbing of the native arm: ranks, barriers, the timing loop."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: pybmc_b200 has no CPU path")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if not os.path.exists(_lib.LIB_PATH):       # snapshot without the built library: compile it (rank 0), never fall back
-        if rank == 0:
-            from pybmc_b200.build import build_library
-            build_library(force=True)
-        if world > 1:
-            dist.barrier()
-    lib = _lib.load()
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: pybmc_b200 has no CPU path")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from pybmc_b200 import _lib
+        if not (os.path.exists(_lib.LIB_PATH) and os.path.exists(_lib.PROBE_LIB_PATH)):
+            if self.rank == 0:      # snapshot without the built libraries: compile them, never fall back
+                from pybmc_b200.build import build_library, build_probe_library
+                build_library(force=not os.path.exists(_lib.LIB_PATH))
+                build_probe_library()
+            if self.world > 1:
+                dist.barrier()
+        self.lib = _lib.load()
+        self.flush = torch.zeros(128 * 2 ** 20, dtype=torch.float32, device=self.dev)
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            self.peaks = {}
+        try:
+            self.constants = json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))
+        except (OSError, ValueError):
+            self.constants = {}
+        self._pipe_peaks = None
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- set-up (untimed): orthogonalise on the device, build the resident sampler -----------------
-    preds, truth = config3_ensemble()
-    orth = pb.orthogonalize_arrays(preds, truth, 8)
-    y, X = orth["y"], orth["U_hat"]
-    prior = [np.zeros(8), np.diag(orth["S_hat"] ** 2), 1.0, 0.02]
-    sampler = ConjugateSampler(y, X, prior, device=dev)
-    thin = ITERATIONS // KEEP_PER_CHAIN
-    chain0 = rank * CHAINS_PER_GPU
-    flush = torch.zeros(128 * 2 ** 20, dtype=torch.float32, device=dev)
-
-    def device_step(dtype="float32"):
-        samples, cstats, meta = sampler.run(ITERATIONS, CHAINS_PER_GPU, SEED, dtype, thin, 0, True, "full", chain0)
-        total = cstats.sum(dim=1)
-        if world > 1:
-            dist.all_reduce(total)              # the only collective: 54 fp64 moment sums
-        return samples, total
-
-    def timed(step_fn, steps, warmup, robust=False):
-        """K timed steps (CUDA events, L2 rewritten before each), max over ranks of the total.  The
-        headline uses the plain mean of exactly K steps; the extras (robust=True) take the median step so
-        that one disturbed step of a 2-3 step sample does not decide the number."""
+    def timed(self, step_fn, steps, warmup, robust=False):
+        """K timed steps (CUDA events on the launching stream, L2 rewritten before each), max over ranks of the
+        total.  The headline metrics use the plain mean of exactly K steps; the extras (robust=True) take the
+        median step so that one disturbed step of a 3-step sample does not decide the number."""
+        torch = self.torch
         for _ in range(warmup):
             step_fn()
-        barrier()
+        self.barrier()
         ms = []
         for _ in range(steps):
-            flush_l2(torch, flush)
+            self.flush.add_(1)          # 512 MiB read + write > 126 MB L2
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             step_fn()
             e1.record()
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
-        barrier()
+        self.barrier()
         if robust:
-            return max_over_ranks(float(np.median(ms)))
-        return max_over_ranks(float(np.sum(ms))) / steps
+            return self.max_over_ranks(float(np.median(ms)))
+        return self.max_over_ranks(float(np.sum(ms))) / steps
 
-    if args.only == "predict":
-        out = extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ranks, barrier, flush, 6551.0,
-                     only_predict=True)
-        if rank == 0:
-            print(json.dumps(out), flush=True)
-        return
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    ms_step = timed(device_step, args.steps, args.warmup)
-    clock_info = clocks.stop() if rank == 0 else None
-    units = CHAINS_PER_GPU * world * ITERATIONS
-    value = units / (ms_step * 1e-3)
+    def wall(self, step_fn, steps, warmup):
+        """End-to-end steps by the host clock (host arrays in, host results out), max over ranks."""
+        for _ in range(warmup):
+            step_fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = step_fn()
+        self.torch.cuda.synchronize()
+        s = self.max_over_ranks(time.perf_counter() - t0) / steps
+        self.barrier()
+        return s, out
 
-    # ---- e2e through the public API, host buffers in, host results out ------------------------------
-    y_h, X_h = np.ascontiguousarray(y), np.ascontiguousarray(X)
-
-    def e2e_step():
-        res = pb.run_gibbs(y_h, X_h, ITERATIONS, prior, n_chains=CHAINS_PER_GPU, seed=SEED, dtype="float32",
-                           thin=thin, stats="full", device=dev, chain_offset=chain0)
-        return res
-    e2e_results = [e2e_step() for _ in range(max(3, args.warmup))]    # warm the pinned-host block cache too
-    del e2e_results
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
-    barrier()
-    h2d = y_h.nbytes + X_h.nbytes + 8 * (8 + 4 * 8)            # design + OLS vector + problem constants
-    d2h = res.samples.nbytes + 8 * (54 + 9 * 9 + 1 + 9 * CHAINS_PER_GPU)
-    e2e = {"value": units / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": 1e3 * e2e_s}
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-            "e2e": e2e, "gpu_launches": args.steps * 1 + args.steps * 5,
-            "gpu_launches_detail": "value region: 1 kernel per step (gibbs_conjugate_kernel); e2e region: 5 per step "
-                                   "(gram_partial, sum_partials, rss_partial, sum_partials, gibbs_conjugate_kernel); "
-                                   "reductions of the moment rows and the sample transpose are torch ops",
-            "clocks": clock_info}
-
-    # ---- roofline of the dominant kernel --------------------------------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    sm_mhz = (clock_info or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-    per_gpu_rate = value / world
-    alg_bytes = CHAINS_PER_GPU * (KEEP_PER_CHAIN * 9 * 4 + 54 * 8 * 2 * (ITERATIONS // 64))
-    kernel_s = ms_step * 1e-3
-    inst = load_inst_per_iter()
-    nominal_issue = 148 * 4 * sm_mhz * 1e6 / 1e9                 # 148 SMs x 4 schedulers x clock, Gwarp-inst/s
-    pipe_peaks = measure_pipe_peaks(torch, dev)
-    issue_peak = max(pipe_peaks["issue"]["Gwarp_inst_per_s"], pipe_peaks["ffma"]["Gwarp_inst_per_s"])
-    _PEAKS["issue"] = issue_peak
-    fma = fma_pipe_view(per_gpu_rate, pipe_peaks) or {}
-    line["roofline"] = {
-        "kernel": "gibbs_conjugate_kernel<float,8,2>",
-        "bound": "fma-pipe", "unit": "Gwarp-inst/s (FFMA slots)",
-        "achieved": fma.get("achieved"), "peak": fma.get("peak"), "frac": fma.get("frac"),
-        "peak_source": "FFMA rate measured in this run by bmc_probe (independent streams, all SMs); nominal "
-                       "148 SMs x 4 schedulers x sampled SM clock = %.0f" % nominal_issue,
-        "work": "FMA-pipe instructions of one chain-iteration priced in FFMA slots (IMAD.WIDE and packed fp32 "
-                "cost more than one, measured): SURVEY.md section 8d counts the same items -- 2.5 Philox calls, "
-                "9 normals, the K-component update, the moment sums",
-        "fma_pipe": fma,
-        "issue": {"bound": "issue", "unit": "Gwarp-inst/s",
-                  "achieved": (inst * per_gpu_rate / 32 / 1e9) if inst else None, "peak": issue_peak,
-                  "frac": (inst * per_gpu_rate / 32 / 1e9 / issue_peak) if inst else None,
-                  "warp_inst_per_chain_iter": inst,
-                  "note": "all executed warp-instructions against the measured issue peak; fell from 0.63 as "
-                          "instructions were removed (427 -> 261 per chain-iteration) faster than time"},
-        "pipe_peaks_measured": pipe_peaks,
-        "traffic": load_dram_bytes(),
-        "hbm": {"bound": "hbm", "achieved": alg_bytes / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": alg_bytes / kernel_s / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs"
-                if peaks else "fallback 6650 GB/s",
-                "note": "algorithmic bytes = kept samples + fp64 moment flushes; the sampler's state is K-sized "
-                        "and lives in registers, so HBM is not the bound (SURVEY.md section 8d)"}}
-
-    # ---- the rest of BASELINE.json's metric, measured the same way -------------------------------------
-    if args.only == "sampler":
-        if rank == 0:
-            print(json.dumps(line), flush=True)
-        return
-    if rank == 0 or world > 1:
-        line["extra"] = extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ranks, barrier,
-                               flush, hbm_peak)
-    if rank == 0 and world == 1:
-        line["cpu_baseline"] = cpu_baseline()
-        line["extra"]["predict_cpu_baseline"] = cpu_predict_baseline()
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    def pipe_peaks(self):
+        if self._pipe_peaks is None:
+            self._pipe_peaks = measure_pipe_peaks(self.torch, self.dev)
+        return self._pipe_peaks
 
 
 def measure_pipe_peaks(torch, dev):
-    """FP32 FMA, MUFU, Philox-mix and dual-issue peaks of this GPU, measured now (bmc_probe)."""
+    """FP32 FMA, FP64-free integer and MUFU issue peaks of this GPU, measured now (libbmc_probe.so)."""
     from pybmc_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_probes()
     sink = torch.zeros(1, dtype=torch.float32, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
-    blocks, threads, iters = 148 * 8, 256, 20000
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks, threads, iters = sms * 8, 256, 20000
     out = {}
-    for kind, name in ((0, "ffma"), (1, "mufu"), (2, "philox_mix"), (3, "issue"), (4, "imad_wide_plus_iadd"),
-                       (5, "imad_hi"), (6, "imad"), (7, "lop3"), (8, "ffma2"), (9, "imad_wide"),
-                       (11, "imad_wide_plus_2ffma")):
+    for kind, name in ((0, "ffma"), (1, "mufu"), (2, "philox_mix"), (3, "issue"), (6, "imad"), (7, "lop3"),
+                       (8, "ffma2"), (9, "imad_wide"), (11, "imad_wide_plus_2ffma")):
         ops = lib.bmc_probe_ops_per_iteration(kind)
         best = None
         for _ in range(3):
@@ -392,95 +406,474 @@ def measure_pipe_peaks(torch, dev):
         thread_ops = float(blocks) * threads * iters * ops
         out[name] = {"Gwarp_inst_per_s": thread_ops / 32 / (best * 1e-3) / 1e9, "ms": best}
     out["ffma"]["TFLOP_per_s"] = out["ffma"]["Gwarp_inst_per_s"] * 32 * 2 / 1e3
+    out["sms"] = sms
     return out
 
 
-_PEAKS = {}
+COUNTER_KEYS = (("fma_pipe_cycles_active_pct", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                ("fma_pipe_cycles_active_pct_busiest_scheduler", "smsp__pipe_fma_cycles_active.max.pct_of_peak_sustained_active"),
+                ("fmaheavy_cycles_active_pct", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active"),
+                ("fmalite_cycles_active_pct", "sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active"),
+                ("alu_pipe_cycles_active_pct", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                ("fp64_pipe_cycles_active_pct", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                ("xu_pipe_inst_pct", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                ("tensor_pipe_cycles_active_pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                ("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                ("issue_active_pct_busiest_scheduler", "smsp__issue_active.max.pct_of_peak_sustained_active"),
+                ("warps_active_pct", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                ("registers_per_thread", "launch__registers_per_thread"),
+                ("ncu_duration_ms", "gpu__time_duration.sum"))
 
 
-def predict_roofline(torch, dev, units_per_s_per_gpu, ms_step):
-    """Issue roofline of the fused prediction step: the tensor-core pass is bound by its consumer
-    (Philox, Box-Muller, compares, predicated counts), not by the MMAs or HBM."""
-    try:
-        c = json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))["predict_pass_tc_f32_k16_q5"]
-    except (OSError, KeyError, ValueError):
+def counters_view(entry):
+    """Hardware counters of the committed ncu capture of a kernel (profiles/kernel_constants.json)."""
+    if not entry:
         return None
-    if "issue" not in _PEAKS:
-        pk = measure_pipe_peaks(torch, dev)
-        _PEAKS["issue"] = max(pk["issue"]["Gwarp_inst_per_s"], pk["ffma"]["Gwarp_inst_per_s"])
-    per_unit = float(c["thread_inst_per_sample_point"]) / 32.0
-    achieved = per_unit * units_per_s_per_gpu / 1e9
-    flops = 2.0 * 16 * 3 * units_per_s_per_gpu / 1e12          # three TF32 products per component
-    return {"kernel": "predict_pass_tc_kernel<16,5> (+ predict_select_kernel)", "bound": "issue", "unit": "Gwarp-inst/s",
-            "achieved": achieved, "peak": _PEAKS["issue"], "frac": achieved / _PEAKS["issue"],
-            "thread_inst_per_sample_point": float(c["thread_inst_per_sample_point"]),
-            "traffic": float(c["dram_bytes_per_launch"]),
-            "tensor": {"kind": "tcgen05.mma kind::tf32, split TF32 (3 products)", "TFLOP_per_s": flops,
-                       "note": "K=16: the MMAs keep the tensor pipe ~3 % busy (ncu); the 16 consumer warps are the bound"},
-            "note": "whole step (pass + select + window set-up) against the pass kernel's instruction count"}
+    c = entry.get("counters", {})
+    out = {name: (c[key] * 1e3 if name == "ncu_duration_ms" else c[key]) for name, key in COUNTER_KEYS if key in c}
+    out["stall_share_pct"] = entry.get("stall_share_pct")
+    out["source"] = f"{entry.get('report')} ({entry.get('report_mtime')}): ncu --set full + pipe-cycle counters, cold clocks " \
+                    "under the profiler: compare SHARES with the live numbers, not absolutes"
+    return out
 
 
-def fma_pipe_view(rate_per_gpu, pipe_peaks):
-    """The sampler's bounding unit is the FMA pipe.  bmc_probe shows that on B200 a 32x32->64 multiply
-    (IMAD.WIDE, two per Philox round) holds the whole pipe for ~4 cycles -- no FFMA flows beside it
-    (IMAD.WIDE + 2 FFMA = 6.1 cycles) -- and that a packed FFMA2 is two FFMA slots.  Work = the kernel's
-    FMA-pipe instructions per warp-iteration (ncu opcode mix, profiles/kernel_constants.json), each class
-    priced in FFMA slots by the rates measured in this run; peak = the measured FFMA rate."""
-    try:
-        mix = json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))[
-            "gibbs_conjugate_f32_k8_full"]["fma_pipe_mix"]
-    except (OSError, KeyError, ValueError):
-        return None
-    ffma = pipe_peaks["ffma"]["Gwarp_inst_per_s"]
-    price = {"fp32": 1.0, "fp32x2": ffma / pipe_peaks["ffma2"]["Gwarp_inst_per_s"],
-             "imad": ffma / pipe_peaks["imad"]["Gwarp_inst_per_s"],
-             "imad_wide": ffma / pipe_peaks["imad_wide"]["Gwarp_inst_per_s"]}
-    slots = sum(float(mix[k]) * price[k] for k in price)                  # FFMA slots per warp-iteration
-    achieved = slots * rate_per_gpu / 32 / 1e9
-    return {"achieved": achieved, "peak": ffma, "frac": achieved / ffma, "ffma_slots_per_warp_iter": slots,
-            "price_in_ffma_slots": price, "mix_per_warp_iter": mix}
+def sampler_roofline(b, key, kernel_name, rate_per_gpu, ms_step, kept_bytes_per_chain, real_bytes):
+    """The sampler has no HBM or tensor traffic to speak of (state in registers, no GEMM): its bound is the FMA
+    pipe (Philox 32x32->64 multiplies + fp32/fp64 arithmetic).  Live view: FMA-pipe instructions of one
+    warp-iteration (opcode mix of the committed ncu capture) priced in FFMA issue slots by the probe rates of THIS
+    run, against the FFMA rate of this run.  Counter view: what the hardware counted in the capture
+    (sm__pipe_fma_cycles_active and friends) -- the corroboration the live model has to live with."""
+    entry = b.constants.get(key) or {}
+    pk = b.pipe_peaks()
+    ffma = pk["ffma"]["Gwarp_inst_per_s"]
+    out = {"kernel": kernel_name, "bound": "fma-pipe", "unit": "Gwarp-inst/s (FFMA issue slots)",
+           "achieved": None, "peak": ffma, "frac": None,
+           "peak_source": "FFMA rate measured in this run by libbmc_probe (independent streams, all SMs)"}
+    mix = entry.get("fma_pipe_mix")
+    if mix:
+        price = {"fp32": 1.0, "fp32x2": ffma / pk["ffma2"]["Gwarp_inst_per_s"],
+                 "imad": ffma / pk["imad"]["Gwarp_inst_per_s"], "imad_wide": ffma / pk["imad_wide"]["Gwarp_inst_per_s"]}
+        slots = sum(float(mix[k]) * price[k] for k in price)
+        fp64_slots = float(entry.get("fp64_per_unit") or 0.0)
+        out.update({"achieved": slots * rate_per_gpu / 32 / 1e9, "frac": slots * rate_per_gpu / 32 / 1e9 / ffma,
+                    "ffma_slots_per_warp_iteration": slots, "price_in_ffma_slots": price, "mix_per_warp_iteration": mix,
+                    "fp64_instructions_per_warp_iteration": fp64_slots,
+                    "mufu_per_warp_iteration": entry.get("mufu_per_unit"),
+                    "warp_inst_per_warp_iteration": entry.get("warp_inst_per_warp_unit")})
+        inst = entry.get("warp_inst_per_warp_unit")
+        if inst:
+            issue_peak = max(pk["issue"]["Gwarp_inst_per_s"], ffma)
+            out["issue"] = {"achieved": inst * rate_per_gpu / 32 / 1e9, "peak": issue_peak,
+                            "frac": inst * rate_per_gpu / 32 / 1e9 / issue_peak, "unit": "Gwarp-inst/s"}
+    out["counters"] = counters_view(entry)
+    if out["counters"] and "fma_pipe_cycles_active_pct" in out["counters"]:
+        out["frac_by_counter"] = out["counters"]["fma_pipe_cycles_active_pct"] / 100.0
+    out["traffic"] = entry.get("dram_bytes_per_launch")
+    alg = CHAINS_PER_GPU * (KEEP_PER_CHAIN * kept_bytes_per_chain * real_bytes + 54 * 8 * 2 * (ITERATIONS // 64))
+    out["hbm"] = {"algorithmic_bytes_per_launch": alg, "achieved": alg / (ms_step * 1e-3) / 1e9,
+                  "peak": float(b.peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
+                  "frac": alg / (ms_step * 1e-3) / 1e9 / float(b.peaks.get("hbm_gbs", 6650.0)),
+                  "note": "kept samples + fp64 moment flushes; not the bound (SURVEY.md section 8d)"}
+    out["pipe_peaks_measured"] = pk
+    return out
 
 
-def load_inst_per_iter():
-    try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))[
-            "gibbs_conjugate_f32_k8_full"]["warp_inst_per_chain_iter"])
-    except (OSError, KeyError, ValueError):
-        return None
+class SamplerWorkload:
+    """BASELINE configs[2] through pybmc_b200.parallel.sharded_gibbs."""
+
+    def __init__(self, b):
+        import pybmc_b200 as pb
+        from pybmc_b200.inference_utils import ConjugateSampler
+        self.b = b
+        preds, truth = config3_ensemble()
+        orth = pb.orthogonalize_arrays(preds, truth, 8, device=b.dev)
+        self.y, self.X = np.ascontiguousarray(orth["y"]), np.ascontiguousarray(orth["U_hat"])
+        self.prior = [np.zeros(8), np.diag(orth["S_hat"] ** 2), 1.0, 0.02]
+        self.sampler = ConjugateSampler(self.y, self.X, self.prior, device=b.dev)
+        self.thin = ITERATIONS // KEEP_PER_CHAIN
+
+    def step_resident(self, dtype, hist=HIST_EVERY, iterations=ITERATIONS):
+        """One step with the problem resident in HBM: this rank's chains, the all-reduces, device results."""
+        from pybmc_b200 import parallel as par
+        return par.sharded_gibbs(None, None, iterations, self.prior, CHAINS_PER_GPU * self.b.world, seed=SEED,
+                                 dtype=dtype, thin=iterations // KEEP_PER_CHAIN, keep_samples=True, hist_every=hist,
+                                 as_numpy=False, sampler=self.sampler, device=self.b.dev)
+
+    def step_e2e(self, dtype):
+        """The public call from host arrays to host results (set-up, sufficient statistics, sampler, all-reduces,
+        D2H of moments, histograms and kept samples)."""
+        from pybmc_b200 import parallel as par
+        return par.sharded_gibbs(self.y, self.X, ITERATIONS, self.prior, CHAINS_PER_GPU * self.b.world, seed=SEED,
+                                 dtype=dtype, thin=self.thin, keep_samples=True, hist_every=HIST_EVERY,
+                                 device=self.b.dev)
+
+    def measure(self, dtype, steps, warmup, with_clocks=False):
+        b = self.b
+        torch_dtype = {"f32": "float32", "f64": "float64"}[dtype]
+        clocks = ClockSampler(b.local).start() if (with_clocks and b.rank == 0) else None
+        ms_step = b.timed(lambda: self.step_resident(torch_dtype), steps, warmup)
+        clock_info = clocks.stop() if clocks else None
+        units = CHAINS_PER_GPU * b.world * ITERATIONS
+        value = units / (ms_step * 1e-3)
+        e2e_s, out = b.wall(lambda: self.step_e2e(torch_dtype), steps, max(3, warmup))
+        mean, cov, local = out
+        real_bytes = 4 if dtype == "f32" else 8
+        h2d = self.y.nbytes + self.X.nbytes + 8 * (8 + 6 * 8 + 2)          # design + OLS vector + problem constants
+        d2h = local.samples.nbytes + 8 * (55 + 9 * 9 + 1) + 8 * 9 * 512
+        kernel = f"gibbs_conjugate_kernel<{'float' if dtype == 'f32' else 'double'}, 8, 2, true>"
+        block = {"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_step, "dtype": dtype,
+                 "higher_is_better": True, "config": workload_config(b.world, dtype),
+                 "e2e": {"value": units / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s,
+                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                         "api": "pybmc_b200.parallel.sharded_gibbs(y, X, ...) from host NumPy arrays"},
+                 "gpu_launches": steps * 1 + steps * 5,
+                 "gpu_launches_detail": "value region: 1 kernel per step (gibbs_conjugate_kernel); e2e region: 5 per "
+                                        "step (gram_partial, sum_partials, rss_partial, sum_partials, "
+                                        "gibbs_conjugate_kernel); the reduction of the moment rows over chains and the "
+                                        "sample transpose are torch ops",
+                 "posterior_check": {"sigma_mean": float(mean[-1]), "b0_mean": float(mean[0]),
+                                     "sigma_q50_from_histogram": float(local.quantiles([50.0])[0, -1])}}
+        key = "gibbs_conjugate_f32_k8_full" if dtype == "f32" else "gibbs_conjugate_f64_k8_full"
+        block["roofline"] = sampler_roofline(b, key, kernel, value / b.world, ms_step, 9, real_bytes)
+        if clock_info is not None:
+            block["clocks"] = clock_info
+        return block
 
 
-def load_dram_bytes():
-    try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))[
-            "gibbs_conjugate_f32_k8_full"]["dram_bytes_per_launch"])
-    except (OSError, KeyError, ValueError):
-        return None
+class PredictWorkload:
+    """BASELINE configs[3]: fused prediction, nuclei sharded over ranks."""
+
+    def __init__(self, b):
+        from pybmc_b200 import _lib
+        from pybmc_b200 import parallel as par
+        from pybmc_b200.sampling_utils import PredictiveProblem
+        self.b = b
+        self.lo, self.hi = par.point_range(PRED_POINTS, b.rank, b.world)
+        self.preds, self.vt, self.theta, self.truth = config4_inputs(PRED_POINTS, PRED_DRAWS, PRED_K)
+        self.prob = PredictiveProblem(self.preds[self.lo:self.hi], self.theta, self.vt, truth=self.truth[self.lo:self.hi],
+                                      dtype="float32", device=b.dev, point0=self.lo)
+        nbytes = int(b.lib.bmc_predict_workspace_bytes(_lib.F32, self.hi - self.lo, len(PRED_Q), PRED_DRAWS))
+        self.ws = b.torch.empty(nbytes, dtype=b.torch.uint8, device=b.dev)
+        self.p_h = np.ascontiguousarray(self.preds[self.lo:self.hi])
+        self.t_h = np.ascontiguousarray(self.truth[self.lo:self.hi])
+
+    def step_resident(self):
+        self.last = self.prob.run(percentiles=PRED_Q, seed=SEED, as_numpy=False, workspace=self.ws)
+
+    def step_e2e(self):
+        """Host arrays in (this rank's block of predictions and truth; the posterior rows -- uploaded once by rank
+        0 and broadcast), host results out: every rank ends with the full-length outputs."""
+        from pybmc_b200 import parallel as par
+        return par.sharded_predictive_summary(self.p_h, self.theta, self.vt, truth=self.t_h, percentiles=PRED_Q,
+                                              seed=SEED, dtype="float32", device=self.b.dev,
+                                              n_points_total=PRED_POINTS)
+
+    def measure(self, steps, warmup):
+        b = self.b
+        ms = b.timed(self.step_resident, steps, warmup)
+        units = PRED_POINTS * PRED_DRAWS
+        value = units / (ms * 1e-3)
+        e2e_s, res = b.wall(self.step_e2e, steps, max(2, warmup))
+        assert res.mean.shape[0] == PRED_POINTS
+        h2d = self.p_h.nbytes + self.t_h.nbytes + self.vt.nbytes + (self.theta.nbytes if b.rank == 0 else 0)
+        block = {"metric": PRED_METRIC, "value": value, "unit": PRED_UNIT, "ms_per_step": ms, "dtype": "f32",
+                 "higher_is_better": True, "passes": self.last.passes, "config": pred_config(b.world),
+                 "e2e": {"value": units / e2e_s, "unit": PRED_UNIT, "ms_per_step": 1e3 * e2e_s,
+                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(PRED_POINTS * 8 * (4 + len(PRED_Q))),
+                         "collectives": "broadcast(theta 13.6 MB fp64, src 0) + all_gather(9 x nuclei fp64)" if b.world > 1
+                         else "none (1 GPU)",
+                         "api": "pybmc_b200.parallel.sharded_predictive_summary from host NumPy arrays"},
+                 "roofline": self.roofline(value / b.world)}
+        return block
+
+    def roofline(self, units_per_s_per_gpu):
+        """The fused pass is bound by its consumer loop (Philox, Box-Muller, compares, predicated counts): issue
+        slots.  Live: thread-instructions per sample x point of the committed capture x the live rate against the
+        issue peak measured in this run; counters of the capture beside it."""
+        b = self.b
+        entry = b.constants.get("predict_pass_tc_f32_k16_q5") or {}
+        c = entry.get("counters", {})
+        pk = b.pipe_peaks()
+        issue_peak = max(pk["issue"]["Gwarp_inst_per_s"], pk["ffma"]["Gwarp_inst_per_s"])
+        out = {"kernel": "predict_pass_tc_kernel<16,5> (+ predict_select_kernel)", "bound": "issue", "unit": "Gwarp-inst/s",
+               "achieved": None, "peak": issue_peak, "frac": None,
+               "note": "whole step (pass + select + window set-up) against the pass kernel's instruction count"}
+        per_unit = None
+        if "thread_inst_per_sample_point" in entry:
+            per_unit = float(entry["thread_inst_per_sample_point"])
+        elif c.get("smsp__thread_inst_executed.sum") and entry.get("units_per_launch"):
+            per_unit = c["smsp__thread_inst_executed.sum"] / entry["units_per_launch"]
+        elif c.get("smsp__inst_executed.sum") and c.get("launch__grid_size"):
+            # one launch = (blocks x 128 nuclei, padded) x all draws of its sample slots: nuclei x draws of the chunk
+            chunk_points = c["launch__grid_size"] / max(1, round(c["launch__grid_size"] / (PRED_POINTS / 4 / 128))) * 128
+            per_unit = c["smsp__inst_executed.sum"] * 32 / (chunk_points * PRED_DRAWS)
+        if per_unit:
+            ach = per_unit / 32.0 * units_per_s_per_gpu / 1e9
+            out.update({"achieved": ach, "frac": ach / issue_peak, "thread_inst_per_sample_point": per_unit})
+        out["tensor"] = {"kind": "tcgen05.mma kind::tf32, split TF32 (3 products)",
+                         "TFLOP_per_s": 2.0 * PRED_K * 3 * units_per_s_per_gpu / 1e12,
+                         "note": "K=16: the MMAs keep the tensor pipe a few % busy (ncu); the 16 consumer warps are the bound"}
+        out["counters"] = counters_view(entry)
+        if out["counters"] and "issue_active_pct" in out["counters"]:
+            out["frac_by_counter"] = out["counters"]["issue_active_pct"] / 100.0
+        out["traffic"] = entry.get("dram_bytes_per_launch")
+        out["algorithmic_bytes_per_step"] = 8 * (PRED_DRAWS * (PRED_K + 1) + PRED_POINTS * (PRED_K + 2)) + 40 * PRED_POINTS
+        sel = b.constants.get("predict_select_f32")
+        if sel:
+            out["select_kernel_counters"] = counters_view(sel)
+        return out
 
 
-def extras(args, torch, dist, dev, world, rank, sampler, pb, timed, max_over_ranks, barrier, flush, hbm_peak,
-           only_predict=False):
+def run_native(args):
+    b = Bench(args)
+    torch, world, rank = b.torch, b.world, b.rank
+    line = {}
+    want_gibbs = args.metric == "gibbs" or args.only == "all"
+    want_predict = args.metric == "predict" or args.only == "all"
+    if args.only == "sampler":
+        want_predict = False
+    if args.only == "predict":
+        want_gibbs = False
+
+    sw = SamplerWorkload(b) if want_gibbs else None
+    gibbs = {}
+    if sw is not None:
+        order = ["f32", "f64"] if args.dtype == "f32" else ["f64", "f32"]
+        if args.only == "sampler":
+            order = order[:1]
+        for i, dt in enumerate(order):
+            gibbs[dt] = sw.measure(dt, args.steps, args.warmup, with_clocks=(i == 0 and args.metric == "gibbs"))
+    predict = None
+    if want_predict:
+        pw = PredictWorkload(b)
+        clocks = ClockSampler(b.local).start() if (args.metric == "predict" and rank == 0) else None
+        predict = pw.measure(args.steps if args.metric == "predict" else min(args.steps, 3), max(args.warmup, 2)
+                             if args.metric == "predict" else 2)
+        if clocks:
+            predict["clocks"] = clocks.stop()
+        del pw
+        torch.cuda.empty_cache()
+
+    common = {"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "scaling": "weak", "vs_baseline": None,
+              "data": "synthetic"}
+    if args.metric == "predict":
+        line = {**predict, **common}
+        if gibbs:
+            line["gibbs"] = gibbs.get("f32")
+            line["f64"] = gibbs.get("f64")
+        line["scaling"] = "strong"           # 1e5 nuclei in total, split over the ranks
+    else:
+        head = gibbs[args.dtype]
+        line = {**head, **common}
+        other = "f64" if args.dtype == "f32" else "f32"
+        if other in gibbs:
+            line[other] = gibbs[other]
+        if predict is not None:
+            line["predict"] = predict
+
+    if args.only == "all" and not args.no_extras:
+        line["extra"] = extras(b, sw)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cg, cp = cpu_baselines(want_gibbs, want_predict)
+        if cg:
+            (line if args.metric == "gibbs" else line.get("gibbs", {}))["cpu_baseline"] = cg
+            if "f64" in line and isinstance(line["f64"], dict):
+                line["f64"]["cpu_baseline"] = cg
+            if "f32" in line and isinstance(line["f32"], dict):
+                line["f32"]["cpu_baseline"] = cg
+        if cp:
+            (line if args.metric == "predict" else line.get("predict", {}))["cpu_baseline"] = cp
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        b.dist.destroy_process_group()
+
+
+def cpu_baselines(want_gibbs, want_predict):
+    """Reference algorithm (oracle port) on the host cores, bounded samples of the same workloads."""
+    import multiprocessing as mp
+    os.environ["OMP_NUM_THREADS"] = "1"
+    cores = os.cpu_count() or 1
+    cg = cp = None
+    with mp.get_context("fork").Pool(cores) as pool:
+        if want_gibbs:
+            problem = cpu_problem()
+            iters = 60000
+            cpu_sampler_rate(100, pool, cores, problem)
+            rate, dt = cpu_sampler_rate(iters, pool, cores, problem)
+            cg = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+                  "sample": gibbs_sample_text(cores, iters)}
+        if want_predict:
+            inputs = config4_inputs(CPU_PRED_POINTS, CPU_PRED_DRAWS + 2000)
+            rate, dt = cpu_predict_rate(pool, cores, inputs)
+            cp = {"value": rate, "unit": PRED_UNIT, "cores": cores, "kind": "port", "seconds": dt,
+                  "sample": predict_sample_text(cores, dt)}
+    return cg, cp
+
+
+# ------------------------------------------------------------------------------------------------
+# extras: the other configurations of BASELINE.json and the pieces around the two metrics
+# ------------------------------------------------------------------------------------------------
+def extras(b, sw):
     out = {}
     steps = 3
-    timed_main = timed
-    timed = lambda fn, k, w: timed_main(fn, k, max(w, 2), robust=True)   # noqa: E731
-    if not only_predict:
-        extras_samplers(out, timed, sampler, pb, dev, world, rank, steps)
-    extras_predict(out, args, torch, dev, world, rank, timed, barrier, flush, hbm_peak, steps, only_predict)
-    if not only_predict:
-        extras_config5(out, torch, dev, world, rank, timed, pb, steps, hbm_peak)
-        if rank == 0:
-            extras_config0(out, torch, pb, dev)
-    barrier()
+    timed = lambda fn, k=steps, w=2: b.timed(fn, k, w, robust=True)   # noqa: E731
+    if sw is not None:
+        extras_samplers(out, b, sw, timed)
+    extras_coverage(out, b)
+    extras_config4(out, b)
+    if b.rank == 0:
+        extras_config0(out, b)
+    b.barrier()
     return out
 
 
-def extras_config0(out, torch, pb, dev):
+def extras_samplers(out, b, sw, timed):
+    import pybmc_b200 as pb
+    from pybmc_b200 import _lib
+    from pybmc_b200.inference_utils import SimplexSampler
+    torch, dev, world, rank = b.torch, b.dev, b.world, b.rank
+    # what the marginal histograms cost: the same step without them
+    for dt, name in (("float32", "f32"), ("float64", "f64")):
+        ms = timed(lambda: sw.step_resident(dt, hist=0))
+        out[f"gibbs_{name}_without_histograms"] = {"value": CHAINS_PER_GPU * world * ITERATIONS / (ms * 1e-3), "unit": UNIT,
+                                                   "ms_per_step": ms}
+    # simplex sampler, BASELINE configs[1]: nuclear-mass surrogate, 4096 chains per GPU
+    preds, truth = config1_ensemble()
+    idx = np.random.default_rng(1).permutation(len(truth))[:377]
+    o = pb.orthogonalize_arrays(preds[idx], truth[idx], 3, device=dev)
+    simplex = SimplexSampler(o["y"], o["U_hat"], o["Vt_hat"], o["S_hat"], [1.0, 0.02], 0.001, device=dev)
+    burn, iters, chains = 10000, 50000, 4096
+    ms = timed(lambda: simplex.run(iters, burn, chains, SEED, "float32", iters // 10, True, "full", rank * chains))
+    out["simplex_f32"] = {"value": chains * world * (burn + iters) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                          "config": "configs[1] surrogate: 377 x 15, K=3, 4096 chains/GPU x (10000 burn + 50000)",
+                          "counters": counters_view(b.constants.get("gibbs_simplex_group16_f32_k4"))}
+    ms = timed(lambda: simplex.run(iters, burn, chains, SEED, "float64", iters // 10, True, "full", rank * chains))
+    out["simplex_f64"] = {"value": chains * world * (burn + iters) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                          "config": "the same in fp64"}
+    # the literal one-chain-per-warp kernel (parity anchor): redoes the O(nK) residual every iteration
+    s = sw.sampler
+    n, k = s.n, s.k
+    xt = s._Xd.t().contiguous().to(torch.float32)
+    yr = s._yd.to(torch.float32)
+    consts = torch.from_numpy(np.concatenate([s.lam.reshape(-1), s.lam @ s.b0])).to(dev)
+    lit_chains, lit_iters = 8192, 200
+    buf = torch.empty((lit_iters, k + 1, lit_chains), dtype=torch.float32, device=dev)
+
+    def lit_step():
+        _lib.check(b.lib.bmc_gibbs_literal_run(_lib.F32, xt.data_ptr(), yr.data_ptr(), n, k, consts.data_ptr(),
+                                               consts.data_ptr() + 8 * k * k, s.nu0, s.sigma20, s.sigma2_init, SEED,
+                                               rank * lit_chains, lit_chains, lit_iters, buf.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream))
+    ms = timed(lit_step)
+    rate = lit_chains * world * lit_iters / (ms * 1e-3)
+    out["literal_f32"] = {"value": rate, "unit": UNIT, "ms_per_step": ms,
+                          "reference_equivalent_tflops": rate * (4 * n * k + 3 * n) / 1e12,
+                          "config": "same problem, one chain per warp, X in shared memory via TMA, residual over all "
+                                    "3000 rows each iteration; 8192 chains x 200 iterations per GPU"}
+
+
+def extras_coverage(out, b):
+    """An HBM-bound kernel of the path: order counts of a materialised matrix (coverage())."""
+    from pybmc_b200 import _lib
+    torch, dev = b.torch, b.dev
+    if b.rank != 0:
+        return
+    s_rows, n_cols = 10000, 65536
+    mat = torch.randn((s_rows, n_cols), dtype=torch.float64, device=dev)
+    tr = torch.zeros(n_cols, dtype=torch.float64, device=dev)
+    c1 = torch.empty(n_cols, dtype=torch.int64, device=dev)
+    c2 = torch.empty(n_cols, dtype=torch.int64, device=dev)
+
+    def cov_step():
+        _lib.check(b.lib.bmc_coverage_counts(mat.data_ptr(), s_rows, n_cols, n_cols, tr.data_ptr(), c1.data_ptr(),
+                                             c2.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    for _ in range(2):
+        cov_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b.flush.add_(1)
+    e0.record(); cov_step(); e1.record(); e1.synchronize()
+    hbm_peak = float(b.peaks.get("hbm_gbs", 6650.0))
+    gbs = mat.numel() * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    out["coverage_counts_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": gbs / hbm_peak, "config": "10000 x 65536 fp64 matrix read once",
+                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs" if b.peaks else "fallback 6650 GB/s"}
+    del mat
+
+
+def extras_config4(out, b):
+    """BASELINE configs[4] END TO END through pybmc_b200.parallel: 256 models x 1e5 points (rows sharded over the
+    ranks), K = 64: sharded_orthogonalize (all-reduce of the 256 x 256 Gram matrix) -> sharded_gibbs(rows_sharded)
+    at K = 64 (all-reduce of X'X, X'y, y'y, n, RSS_min; then of the moment sums) -> sharded_predictive_summary on
+    the same 1e5 points with 1e4 posterior draws (broadcast + all-gather).  Host arrays in, host results out."""
+    from pybmc_b200 import parallel as par
+    torch, world, rank, dev = b.torch, b.world, b.rank, b.dev
+    n_total, m, k = 100_000, 256, 64
+    lo, hi = par.point_range(n_total, rank, world)
+    preds, truth = config5_rows(lo, hi, m, k)
+    chains_total, iters, keep = 16384 * world, 1000, 10
+    n_draws = 10000
+
+    def wall(fn):
+        b.barrier()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        return b.max_over_ranks(time.perf_counter() - t0) * 1e3, r
+
+    res = {}
+    for rep in range(2):            # second pass: warm allocator, NCCL channels and cuSOLVER handles
+        ms_o, orth = wall(lambda: par.sharded_orthogonalize(preds, truth, k, device=dev))
+        prior = [np.zeros(k), np.diag(orth["S_hat"] ** 2), 1.0, 0.02]
+        ms_g, (mean, cov, local) = wall(lambda: par.sharded_gibbs(
+            orth["y"], orth["U_hat"], iters, prior, chains_total, seed=SEED + 5, dtype="float32", thin=iters // keep,
+            keep_samples=True, device=dev, rows_sharded=True))
+        # 1e4 posterior rows for the prediction: the kept draws of this rank's first chains (same rows on every
+        # rank would need an all-gather; rank 0's are broadcast by sharded_predictive_summary)
+        theta = np.ascontiguousarray(local.samples[:n_draws]).astype(np.float64)
+        ms_p, pred = wall(lambda: par.sharded_predictive_summary(
+            preds, theta, orth["Vt_hat"], truth=truth, percentiles=[2.5, 50.0, 97.5], seed=SEED + 6, dtype="float32",
+            device=dev, n_points_total=n_total))
+        res = {"orthogonalize_ms": ms_o, "gibbs_ms": ms_g, "predict_ms": ms_p, "total_ms": ms_o + ms_g + ms_p}
+    from pybmc_b200.sampling_utils import coverage_from_counts
+    cover = coverage_from_counts([68, 95], n_draws, pred.c_lt, pred.c_le, device=dev) if rank == 0 else None
+    out["config4_end_to_end"] = {
+        "config": f"configs[4]: 1e5 x 256 fp64 table, rows over {world} GPU(s) ({hi - lo} here), K=64; sampler "
+                  f"{chains_total} chains x {iters} iterations fp32 (marginal moments); prediction 1e5 nuclei x {n_draws} "
+                  "draws x K=64, 3 percentiles + coverage counts",
+        **res, "method": orth["method"],
+        "gibbs_chain_iters_per_sec": chains_total * iters / (res["gibbs_ms"] * 1e-3),
+        "predict_samples_x_points_per_sec": float(n_total) * n_draws / (res["predict_ms"] * 1e-3),
+        "collectives": "all_reduce(Gram 256x256 fp64 = 512 KB); all_reduce([X|y]'[X|y] 65x65, n, RSS_min); "
+                       "all_reduce(moment sums); broadcast(theta 5.2 MB); all_gather(7 x nuclei fp64)" if world > 1
+        else "none (1 GPU)",
+        "check": {"sigma_posterior_mean": float(mean[-1]), "S_hat_first_last": [float(orth["S_hat"][0]), float(orth["S_hat"][-1])],
+                  "coverage_68_95_pct": cover}}
+    # device-only stage times of the same problem (resident inputs), for the share of the collectives / copies
+    from pybmc_b200.inference_utils import ConjugateSampler
+    from pybmc_b200 import _lib
+    smp = ConjugateSampler(orth["y"], orth["U_hat"], prior, device=dev, reduce=par.sum_over_ranks())
+    per = chains_total // world
+    ms = b.timed(lambda: smp.run(iters, per, SEED + 5, "float32", iters // keep, 0, True, "diag", rank * per), 3, 2, robust=True)
+    out["config4_end_to_end"]["gibbs_kernel_only"] = {
+        "ms": ms, "chain_iters_per_sec": chains_total * iters / (ms * 1e-3),
+        "kernel": "gibbs_conjugate_kernel<float, 64, 1>", "counters": counters_view(b.constants.get("gibbs_conjugate_f32_k64_diag"))}
+    ms64 = b.timed(lambda: smp.run(iters // 4, per, SEED + 5, "float64", iters // keep, 0, False, "diag", rank * per), 3, 1,
+                   robust=True)
+    out["config4_end_to_end"]["gibbs_kernel_only_f64"] = {"ms": ms64, "chain_iters_per_sec": chains_total * (iters // 4) / (ms64 * 1e-3)}
+    del smp, preds
+
+
+def extras_config0(out, b):
     """BASELINE configs[0], the reference's own workflow through the drop-in class (surrogate for the absent
     selected_data.h5: 629 nuclei x 15 models, 377 training rows, K = 3): wall-clock of each public call,
     second call of a process (the first also pays one-time CUDA / cuSOLVER initialisation)."""
     import contextlib
     import io
     import pandas as pd
+    import pybmc_b200 as pb
+    torch, dev = b.torch, b.dev
     preds, truth = config1_ensemble()
     models = [f"m{i}" for i in range(preds.shape[1])]
     df = pd.DataFrame(preds, columns=models)
@@ -510,241 +903,23 @@ def extras_config0(out, torch, pb, dev):
                                                  "(NumPy, one core): ~7000 / 840 / 2500 ms for train / predict2 / evaluate")
 
 
-def extras_samplers(out, timed, sampler, pb, dev, world, rank, steps):
-    from pybmc_b200.inference_utils import SimplexSampler
-    chain0 = rank * CHAINS_PER_GPU
-    thin = ITERATIONS // KEEP_PER_CHAIN
-    # conjugate sampler in fp64 (the reference's arithmetic type)
-    ms = timed(lambda: sampler.run(ITERATIONS // 4, CHAINS_PER_GPU, SEED, "float64", thin, 0, True, "full", chain0),
-               steps, 1)
-    out["gibbs_f64"] = {"value": CHAINS_PER_GPU * world * (ITERATIONS // 4) / (ms * 1e-3), "unit": UNIT,
-                        "ms_per_step": ms, "config": "same problem, fp64 arithmetic, 2500 iterations per chain"}
-
-    # simplex sampler, BASELINE configs[1]: nuclear-mass surrogate, 4096 chains per GPU
-    preds, truth = config1_ensemble()
-    rng = np.random.default_rng(1)
-    idx = rng.permutation(len(truth))[:377]
-    o = pb.orthogonalize_arrays(preds[idx], truth[idx], 3)
-    simplex = SimplexSampler(o["y"], o["U_hat"], o["Vt_hat"], o["S_hat"], [1.0, 0.02], 0.001, device=dev)
-    burn, iters, chains = 10000, 50000, 4096
-    ms = timed(lambda: simplex.run(iters, burn, chains, SEED, "float32", iters // 10, True, "full", rank * chains),
-               steps, 1)
-    out["simplex_f32"] = {"value": chains * world * (burn + iters) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-                          "config": "configs[1] surrogate: 377 x 15, K=3, 4096 chains/GPU x (10000 burn + 50000)"}
-
-    # the literal one-chain-per-warp kernel (parity anchor): redoes the O(nK) residual every iteration
-    import torch
-    from pybmc_b200 import _lib
-    lib = _lib.load()
-    n, k = sampler.n, sampler.k
-    xt = sampler._Xd.t().contiguous().to(torch.float32)
-    yr = sampler._yd.to(torch.float32)
-    consts = torch.from_numpy(np.concatenate([sampler.lam.reshape(-1), sampler.lam @ sampler.b0])).to(dev)
-    lit_chains, lit_iters = 8192, 200
-    buf = torch.empty((lit_iters, k + 1, lit_chains), dtype=torch.float32, device=dev)
-
-    def lit_step():
-        _lib.check(lib.bmc_gibbs_literal_run(_lib.F32, xt.data_ptr(), yr.data_ptr(), n, k, consts.data_ptr(),
-                                             consts.data_ptr() + 8 * k * k, sampler.nu0, sampler.sigma20,
-                                             sampler.sigma2_init, SEED, rank * lit_chains, lit_chains, lit_iters,
-                                             buf.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
-    ms = timed(lit_step, steps, 1)
-    rate = lit_chains * world * lit_iters / (ms * 1e-3)
-    out["literal_f32"] = {"value": rate, "unit": UNIT, "ms_per_step": ms,
-                          "reference_equivalent_tflops": rate * (4 * n * k + 3 * n) / 1e12,
-                          "config": "same problem, one chain per warp, X in shared memory via TMA, residual over all "
-                                    "3000 rows each iteration; 8192 chains x 200 iterations per GPU"}
-
-
-
-def extras_predict(out, args, torch, dev, world, rank, timed, barrier, flush, hbm_peak, steps, only_predict):
-    from pybmc_b200.sampling_utils import PredictiveProblem
-    from pybmc_b200 import _lib
-    lib = _lib.load()
-    # fused prediction, BASELINE configs[3]: 1e5 nuclei (sharded over ranks) x 1e5 draws x K=16
-    n_total, n_draws = 100_000, 100_000
-    per = -(-n_total // world) // 4 * 4 + (4 if (-(-n_total // world)) % 4 else 0)
-    lo, hi = min(rank * per, n_total), min((rank + 1) * per, n_total)
-    preds, vt, theta, truth = config4_inputs(n_total, n_draws)
-    prob = PredictiveProblem(preds[lo:hi], theta, vt, truth=truth[lo:hi], dtype="float32", device=dev, point0=lo)
-    nbytes = int(lib.bmc_predict_workspace_bytes(_lib.F32, hi - lo, 5, n_draws))
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    q = [2.5, 16.0, 50.0, 84.0, 97.5]
-    holder = {}
-
-    def pred_step():
-        holder["r"] = prob.run(percentiles=q, seed=SEED, as_numpy=False, workspace=ws)
-    ms = timed(pred_step, steps, 1)
-    out["predict_f32"] = {"metric": "posterior_pred_samples_x_points_per_sec",
-                          "value": n_total * n_draws / (ms * 1e-3), "unit": "samples*points/s", "ms_per_step": ms,
-                          "passes": holder["r"].passes,
-                          "roofline": predict_roofline(torch, dev, n_total * n_draws / (ms * 1e-3) / world, ms),
-                          "config": "configs[3]: 1e5 nuclei x 1e5 draws x K=16, mean/var/5 percentiles/coverage "
-                                    "counts, no S x N matrix, nuclei sharded over ranks"}
-    del prob, ws
-
-    # the same step end to end through the public call: host arrays in (this rank's predictions, truth, all
-    # posterior rows), host results out (mean, variance, percentiles, order counts)
-    from pybmc_b200.sampling_utils import predictive_summary
-    p_h, t_h = np.ascontiguousarray(preds[lo:hi]), np.ascontiguousarray(truth[lo:hi])
-
-    def pred_e2e():
-        return predictive_summary(p_h, theta, vt, truth=t_h, percentiles=q, seed=SEED, dtype="float32",
-                                  subsample=False, device=dev, point0=lo)
-    for _ in range(2):
-        r = pred_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        r = pred_e2e()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / steps
-    if world > 1:
-        import torch.distributed as dist
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    out["predict_f32"]["e2e"] = {
-        "value": n_total * n_draws / e2e_s, "unit": "samples*points/s", "ms_per_step": 1e3 * e2e_s,
-        "h2d_bytes_per_step": int(p_h.nbytes + t_h.nbytes + theta.nbytes + vt.nbytes),
-        "d2h_bytes_per_step": int((hi - lo) * 8 * (2 + len(q) + 2))}
-    del r
-
-    # an HBM-bound kernel of the path: order counts of a materialised matrix (coverage())
-    if rank == 0 and not only_predict:
-        s_rows, n_cols = 10000, 65536
-        mat = torch.randn((s_rows, n_cols), dtype=torch.float64, device=dev)
-        tr = torch.zeros(n_cols, dtype=torch.float64, device=dev)
-        c1 = torch.empty(n_cols, dtype=torch.int64, device=dev)
-        c2 = torch.empty(n_cols, dtype=torch.int64, device=dev)
-
-        def cov_step():
-            _lib.check(lib.bmc_coverage_counts(mat.data_ptr(), s_rows, n_cols, n_cols, tr.data_ptr(), c1.data_ptr(),
-                                               c2.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
-        for _ in range(2):
-            cov_step()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush_l2(torch, flush)
-        e0.record(); cov_step(); e1.record(); e1.synchronize()
-        gbs = mat.numel() * 8 / (e0.elapsed_time(e1) * 1e-3) / 1e9
-        out["coverage_counts_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                                      "frac": gbs / hbm_peak, "config": "10000 x 65536 fp64 matrix read once"}
-        del mat
-    barrier()
-    return out
-
-
-def extras_config5(out, torch, dev, world, rank, timed, pb, steps, hbm_peak):
-    """BASELINE configs[4]: 256 models x 1e5 points, K = 64 (rows sharded over ranks for the projection)."""
-    from pybmc_b200 import _lib
-    lib = _lib.load()
-    n_total, m, k = 100_000, 256, 64
-    n = n_total // world
-    gen = torch.Generator(device=dev).manual_seed(1005 + rank)
-    latent = torch.randn((n, k), generator=gen, device=dev, dtype=torch.float64) * torch.logspace(
-        0, -3, k, device=dev, dtype=torch.float64)
-    mix = torch.randn((k, m), generator=torch.Generator(device=dev).manual_seed(7), device=dev, dtype=torch.float64)
-    preds = (torch.rand((n, 1), generator=gen, device=dev, dtype=torch.float64) * 1900 + 100
-             + 30 * latent @ mix + 0.05 * torch.randn((n, m), generator=gen, device=dev, dtype=torch.float64))
-    truth = preds.mean(dim=1)
-    mu = torch.empty(n, dtype=torch.float64, device=dev)
-    y = torch.empty(n, dtype=torch.float64, device=dev)
-    xc = torch.empty((n, m), dtype=torch.float64, device=dev)
-    gram = torch.empty((m, m), dtype=torch.float64, device=dev)
-    ws = torch.empty(int(lib.bmc_gram_workspace_bytes(n, m)), dtype=torch.uint8, device=dev)
-    vt = torch.randn((k, m), generator=torch.Generator(device=dev).manual_seed(8), device=dev, dtype=torch.float64)
-    u = torch.empty((n, k), dtype=torch.float64, device=dev)
-    st = torch.cuda.current_stream(dev).cuda_stream
-
-    def center():
-        _lib.check(lib.bmc_center_rows(preds.data_ptr(), n, m, m, truth.data_ptr(), mu.data_ptr(), y.data_ptr(),
-                                       xc.data_ptr(), m, st))
-
-    def gram_step():
-        _lib.check(lib.bmc_gram(xc.data_ptr(), n, m, m, None, None, gram.data_ptr(), ws.data_ptr(), ws.numel(), st))
-
-    def project():
-        _lib.check(lib.bmc_project_rows(xc.data_ptr(), n, m, m, None, vt.data_ptr(), k, u.data_ptr(), k, st))
-    res = {}
-    for name, fn, bytes_, flops in (("center_rows", center, 8 * n * m * 2, 0),
-                                    ("gram", gram_step, 8 * n * m, 2.0 * n * m * m),
-                                    ("project_rows", project, 8 * n * (m + k), 2.0 * n * m * k)):
-        ms = timed(fn, steps, 1)
-        res[name] = {"ms": ms, "GB/s": bytes_ / (ms * 1e-3) / 1e9, "frac_of_hbm": bytes_ / (ms * 1e-3) / 1e9 / hbm_peak,
-                     "fp64_TFLOP/s": flops / (ms * 1e-3) / 1e12}
-    out["config5_orthogonalize_f64"] = {"config": f"configs[4]: {n} x 256 fp64 rows per GPU, K=64", **res}
-    del preds, xc
-
-    # prediction at K = 64: the contraction runs on the tensor cores (tcgen05 kind::tf32, split TF32)
-    from pybmc_b200.sampling_utils import PredictiveProblem
-    rng = np.random.default_rng(1005)
-    n_draws = 10000
-    lo, hi = rank * n, (rank + 1) * n
-    pr = rng.uniform(100, 2000, n)[:, None] + rng.normal(0, 3.0, (n, 80))
-    vt64 = rng.normal(size=(k, 80)) * 0.02
-    vt64 -= vt64.mean(axis=1, keepdims=True)          # Vt_hat of row-centred predictions is orthogonal to 1
-    theta = np.column_stack([rng.normal(size=k)[None, :] + 0.1 * rng.normal(size=(n_draws, k)),
-                             np.abs(rng.normal(0.15, 0.01, n_draws))])
-    prob = PredictiveProblem(pr, theta, vt64, truth=pr.mean(axis=1), dtype="float32", device=dev, point0=lo)
-    ws = torch.empty(int(lib.bmc_predict_workspace_bytes(_lib.F32, n, 3, n_draws)), dtype=torch.uint8, device=dev)
-    ms = timed(lambda: prob.run(percentiles=[2.5, 50.0, 97.5], seed=SEED, as_numpy=False, workspace=ws), steps, 1)
-    out["config5_predict_f32"] = {"metric": "posterior_pred_samples_x_points_per_sec",
-                                  "value": float(n) * world * n_draws / (ms * 1e-3), "unit": "samples*points/s",
-                                  "ms_per_step": ms, "config": f"configs[4]: {n} nuclei per GPU x 10000 draws x K=64, "
-                                  "3 percentiles + coverage counts"}
-
-
-def _cpu_predict(args):
-    os.environ["OMP_NUM_THREADS"] = "1"
-    preds, theta, vt, truth, seed = args
-    from oracle import bmc_oracle as oc
-    rndm_m, _ = oc.predictive_draws(preds, theta, vt, np.random.default_rng(seed))
-    # the reference re-sorts every column for each of the 21 levels (pybmc/sampling_utils.py:24-28); the
-    # port sorts once, so this baseline is faster than the reference itself
-    oc.coverage_levels(np.arange(0, 101, 5), rndm_m, truth)
-    return rndm_m.shape[0] * rndm_m.shape[1]
-
-
-def cpu_predict_baseline():
-    """rndm_m_random_calculator + coverage (oracle port) at the reference's S = 10^4 on all host cores."""
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    preds, vt, theta, truth = config4_inputs(629, 12000)
-    jobs = [(preds, theta, vt, truth, 50 + c) for c in range(cores)]
-    with mp.get_context("fork").Pool(cores) as pool:
-        t0 = time.perf_counter()
-        units = sum(pool.map(_cpu_predict, jobs))
-        dt = time.perf_counter() - t0
-    return {"value": units / dt, "unit": "samples*points/s", "cores": cores, "kind": "port",
-            "sample": f"{cores} x (629 points x 10000 draws x K=16: predictive matrix, 3 percentiles, 21 coverage "
-                      f"levels), one process per core, {dt:.1f} s"}
-
-
-def cpu_baseline():
-    """Reference algorithm (oracle port) on the host cores, bounded sample of the same workload."""
-    import multiprocessing as mp
-    os.environ["OMP_NUM_THREADS"] = "1"
-    cores = os.cpu_count() or 1
-    problem = cpu_problem()
-    iters = 100000
-    with mp.get_context("fork").Pool(cores) as pool:
-        cpu_sampler_rate(100, pool, cores, problem)
-        rate, dt = cpu_sampler_rate(iters, pool, cores, problem)
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{cores} chains x {iters} iterations of the same 3000 x 8 problem, one process per core, "
-                      f"{dt:.1f} s"}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--metric", default="gibbs", choices=["gibbs", "predict"],
+                    help="which of BASELINE.json's two metrics is the top-level line (the other is a sibling object)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"],
+                    help="arithmetic type of the top-level gibbs line (the other type is a sibling object)")
     ap.add_argument("--only", default="all", choices=["all", "sampler", "predict"],
-                    help="profiling aid: restrict the run to one kernel family (no JSON contract)")
+                    help="profiling aid: restrict the run to one kernel family")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `extra` block")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
+    if args.only == "predict":
+        args.metric = "predict"
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -16,7 +16,11 @@
  *     ("real" below).  Orthogonalisation kernels are always fp64.
  *   - return value 0 on success, negative error code otherwise; bmc_last_error() returns a
  *     thread-local message for the last failure.
- *   - asynchronous w.r.t. the host unless stated; no global mutable state.
+ *   - asynchronous w.r.t. the host unless stated.  No global mutable state: every switch between kernels
+ *     that compute the same thing is a field of the problem struct of the call (`layout`, `tensor_min_k`);
+ *     the only per-thread state is the message behind bmc_last_error().
+ *   - launch shapes are derived from the SM count of the current device (cudaDevAttrMultiProcessorCount),
+ *     never from a hard-coded 148.
  */
 #ifndef BMC_B200_H
 #define BMC_B200_H
@@ -47,6 +51,17 @@ extern "C" {
 
 #define BMC_MAX_COMPONENTS 64
 #define BMC_MAX_QUANTILES 8
+
+/* `layout` of the sampler problems: which kernel family walks the chains.  Every layout draws the same
+ * variates for the same (seed, global chain id, iteration), so they produce the same chains (up to the
+ * summation order of RSS); AUTO picks by chain count.  Forcing one is for tests, A/B timing and the
+ * parity checks of the benchmarked thread-per-chain kernels. */
+#define BMC_LAYOUT_AUTO 0
+#define BMC_LAYOUT_THREAD 1   /* one chain per thread                                                   */
+#define BMC_LAYOUT_GROUP 2    /* eight lanes per chain (k <= 8); simplex: the general group kernel        */
+#define BMC_LAYOUT_WARP 3     /* conjugate: a warp per chain (k <= 8); simplex: the <= 16-model group kernel
+                                 that precomputes the state-independent part of 32 proposals at a time    */
+#define BMC_HIST_BINS 512     /* bins of the sampler's marginal histograms (see bmc_gibbs_hist)          */
 
 int bmc_version(void);
 const char* bmc_last_error(void);
@@ -94,6 +109,7 @@ typedef struct {
     double n_obs;              /* len(y)                                                    (:23)  */
     double nu0, sigma20;       /* prior_info[2], prior_info[3]                              (:21)  */
     double sigma2_init;        /* max(rss_min / n, 1e-6)                                  (:31,37) */
+    int layout;                /* BMC_LAYOUT_*; 0 = choose by chain count                          */
 } bmc_gibbs_problem;
 
 /* Runs chains [chain0, chain0 + n_chains) for `iterations` iterations each.
@@ -109,9 +125,25 @@ typedef struct {
  * (kp+1)-square cross-moment matrix, row-major (BMC_STATS_FULL).  Padded components stay 0. */
 int bmc_padded_components(int k);
 int64_t bmc_gibbs_n_stat(int kp, int stats_mode);
+
+/* Marginal histograms of [b_0..b_{k-1}, sigma] over the run (the second thing, after the
+ * moment sums, that ranks all-reduce): the state after every `every`-th iteration (t with (t+1) % every == 0) is
+ * binned into BMC_HIST_BINS equal bins per coordinate, bin = floor((v - lo[c]) * inv_width[c]) clamped to the
+ * edge bins.  Blocks count in shared memory (uint32) and merge into `counts` with 64-bit atomics when they
+ * finish, so the result does not depend on the layout or the sharding.  `counts` is zeroed by the call; sum it
+ * over ranks with one all-reduce.  k <= 16.  every = 64 coincides with the kernels' moment flushes and costs
+ * nothing in the iteration loop. */
+typedef struct {
+    int64_t every;             /* 0 = off                                                          */
+    const double* lo;          /* dev [k+1]  lower edge of bin 0 per coordinate                   */
+    const double* inv_width;   /* dev [k+1]  1 / bin width                                        */
+    uint64_t* counts;          /* dev [k+1][BMC_HIST_BINS]                                        */
+} bmc_gibbs_hist;
+
 int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* problem /*host*/, uint64_t seed, uint64_t chain0,
                   int64_t n_chains, int64_t iterations, int64_t store_from, int64_t thin, int64_t n_kept,
-                  void* samples /*dev*/, double* chain_stats /*dev*/, int stats_mode, void* stream);
+                  void* samples /*dev*/, double* chain_stats /*dev*/, int stats_mode,
+                  const bmc_gibbs_hist* hist /*host, may be NULL*/, void* stream);
 
 /* Literal form of the same sampler, one chain per warp: X' ([k][n], real) and y ([n], real) are
  * staged in shared memory by TMA and every iteration factors X'X/s2 + Lambda + 1e-6 I (:41), draws b
@@ -135,6 +167,7 @@ typedef struct {
     double rss_min;            /* |y - X b_ols|^2                                                  */
     double rss_zero;           /* |y|^2 = RSS at the start b = 0                          (:82-85) */
     double n_obs, nu0, sigma20;
+    int layout;                /* BMC_LAYOUT_*; 0 = choose by chain count and model count          */
 } bmc_simplex_problem;
 
 /* Burn-in iterations [0, burn) are run but not recorded; iteration burn + t is kept when
@@ -170,6 +203,10 @@ typedef struct {
     const double* theta_cov;   /* dev [(k+1)^2] sample covariance of the draws                     */
     const double* center;      /* dev [n_points] optional override of the guess (matrix mode)      */
     const double* scale;       /* dev [n_points]                                                   */
+    int tensor_min_k;          /* fp32 contractions u . beta run on the tensor cores (tcgen05 kind::tf32, split
+                                  TF32: fp32-level accuracy) when the padded component count reaches this
+                                  threshold.  0 = the default (every k: measured faster for all of them);
+                                  negative = never (FFMA kernels for every k); n >= 1 = threshold n           */
 } bmc_predict_problem;
 
 /* Outputs (all dev, fp64/int64): mean, var [n_points]; quant [nq][n_points]; c_lt, c_le [n_points]
@@ -180,10 +217,6 @@ int bmc_predict_theta_stride(int k);
 int bmc_predict_fused(int dtype, const bmc_predict_problem* problem /*host*/, double* mean, double* var,
                       double* quant, int64_t* c_lt, int64_t* c_le, double* draws_out, int64_t ld_out,
                       void* workspace, size_t workspace_bytes, int* passes_out /*host, may be NULL*/, void* stream);
-/* fp32 contractions u . beta run on the tensor cores (tcgen05 kind::tf32, split TF32: fp32-level
- * accuracy) when the padded component count reaches a threshold.  mode 0: never (FFMA kernels for
- * every k); mode 1: the default threshold; mode >= 2: threshold = mode (A/B timing and tests). */
-void bmc_predict_set_tensor_path(int mode);
 
 /* Order counts of a materialised S-by-N matrix (the reference's rndm_m): sort-free form of
  * pybmc/sampling_utils.py:28-33.  c_lt/c_le dev int64 [n_cols]. */
@@ -200,26 +233,11 @@ int bmc_column_moments(const double* matrix, int64_t s_rows, int64_t n_cols, int
 int bmc_coverage_levels(const int64_t* c_lt, const int64_t* c_le, int64_t n_points, const int64_t* lo_idx,
                         const int64_t* hi_idx, int n_levels, int64_t* covered, void* stream);
 
-/* A/B switch of the simplex sampler's few-chains kernel for at most 16 models (state-independent parts of
- * a proposal precomputed 32 iterations at a time; gibbs_kernels.cuh).  Same stream and decisions either way.
- * Returns the previous setting; default on. */
-int bmc_simplex_set_group16(int enabled);
-
 /* ---- data split by distance: Dataset.separate_points_distance_allSets, pybmc/data.py:194-245 ---------
  * cls[i] = 0 if a reference point lies within d1 of point i (Euclidean, <=), 1 if one lies within d2 but
  * none within d1, 2 otherwise.  points dev [n][dim], refs dev [r][dim] (fp64), cls dev int32 [n]. */
 int bmc_nearest_class(const double* points, int64_t n, const double* refs, int64_t r, int dim, double d1,
                       double d2, int32_t* cls, void* stream);
-
-/* ---- peak probes for the pipe rooflines: register-only kernels measuring what the
- *      box sustains on the FP32 FMA pipe (kind 0), the MUFU pipe (1), the Philox integer mix (2) and
- *      dual-pipe issue (3); single-instruction streams IMAD.WIDE+IADD / IMAD.HI / IMAD / LOP3 (4-7), packed
- *      FFMA2 (8), IMAD.WIDE alone (9), and the mixes that show which classes share a pipe: IMAD.WIDE + FFMA
- *      (10), + 2 FFMA (11), + FFMA2 (12), MUFU + 4 FFMA (13), MUFU + 2 IMAD.WIDE (14), FFMA2 + FFMA (15).
- *      `iters` loop iterations per thread, each issuing
- *      bmc_probe_ops_per_iteration(kind) thread-level operations; `sink` is a dev float[1]. */
-int bmc_probe_ops_per_iteration(int kind);
-int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,10 +18,9 @@ def tf32(x):
 for k, n, s in [(17, 300, 3000), (64, 700, 2500)]:
     preds, vt, theta, truth = _problem(k, n, s)
     prob = PredictiveProblem(preds, theta, vt, truth=truth, dtype="float32")
-    lib = _lib.load()
-    lib.bmc_predict_set_tensor_path(1)
+    prob.tensor_min_k = 0            # bmc_predict_problem.tensor_min_k: tensor cores for every k (default)
     tc = prob.run(noise="none", return_draws=True).draws
-    lib.bmc_predict_set_tensor_path(0)
+    prob.tensor_min_k = -1           # FFMA kernels
     ff = prob.run(noise="none", return_draws=True).draws
     mu = preds.mean(axis=1)
     u = (preds @ vt.T).astype(np.float32)

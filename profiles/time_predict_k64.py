@@ -18,7 +18,7 @@ for k, n, n_draws in [(16, 100000, 100000), (64, 100000, 10000), (16, 629, 10000
     prob = PredictiveProblem(pr, theta, vt, truth=pr.mean(axis=1), dtype="float32")
     ws = torch.empty(int(lib.bmc_predict_workspace_bytes(_lib.F32, n, 3, n_draws)), dtype=torch.uint8, device="cuda")
     for mode in (1, 0):
-        lib.bmc_predict_set_tensor_path(mode)
+        prob.tensor_min_k = 0 if mode else -1
         times = []
         for it in range(6):
             torch.cuda.synchronize()
@@ -29,4 +29,3 @@ for k, n, n_draws in [(16, 100000, 100000), (64, 100000, 10000), (16, 629, 10000
         ms = float(np.median(times[2:]))
         print(f"K={k} n={n} S={n_draws} tensor={mode}: {ms:.2f} ms  {n * n_draws / ms / 1e6:.1f} G units/s  passes={res.passes}",
               flush=True)
-    lib.bmc_predict_set_tensor_path(1)

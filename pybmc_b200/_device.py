@@ -33,6 +33,23 @@ def device(dev=None):
     return torch.device(dev)
 
 
+def on(dev):
+    """Context manager making ``dev`` the current CUDA device: the C ABI launches on the current device, so
+    every public entry point wraps its launches in this (``device=`` may name any visible GPU)."""
+    return torch.cuda.device(dev)
+
+
+def on_own_device(method):
+    """Decorator for methods of objects that carry their device in ``self.dev``."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.dev):
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 def stream_ptr(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
@@ -42,13 +59,19 @@ def ptr(t):
 
 
 def to_device(a, dev, dtype=torch.float64):
-    """Host array -> contiguous device tensor through pinned staging memory."""
+    """Host array -> contiguous device tensor.  Large arrays are staged through a page-locked block taken
+    from PyTorch's caching host allocator (a cached block costs nothing; ``Tensor.pin_memory()`` would
+    page-lock a fresh allocation on every call, ~1 ms per MB) and copied asynchronously."""
     if isinstance(a, torch.Tensor):
         return a.to(device=dev, dtype=dtype).contiguous()
-    host = torch.from_numpy(np.array(a, dtype=np.float64, order="C", copy=True))
-    if host.numel() > 4096:
-        host = host.pin_memory()
-    t = host.to(dev, non_blocking=True)
+    arr = np.asarray(a, dtype=np.float64)
+    if arr.size <= 4096:
+        t = torch.from_numpy(np.array(arr, order="C", copy=True)).to(dev)
+    else:
+        stage = torch.empty(arr.shape, dtype=torch.float64, pin_memory=True)
+        np.copyto(stage.numpy(), arr)              # one pass: gathers non-contiguous input as it goes
+        t = stage.to(dev, non_blocking=True)
+        # the caching host allocator keeps `stage` alive until the copy has run (stream-ordered reuse)
     return t if dtype == torch.float64 else t.to(dtype)
 
 

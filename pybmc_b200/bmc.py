@@ -36,19 +36,41 @@ def orthogonalize_arrays(preds, truth, components_kept, method="auto", device=No
     Returns dict(y, mu, U_hat, S_hat, Vt_hat, Vt_hat_normalized, method); with ``reduce`` the
     per-point entries (y, mu, U_hat) cover this rank's rows.
     """
-    lib = _lib.load()
     dev = D.device(device)
+    with D.on(dev):
+        return _orthogonalize(dev, preds, truth, components_kept, method, reduce)
+
+
+def _tsqr_svd(xc, reduce):
+    """Singular values / right singular vectors of the row-sharded centred matrix without squaring its
+    condition number: local QR, the M-by-M R factors of all ranks stacked (exchanged as one summed
+    [world, M, M] tensor -- 512 KB per rank at M = 256), SVD of the stack on every rank."""
+    m = xc.shape[1]
+    r_local = torch.linalg.qr(xc, mode="r")[1] if xc.shape[0] > 0 else xc.new_zeros((0, m))
+    stack = xc.new_zeros((reduce.world, m, m))
+    stack[reduce.rank, : r_local.shape[0]] = r_local
+    stack = reduce(stack)
+    _, s, vt = torch.linalg.svd(stack.reshape(reduce.world * m, m), full_matrices=False)
+    return s, vt
+
+
+def _orthogonalize(dev, preds, truth, components_kept, method, reduce):
+    lib = _lib.load()
     preds = np.asarray(preds, dtype=np.float64)
     if preds.ndim != 2:
         raise ValueError("model predictions must be [n_points, n_models]")
     n, m = preds.shape
     k = int(components_kept)
-    if reduce is not None:
-        method = "gram"
+    if reduce is not None and method == "auto":
+        method = "gram_checked"          # Gram route, TSQR when the spectrum is too graded for it
     if k < 1 or k > (m if reduce is not None else min(n, m)):
         raise IndexError(f"components_kept={k} outside 1..{min(n, m)}")   # upstream: IndexError from U.T[i]
+    truth = np.asarray(truth, dtype=np.float64).reshape(-1)
+    if truth.shape[0] != n:
+        # upstream subtracts two pandas columns of the same frame (bmc.py:109-111); arrays must match
+        raise ValueError(f"truth has {truth.shape[0]} entries for {n} rows of predictions")
     pd_ = D.to_device(preds, dev)
-    td = D.to_device(np.asarray(truth, dtype=np.float64).reshape(-1), dev)
+    td = D.to_device(truth, dev)
     st = D.stream_ptr(dev)
     mu = torch.empty(n, dtype=torch.float64, device=dev)
     y = torch.empty(n, dtype=torch.float64, device=dev)
@@ -57,7 +79,7 @@ def orthogonalize_arrays(preds, truth, components_kept, method="auto", device=No
                "bmc_center_rows")
     used = method
     vt = s = None
-    if method in ("auto", "gram"):
+    if method in ("auto", "gram", "gram_checked"):
         gram = torch.empty((m, m), dtype=torch.float64, device=dev)
         ws = torch.empty(max(int(lib.bmc_gram_workspace_bytes(n, m)), 8), dtype=torch.uint8, device=dev)
         _lib.check(lib.bmc_gram(D.ptr(xc), n, m, m, None, None, D.ptr(gram), D.ptr(ws), ws.numel(), st), "bmc_gram")
@@ -69,6 +91,15 @@ def orthogonalize_arrays(preds, truth, components_kept, method="auto", device=No
         ratio = float(lam[k - 1] / lam[0]) if float(lam[0]) > 0 else 0.0
         if method == "gram" or ratio >= GRAM_RATIO_MIN:
             s, vt, used = torch.sqrt(lam), vec.t().contiguous(), "gram"
+        elif method == "gram_checked" and not hasattr(reduce, "world"):
+            import warnings
+            warnings.warn(f"row-sharded orthogonalisation: lambda_K/lambda_1 = {ratio:.1e} of the Gram matrix is below "
+                          f"{GRAM_RATIO_MIN:g}; its eigenvectors carry errors ~ eps*lambda_1/lambda_K and the reducer "
+                          "offers no rank/world for the TSQR route", RuntimeWarning, stacklevel=3)
+            s, vt, used = torch.sqrt(lam), vec.t().contiguous(), "gram"
+    if vt is None and reduce is not None:
+        s, vt = _tsqr_svd(xc, reduce)                             # graded spectrum, rows on several ranks
+        used = "tsqr"
     if vt is None:
         # graded spectrum (or method="svd"): thin SVD of the centred matrix, still on the device
         _, s, vt = torch.linalg.svd(xc, full_matrices=False)

@@ -13,7 +13,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libbmc_b200.so")
-UNITS = ["linalg.cu", "gibbs.cu", "simplex.cu", "predict.cu", "literal.cu", "probe.cu"]
+PROBE_LIB = os.path.join(CSRC, "bench", "libbmc_probe.so")     # benchmark tooling, separate from the product ABI
+UNITS = ["linalg.cu", "gibbs.cu", "simplex.cu", "predict.cu", "literal.cu"]
 HEADERS = ["common.h", "rng.cuh", "gibbs_kernels.cuh", "linalg_kernels.cuh", "predict_kernels.cuh", "predict_tc_kernels.cuh",
            "literal_kernels.cuh", "tma.cuh", "select_logic.h", os.path.join("..", "..", "include", "bmc_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -38,6 +39,19 @@ def _stale():
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in _units() + HEADERS]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build_probe_library(force=False):
+    """libbmc_probe.so: the pipe-peak probes bench.py divides by (pybmc_b200/csrc/bench/probe.h)."""
+    src = os.path.join(CSRC, "bench", "probe.cu")
+    if not force and os.path.exists(PROBE_LIB) and os.path.getmtime(PROBE_LIB) >= max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "bench", "probe.h"))):
+        return PROBE_LIB
+    cmd = [_nvcc(), *ARCH, *FLAGS, "-shared", src, "-o", PROBE_LIB, "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on probe.cu:\n{r.stdout}\n{r.stderr}")
+    return PROBE_LIB
 
 
 def build_library(force=False, verbose=False):
@@ -76,3 +90,4 @@ def build_library(force=False, verbose=False):
 if __name__ == "__main__":
     path = build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)
+    print(build_probe_library(force="--force" in sys.argv))

@@ -1,9 +1,11 @@
-// Peak probes for the non-HBM rooflines.  SURVEY.md section 8(d): the sampler and predictive kernels
+// Peak probes for the non-HBM rooflines (benchmark tooling: built into libbmc_probe.so, NOT part of the
+// product ABI in include/bmc_b200.h; bench.py and profiles/pipe_probes.py are the only callers).  SURVEY.md section 8(d): the sampler and predictive kernels
 // are bound by the FP32 FMA pipe, the MUFU (XU) pipe and integer issue, and MEASURED_PEAKS.json only
 // holds the HBM and bf16 tensor peaks -- so bench.py measures the pipe peaks it divides by with these
 // kernels, on the same box and at the clocks of the same run.  Each probe is a grid of warps running
 // `iters` iterations of independent register-only chains; the result is written so nothing is elided.
-#include "common.h"
+#include <cuda_runtime.h>
+#include "probe.h"
 
 namespace {
 
@@ -187,9 +189,8 @@ int bmc_probe_ops_per_iteration(int kind) {
 }
 
 int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, void* stream) {
-    BMC_REQUIRE(kind >= 0 && kind <= 15 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink,
-                "bmc_probe: bad arguments");
-    cudaStream_t st = bmc::as_stream(stream);
+    if (!(kind >= 0 && kind <= 15 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink)) return -1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (kind) {
         case 0: probe_ffma<<<blocks, threads, 0, st>>>(iters, sink); break;
         case 1: probe_mufu<<<blocks, threads, 0, st>>>(iters, sink); break;
@@ -208,8 +209,7 @@ int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, voi
         case 14: probe_mix<2, 0, 0, 1, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
         default: probe_mix<0, 1, 1, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
     }
-    BMC_LAUNCH_CHECK();
-    return BMC_OK;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 }  // extern "C"

@@ -11,6 +11,15 @@ void set_error(const char* fmt, ...);
 
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
+// SMs of the current device (148 on B200): grids are sized from this, never from a literal.
+inline int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        return 148;
+    return n;
+}
+
 #define BMC_REQUIRE(cond, ...)            \
     do {                                  \
         if (!(cond)) {                    \

@@ -7,9 +7,39 @@ using namespace bmc;
 
 namespace {
 
+// with fewer chains than this a thread-per-chain launch leaves schedulers idle; eight lanes per chain
+// cost ~50 % more instructions per chain-iteration but bring eight times the warps.  Measured crossover
+// on B200 (profiles/layout_sweep.py): 16,384 chains (1.23 vs 1.18 ms); 32,768: 1.8 vs 2.3; 4096: 1.2 vs 0.5.
+constexpr long long kConjGroupBelow = 16384;
+// below this a chain gets the whole warp for generating its variates: one chain of 50,000 fp64 iterations
+// 23.5 -> 16.2 ms; break-even near 2,048 chains (profiles/warp_sweep.py)
+constexpr long long kConjWarpBelow = 1536;
+
+// dynamic shared memory of a launch: the block's marginal histograms, when they are on
+size_t hist_smem(const GibbsArgs& a) {
+    return a.hist_every ? sizeof(unsigned) * static_cast<size_t>(a.k + 1) * kHistBins : 0;
+}
+
 template <typename real, int KP>
 int launch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream_t stream) {
     const unsigned blocks = static_cast<unsigned>((a.n_chains + threads - 1) / threads);
+    const size_t smem = hist_smem(a);
+    if (a.hist_every) {
+        if constexpr (KP <= 16) {
+            switch (stats_mode) {
+                case BMC_STATS_NONE:
+                    gibbs_conjugate_kernel<real, KP, 0, true><<<blocks, threads, smem, stream>>>(a);
+                    break;
+                case BMC_STATS_DIAG:
+                    gibbs_conjugate_kernel<real, KP, 1, true><<<blocks, threads, smem, stream>>>(a);
+                    break;
+                default:
+                    gibbs_conjugate_kernel<real, KP, 2, true><<<blocks, threads, smem, stream>>>(a);
+            }
+            BMC_LAUNCH_CHECK();
+            return BMC_OK;
+        }
+    }
     switch (stats_mode) {
         case BMC_STATS_NONE:
             gibbs_conjugate_kernel<real, KP, 0><<<blocks, threads, 0, stream>>>(a);
@@ -33,36 +63,38 @@ template <typename real, int KP, int GEN>
 int launch_group(const GibbsArgs& a, int stats_mode, cudaStream_t stream) {
     const int wpb = 4, cpw = 32 / GEN;
     const unsigned blocks = static_cast<unsigned>((a.n_chains + wpb * cpw - 1) / (wpb * cpw));
+    const size_t smem = hist_smem(a);
+    // the group kernels keep their iteration counters in 32-bit signed registers
+    BMC_REQUIRE(a.iterations < (1ll << 31) && a.thin < (1ll << 31) && a.store_from < (1ll << 31),
+                "bmc_gibbs_run: iterations, thin and store_from must fit 31 bits with fewer than %lld chains "
+                "(eight lanes / a warp per chain)", kConjGroupBelow);
     switch (stats_mode) {
         case BMC_STATS_NONE:
-            gibbs_conjugate_group_kernel<real, KP, 0, GEN><<<blocks, wpb * 32, 0, stream>>>(a);
+            gibbs_conjugate_group_kernel<real, KP, 0, GEN><<<blocks, wpb * 32, smem, stream>>>(a);
             break;
         case BMC_STATS_DIAG:
-            gibbs_conjugate_group_kernel<real, KP, 1, GEN><<<blocks, wpb * 32, 0, stream>>>(a);
+            gibbs_conjugate_group_kernel<real, KP, 1, GEN><<<blocks, wpb * 32, smem, stream>>>(a);
             break;
         default:
-            gibbs_conjugate_group_kernel<real, KP, 2, GEN><<<blocks, wpb * 32, 0, stream>>>(a);
+            gibbs_conjugate_group_kernel<real, KP, 2, GEN><<<blocks, wpb * 32, smem, stream>>>(a);
     }
     BMC_LAUNCH_CHECK();
     return BMC_OK;
 }
 
-// with fewer chains than this a thread-per-chain launch leaves schedulers idle; eight lanes per chain
-// cost ~50 % more instructions per chain-iteration but bring eight times the warps.  Measured crossover
-// on B200 (profiles/layout_sweep.py): 16,384 chains (1.23 vs 1.18 ms); 32,768: 1.8 vs 2.3; 4096: 1.2 vs 0.5.
-constexpr long long kConjGroupBelow = 16384;
-// below this a chain gets the whole warp for generating its variates: one chain of 50,000 fp64 iterations
-// 23.5 -> 16.2 ms; break-even near 2,048 chains (profiles/warp_sweep.py)
-constexpr long long g_conj_warp_below = 1536;
-
 template <typename real>
-int dispatch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream_t stream) {
+int dispatch_conjugate(const GibbsArgs& a, int layout, int stats_mode, int threads, cudaStream_t stream) {
     // (a two-lanes-per-chain variant was measured in round 1: 46 % more instructions for 70 % instead of
     //  61 % issue utilisation and register-limited to 16 warps/SM -- slower; see profiles/r1_notes.md)
-    if (a.n_chains < g_conj_warp_below && a.k <= 8)
+    if (layout == BMC_LAYOUT_AUTO) {
+        const bool wide_counts = a.iterations >= (1ll << 31) || a.thin >= (1ll << 31) || a.store_from >= (1ll << 31);
+        if (a.k > 8 || a.n_chains >= kConjGroupBelow || wide_counts) layout = BMC_LAYOUT_THREAD;
+        else layout = a.n_chains < kConjWarpBelow ? BMC_LAYOUT_WARP : BMC_LAYOUT_GROUP;
+    }
+    if (layout == BMC_LAYOUT_WARP)
         return a.k <= 4 ? launch_group<real, 4, 32>(a, stats_mode, stream)
                         : launch_group<real, 8, 32>(a, stats_mode, stream);
-    if (a.n_chains < kConjGroupBelow && a.k <= 8)
+    if (layout == BMC_LAYOUT_GROUP)
         return a.k <= 4 ? launch_group<real, 4, 8>(a, stats_mode, stream)
                         : launch_group<real, 8, 8>(a, stats_mode, stream);
     if (a.k <= 4) return launch_conjugate<real, 4>(a, stats_mode, threads, stream);
@@ -72,10 +104,28 @@ int dispatch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStre
     return launch_conjugate<real, 64>(a, stats_mode, threads, stream);
 }
 
+// d and pull travel inside the kernel parameters as well (constant-bank operands of the thread-per-chain
+// kernel): 2 k doubles read back from the caller's device arrays -- the only synchronisation of the call,
+// a few microseconds against launches of milliseconds.
+int fill_consts(GibbsArgs& a, const bmc_gibbs_problem* p, cudaStream_t st) {
+    double host[2 * BMC_MAX_COMPONENTS];
+    BMC_CUDA(cudaMemcpyAsync(host, p->d, sizeof(double) * p->k, cudaMemcpyDeviceToHost, st));
+    BMC_CUDA(cudaMemcpyAsync(host + BMC_MAX_COMPONENTS, p->pull, sizeof(double) * p->k, cudaMemcpyDeviceToHost, st));
+    BMC_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < BMC_MAX_COMPONENTS; ++k) {
+        a.d_d[k] = k < p->k ? host[k] : 0.0;
+        a.pull_d[k] = k < p->k ? host[BMC_MAX_COMPONENTS + k] : 0.0;
+        a.d_f[k] = static_cast<float>(a.d_d[k]);
+        a.pull_f[k] = static_cast<float>(a.pull_d[k]);
+    }
+    return BMC_OK;
+}
+
 int pick_threads(long long n_chains) {
-    // small blocks spread few chains over all 148 SMs; 128 once there is plenty of work
-    if (n_chains >= 148ll * 128 * 8) return 128;
-    if (n_chains >= 148ll * 64 * 2) return 64;
+    // small blocks spread few chains over all SMs; 128 once there is plenty of work
+    const long long sms = sm_count();
+    if (n_chains >= sms * 128 * 8) return 128;
+    if (n_chains >= sms * 64 * 2) return 64;
     return 32;
 }
 
@@ -94,7 +144,7 @@ int64_t bmc_gibbs_n_stat(int k, int stats_mode) {
 
 int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t chain0, int64_t n_chains,
                   int64_t iterations, int64_t store_from, int64_t thin, int64_t n_kept, void* samples,
-                  double* chain_stats, int stats_mode, void* stream) {
+                  double* chain_stats, int stats_mode, const bmc_gibbs_hist* hist, void* stream) {
     BMC_REQUIRE(p, "bmc_gibbs_run: problem is NULL");
     BMC_REQUIRE(dtype == BMC_F32 || dtype == BMC_F64, "bmc_gibbs_run: bad dtype %d", dtype);
     BMC_REQUIRE(p->k >= 1 && p->k <= BMC_MAX_COMPONENTS, "bmc_gibbs_run: k=%d outside 1..%d", p->k,
@@ -106,6 +156,16 @@ int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t
     BMC_REQUIRE(stats_mode >= 0 && stats_mode <= 2, "bmc_gibbs_run: bad stats_mode");
     BMC_REQUIRE(stats_mode == 0 || chain_stats, "bmc_gibbs_run: chain_stats is NULL");
     BMC_REQUIRE(p->nu0 + p->n_obs > 0 && p->sigma2_init > 0, "bmc_gibbs_run: bad variance prior");
+    BMC_REQUIRE(p->layout >= BMC_LAYOUT_AUTO && p->layout <= BMC_LAYOUT_WARP, "bmc_gibbs_run: bad layout %d",
+                p->layout);
+    BMC_REQUIRE(p->layout == BMC_LAYOUT_AUTO || p->layout == BMC_LAYOUT_THREAD || p->k <= 8,
+                "bmc_gibbs_run: the group layouts hold one component per lane (k <= 8), k=%d", p->k);
+    if (hist && hist->every > 0) {
+        BMC_REQUIRE(hist->lo && hist->inv_width && hist->counts, "bmc_gibbs_run: histogram arrays missing");
+        BMC_REQUIRE(hist->every < (1ll << 31), "bmc_gibbs_run: hist.every must fit 31 bits");
+        BMC_REQUIRE(p->k <= 16, "bmc_gibbs_run: marginal histograms need k <= 16 (one block's bins live in "
+                                "shared memory), k=%d", p->k);
+    }
     if (samples) {
         BMC_REQUIRE(thin >= 1 && store_from >= 0, "bmc_gibbs_run: thin=%lld store_from=%lld", (long long)thin,
                     (long long)store_from);
@@ -135,6 +195,7 @@ int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t
         a.keys.k0[r] = a.key0 + static_cast<uint32_t>(r) * kPhiloxW0;
         a.keys.k1[r] = a.key1 + static_cast<uint32_t>(r) * kPhiloxW1;
     }
+    if (fill_consts(a, p, st) != BMC_OK) return BMC_ERR_CUDA;
     a.chain0 = chain0;
     a.n_chains = n_chains;
     a.iterations = iterations;
@@ -144,6 +205,13 @@ int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t
     a.samples = samples;
     a.chain_stats = chain_stats;
     a.stats_mode = stats_mode;
+    if (hist && hist->every > 0) {
+        a.hist_every = static_cast<uint32_t>(hist->every);
+        a.hist_lo = hist->lo;
+        a.hist_inv = hist->inv_width;
+        a.hist = reinterpret_cast<unsigned long long*>(hist->counts);
+        BMC_CUDA(cudaMemsetAsync(hist->counts, 0, sizeof(uint64_t) * static_cast<size_t>(p->k + 1) * kHistBins, st));
+    }
     if (stats_mode != 0) {
         // the kernel accumulates with the padded component count kp = bmc_padded_components(k)
         const int kp = bmc_padded_components(p->k);
@@ -152,8 +220,8 @@ int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t
     }
     if (iterations == 0) return BMC_OK;
     const int threads = pick_threads(n_chains);
-    return dtype == BMC_F32 ? dispatch_conjugate<float>(a, stats_mode, threads, st)
-                            : dispatch_conjugate<double>(a, stats_mode, threads, st);
+    return dtype == BMC_F32 ? dispatch_conjugate<float>(a, p->layout, stats_mode, threads, st)
+                            : dispatch_conjugate<double>(a, p->layout, stats_mode, threads, st);
 }
 
 }  // extern "C"

@@ -49,7 +49,7 @@ int bmc_center_rows(const double* preds, int64_t n, int m, int64_t ld, const dou
     if (n == 0) return BMC_OK;
     const int threads = 256;
     const long long warps_needed = n;
-    const int blocks = static_cast<int>(std::min<long long>((warps_needed * 32 + threads - 1) / threads, 148 * 16));
+    const int blocks = static_cast<int>(std::min<long long>((warps_needed * 32 + threads - 1) / threads, sm_count() * 16));
     center_rows_kernel<<<blocks, threads, 0, as_stream(stream)>>>(preds, n, m, ld, truth, mu, y, xc, ldx);
     BMC_LAUNCH_CHECK();
     return BMC_OK;

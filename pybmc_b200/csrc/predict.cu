@@ -38,10 +38,27 @@ double norm_ppf(double p) {
            (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
 }
 
-// fp32 contractions with padded K >= this go to the tensor cores; kTensorOff sends every K to the FFMA kernels
-constexpr int kTensorOff = 1 << 20;
+// fp32 contractions with padded K >= this go to the tensor cores (bmc_predict_problem.tensor_min_k overrides it)
 constexpr int kTensorDefaultMinK = 4;      // measured faster for every K (profiles/r1_notes.md)
-int g_tensor_min_k = kTensorDefaultMinK;
+inline bool use_tensor_path(int kp, int tensor_min_k) {
+    if (tensor_min_k < 0) return false;
+    return kp >= (tensor_min_k == 0 ? kTensorDefaultMinK : tensor_min_k);
+}
+
+// The quantile plan travels to the device as a kernel argument (no copy from the caller's stack, no
+// synchronisation): layout of the destination = rank[kMaxQuant], frac[], zq[], hw[].
+struct PlanImage {
+    long long rank[kMaxQuant];
+    double frac[kMaxQuant], zq[kMaxQuant], hw[kMaxQuant];
+};
+__global__ void store_plan_kernel(const PlanImage p, PlanImage* dst) {
+    if (threadIdx.x < kMaxQuant) {
+        dst->rank[threadIdx.x] = p.rank[threadIdx.x];
+        dst->frac[threadIdx.x] = p.frac[threadIdx.x];
+        dst->zq[threadIdx.x] = p.zq[threadIdx.x];
+        dst->hw[threadIdx.x] = p.hw[threadIdx.x];
+    }
+}
 
 struct QuantPlan {
     int nq;
@@ -92,16 +109,16 @@ struct PassShape {
 };
 
 // tensor-core pass: blocks of 128 nuclei, one block per SM, four slots per block
-PassShape make_shape_tc(long long n_points, long long n_draws, double expected) {
+PassShape make_shape_tc(long long n_points, long long n_draws, double expected, int sms) {
     PassShape sh{};
     const int tiles = static_cast<int>((n_draws + kTcTile - 1) / kTcTile);
     const long long blocks_x = (n_points + kTcRows - 1) / kTcRows;
     const int gy_max = std::max(1, std::min(tiles, kMaxSlots / kTcSlotsPerBlock));
     int gy = 1;
     double best = 0.0;
-    for (int g = 1; g <= gy_max; ++g) {          // fewest splits that fill whole waves of 148 blocks
+    for (int g = 1; g <= gy_max; ++g) {          // fewest splits that fill whole waves of one block per SM
         const long long total = blocks_x * g;
-        const double eff = static_cast<double>(total) / static_cast<double>((total + 147) / 148 * 148);
+        const double eff = static_cast<double>(total) / static_cast<double>((total + sms - 1) / sms * sms);
         if (eff > best + 1e-9) {
             best = eff;
             gy = g;
@@ -117,12 +134,12 @@ PassShape make_shape_tc(long long n_points, long long n_draws, double expected) 
     return sh;
 }
 
-PassShape make_shape(long long n_points, long long n_draws, double expected, bool tc = false) {
-    if (tc) return make_shape_tc(n_points, n_draws, expected);
+PassShape make_shape(long long n_points, long long n_draws, double expected, bool tc = false, int sms = 148) {
+    if (tc) return make_shape_tc(n_points, n_draws, expected, sms);
     PassShape sh{};
     const int tiles = static_cast<int>((n_draws + kPredTile - 1) / kPredTile);
     const long long blocks_x = (n_points + kPredWarps * 32 - 1) / (kPredWarps * 32);
-    const int target = 444;                          // three resident blocks per SM
+    const int target = 3 * sms;                      // three resident blocks per SM
     int s = 1;
     if (blocks_x < target) s = static_cast<int>((target + blocks_x - 1) / blocks_x);
     s = std::max(1, std::min(s, std::min(tiles, kMaxSlots)));
@@ -153,7 +170,7 @@ Layout make_layout(long long nc, int nq, int cand_stride, size_t sz, size_t imag
         return at;
     };
     const size_t nqn = static_cast<size_t>(nc) * nq;
-    l.plan = take(kMaxQuant * (sizeof(long long) + 3 * sizeof(double)));
+    l.plan = take(sizeof(PlanImage));
     l.counter = take(sizeof(int));
     l.center = take(nc * sz);
     l.scale = take(nc * sz);
@@ -234,7 +251,9 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
     const QuantPlan plan = make_plan(p->probs, p->nq, p->n_draws);
     const int kp = bmc_padded_components(p->k > 0 ? p->k : 1);
     // wide bases in fp32: the contraction goes to the tensor cores (predict_tc_kernels.cuh)
-    const bool tc = sizeof(real) == 4 && p->theta && kp >= g_tensor_min_k && p->noise_mode != BMC_NOISE_EXTERNAL;
+    const bool tc = sizeof(real) == 4 && p->theta && use_tensor_path(kp, p->tensor_min_k) &&
+                    p->noise_mode != BMC_NOISE_EXTERNAL;
+    const int sms = sm_count();
     const int kt = std::max(kp, 8);               // operand width of the tensor path (one MMA spans 8 components)
     const long long tiles_tc = (p->n_draws + kTcTile - 1) / kTcTile;
     const size_t image_bytes = tc ? static_cast<size_t>(tiles_tc) * (2 * kt * 128 * 4 + kTcTile * 4) : 0;
@@ -243,10 +262,10 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
     };
     // largest chunk of nuclei the workspace can hold (the shape depends on the chunk size)
     long long nc = std::min<long long>(p->n_points, kChunkPoints);
-    PassShape shape = make_shape(nc, p->n_draws, plan.max_expected, tc);
+    PassShape shape = make_shape(nc, p->n_draws, plan.max_expected, tc, sms);
     while (nc > 32 && total_for(nc, shape) > workspace_bytes) {
         nc = std::max<long long>(32, nc / 2);
-        shape = make_shape(nc, p->n_draws, plan.max_expected, tc);
+        shape = make_shape(nc, p->n_draws, plan.max_expected, tc, sms);
     }
     if (total_for(nc, shape) > workspace_bytes) {
         set_error("bmc_predict_fused: workspace of %zu bytes is too small (need %zu for %lld nuclei)",
@@ -258,7 +277,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         const long long n_chunks = (p->n_points + nc - 1) / nc;
         const long long even = ((p->n_points + n_chunks - 1) / n_chunks + 255) / 256 * 256;
         if (even < nc) {
-            const PassShape es = make_shape(even, p->n_draws, plan.max_expected, tc);
+            const PassShape es = make_shape(even, p->n_draws, plan.max_expected, tc, sms);
             if (total_for(even, es) <= workspace_bytes) {
                 nc = even;
                 shape = es;
@@ -273,15 +292,20 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
     unsigned char* ws = static_cast<unsigned char*>(workspace);
 
     // quantile plan to the device
-    long long* d_rank = reinterpret_cast<long long*>(ws + lay.plan);
-    double* d_frac = reinterpret_cast<double*>(d_rank + kMaxQuant);
-    double* d_zq = d_frac + kMaxQuant;
-    double* d_hw = d_zq + kMaxQuant;
-    BMC_CUDA(cudaMemcpyAsync(d_rank, plan.rank, sizeof(plan.rank), cudaMemcpyHostToDevice, st));
-    BMC_CUDA(cudaMemcpyAsync(d_frac, plan.frac, sizeof(plan.frac), cudaMemcpyHostToDevice, st));
-    BMC_CUDA(cudaMemcpyAsync(d_zq, plan.zq, sizeof(plan.zq), cudaMemcpyHostToDevice, st));
-    BMC_CUDA(cudaMemcpyAsync(d_hw, plan.hw, sizeof(plan.hw), cudaMemcpyHostToDevice, st));
-    BMC_CUDA(cudaStreamSynchronize(st));   // the plan lives on this stack frame
+    PlanImage* d_plan = reinterpret_cast<PlanImage*>(ws + lay.plan);
+    long long* d_rank = d_plan->rank;
+    double* d_frac = d_plan->frac;
+    double* d_zq = d_plan->zq;
+    double* d_hw = d_plan->hw;
+    {
+        PlanImage img{};
+        std::memcpy(img.rank, plan.rank, sizeof(img.rank));
+        std::memcpy(img.frac, plan.frac, sizeof(img.frac));
+        std::memcpy(img.zq, plan.zq, sizeof(img.zq));
+        std::memcpy(img.hw, plan.hw, sizeof(img.hw));
+        store_plan_kernel<<<1, 32, 0, st>>>(img, d_plan);     // by value in the launch: nothing to wait for
+        BMC_LAUNCH_CHECK();
+    }
 
     auto select_kern = predict_select_kernel<real>;
     BMC_CUDA(cudaFuncSetAttribute(select_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kSelStageBytes));
@@ -333,7 +357,7 @@ int run_predict(const bmc_predict_problem* p, double* mean, double* var, double*
         BMC_LAUNCH_CHECK();
 
         // the first pass of a short last chunk may use more sample splits than the full-size chunk
-        PassShape cs = make_shape(n, p->n_draws, plan.max_expected, tc);
+        PassShape cs = make_shape(n, p->n_draws, plan.max_expected, tc, sms);
         if (cs.cand_stride > shape.cand_stride) cs = shape;
         if (cs.s_splits * segment_len(plan.max_expected, cs.s_splits) > shape.cand_stride) cs = shape;
 
@@ -488,19 +512,16 @@ size_t bmc_predict_workspace_bytes(int dtype, int64_t n_points, int nq, int64_t 
     const size_t sz = dtype == BMC_F32 ? 4 : 8;
     // chunks of 32768 nuclei keep the candidate buffers in the hundreds of MB
     const long long nc = std::min<long long>(n_points, kChunkPoints);
-    const PassShape shape = make_shape(nc, n_draws, plan.max_expected);
+    const int sms = sm_count();
+    const PassShape shape = make_shape(nc, n_draws, plan.max_expected, false, sms);
     size_t need = make_layout(nc, nq, shape.cand_stride, sz).total;
     if (dtype == BMC_F32) {
         // room for the tensor-core path (K > 16): its slot layout and the operand image of the draws
-        const PassShape ts = make_shape(nc, n_draws, plan.max_expected, true);
+        const PassShape ts = make_shape(nc, n_draws, plan.max_expected, true, sms);
         const size_t image = static_cast<size_t>((n_draws + kTcTile - 1) / kTcTile) * TcImage<64>::kStride;
         need = std::max(need, make_layout(nc, nq, ts.cand_stride, sz, image).total);
     }
     return need;
-}
-
-void bmc_predict_set_tensor_path(int mode) {
-    g_tensor_min_k = mode == 0 ? kTensorOff : (mode == 1 ? kTensorDefaultMinK : mode);
 }
 
 int bmc_predict_theta_stride(int k) { return bmc_padded_components(k > 0 ? k : 1) + 4; }
@@ -547,7 +568,7 @@ int bmc_coverage_counts(const double* matrix, int64_t s_rows, int64_t n_cols, in
     BMC_CUDA(cudaMemsetAsync(c_le, 0, sizeof(int64_t) * n_cols, st));
     const unsigned gx = static_cast<unsigned>((n_cols + 255) / 256);
     // enough row blocks to cover the machine a few times over
-    long long gy = std::max<long long>(1, std::min<long long>((148 * 8 + gx - 1) / gx, (s_rows + 63) / 64));
+    long long gy = std::max<long long>(1, std::min<long long>((sm_count() * 8 + gx - 1) / gx, (s_rows + 63) / 64));
     const long long rows_per_block = (s_rows + gy - 1) / gy;
     gy = (s_rows + rows_per_block - 1) / rows_per_block;
     coverage_counts_kernel<<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, st>>>(
@@ -573,7 +594,7 @@ int bmc_coverage_levels(const int64_t* c_lt, const int64_t* c_le, int64_t n_poin
     BMC_REQUIRE(n_points >= 1 && n_levels >= 1, "bmc_coverage_levels: bad shape");
     cudaStream_t st = as_stream(stream);
     BMC_CUDA(cudaMemsetAsync(covered, 0, sizeof(int64_t) * n_levels, st));
-    const unsigned gx = static_cast<unsigned>(std::min<long long>((n_points + 255) / 256, 148 * 4));
+    const unsigned gx = static_cast<unsigned>(std::min<long long>((n_points + 255) / 256, sm_count() * 4));
     coverage_levels_kernel<<<dim3(gx, n_levels), 256, 0, st>>>(
         reinterpret_cast<const long long*>(c_lt), reinterpret_cast<const long long*>(c_le), n_points,
         reinterpret_cast<const long long*>(lo_idx), reinterpret_cast<const long long*>(hi_idx), n_levels,

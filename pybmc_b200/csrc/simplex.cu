@@ -88,21 +88,29 @@ int launch_simplex_group16(const SimplexArgs& a, int stats_mode, cudaStream_t st
     return BMC_OK;
 }
 
-int g_simplex_group16 = 1;      // bmc_simplex_set_group16(): A/B switch, default on
-
-// below this many chains a thread-per-chain launch cannot fill the machine (148 SMs x 4 schedulers x
+// below this many chains a thread-per-chain launch cannot fill the machine (SMs x 4 schedulers x
 // a few warps each): give every chain eight lanes instead.  Measured crossover on B200
 // (profiles/layout_sweep.py): 16,384 chains (4.08 vs 4.03 ms); 32,768: 4.8 vs 7.8 ms; 4096: 4.1 vs 1.7 ms.
 constexpr long long kGroupPerChainBelow = 16384;
 
+// layout (bmc_simplex_problem.layout): AUTO = by chain and model count; THREAD = one chain per thread;
+// GROUP = the general eight-lanes kernel; WARP = the eight-lanes kernel for at most 16 models that precomputes
+// the state-independent part of 32 proposals at a time.  A forced group layout that does not fit (shared
+// memory) falls through to the next one, as AUTO does.
 template <typename real>
-int dispatch_simplex(const SimplexArgs& a, int stats_mode, int threads, cudaStream_t stream) {
-    if (a.n_chains < kGroupPerChainBelow && a.k <= 8 && a.m <= kSimplexModels16 && g_simplex_group16) {
+int dispatch_simplex(const SimplexArgs& a, int layout, int stats_mode, int threads, cudaStream_t stream) {
+    const bool few = a.n_chains < kGroupPerChainBelow;
+    const bool group_fits = a.k <= 8 && a.burn + a.iterations < (1ll << 31) && a.thin < (1ll << 31);
+    const bool try16 = group_fits && a.m <= kSimplexModels16 &&
+                       (layout == BMC_LAYOUT_WARP || (layout == BMC_LAYOUT_AUTO && few));
+    const bool try8 = group_fits && (layout == BMC_LAYOUT_GROUP || layout == BMC_LAYOUT_WARP ||
+                                     (layout == BMC_LAYOUT_AUTO && few));
+    if (try16) {
         const int rc = a.k <= 4 ? launch_simplex_group16<real, 4>(a, stats_mode, stream)
                                 : launch_simplex_group16<real, 8>(a, stats_mode, stream);
         if (rc <= 0) return rc;
     }
-    if (a.n_chains < kGroupPerChainBelow && a.k <= 8) {
+    if (try8) {
         const int rc = a.k <= 4 ? launch_simplex_group<real, 4>(a, stats_mode, stream)
                                 : launch_simplex_group<real, 8>(a, stats_mode, stream);
         if (rc <= 0) return rc;
@@ -117,12 +125,6 @@ int dispatch_simplex(const SimplexArgs& a, int stats_mode, int threads, cudaStre
 }  // namespace
 
 extern "C" {
-
-int bmc_simplex_set_group16(int enabled) {
-    const int before = g_simplex_group16;
-    g_simplex_group16 = enabled != 0;
-    return before;
-}
 
 int bmc_gibbs_simplex_run(int dtype, const bmc_simplex_problem* p, uint64_t seed, uint64_t chain0,
                           int64_t n_chains, int64_t burn, int64_t iterations, int64_t thin, int64_t n_kept,
@@ -140,6 +142,8 @@ int bmc_gibbs_simplex_run(int dtype, const bmc_simplex_problem* p, uint64_t seed
     BMC_REQUIRE(stats_mode >= 0 && stats_mode <= 2, "bmc_gibbs_simplex_run: bad stats_mode");
     BMC_REQUIRE(stats_mode == 0 || chain_stats, "bmc_gibbs_simplex_run: chain_stats is NULL");
     BMC_REQUIRE(p->n_obs > 0 && p->nu0 + p->n_obs > 0, "bmc_gibbs_simplex_run: bad n_obs / nu0");
+    BMC_REQUIRE(p->layout >= BMC_LAYOUT_AUTO && p->layout <= BMC_LAYOUT_WARP, "bmc_gibbs_simplex_run: bad layout %d",
+                p->layout);
     if (samples) {
         BMC_REQUIRE(thin >= 1, "bmc_gibbs_simplex_run: thin=%lld", (long long)thin);
         BMC_REQUIRE(n_kept >= (iterations + thin - 1) / thin, "bmc_gibbs_simplex_run: n_kept too small");
@@ -183,9 +187,10 @@ int bmc_gibbs_simplex_run(int dtype, const bmc_simplex_problem* p, uint64_t seed
     }
     if (accepted) BMC_CUDA(cudaMemsetAsync(accepted, 0, sizeof(int32_t) * n_chains, st));
     if (burn + iterations == 0) return BMC_OK;
-    const int threads = n_chains >= 148ll * 128 * 8 ? 128 : (n_chains >= 148ll * 64 * 2 ? 64 : 32);
-    return dtype == BMC_F32 ? dispatch_simplex<float>(a, stats_mode, threads, st)
-                            : dispatch_simplex<double>(a, stats_mode, threads, st);
+    const long long sms = sm_count();
+    const int threads = n_chains >= sms * 128 * 8 ? 128 : (n_chains >= sms * 64 * 2 ? 64 : 32);
+    return dtype == BMC_F32 ? dispatch_simplex<float>(a, p->layout, stats_mode, threads, st)
+                            : dispatch_simplex<double>(a, p->layout, stats_mode, threads, st);
 }
 
 }  // extern "C"

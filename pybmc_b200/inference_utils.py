@@ -49,6 +49,41 @@ class GibbsResult:
     info: dict = field(default_factory=dict)
     rhat: np.ndarray = None   # [K+1] Gelman-Rubin potential scale reduction (needs >= 2 chains, full stats)
     ess: np.ndarray = None    # [K+1] effective sample size of the whole run (all chains), same requirements
+    hist: np.ndarray = None   # [K+1, HIST_BINS] int64 marginal histograms of [b, sigma] (hist_every > 0)
+    hist_lo: np.ndarray = None      # [K+1] lower edge of bin 0
+    hist_width: np.ndarray = None   # [K+1] bin width
+
+    def quantiles(self, probs):
+        """Marginal quantiles of [b_0..b_{K-1}, sigma] from the device histograms: ``[len(probs), K+1]``
+        (probs in percent, like ``np.percentile``).  NaN where the quantile falls into an edge bin (the
+        posterior reached beyond the binned range)."""
+        if self.hist is None:
+            raise ValueError("no histograms were collected: run with hist_every > 0")
+        return histogram_quantiles(self.hist, self.hist_lo, self.hist_width, probs)
+
+
+def histogram_quantiles(counts, lo, width, probs):
+    """Quantiles of binned data, linear inside the bin that holds the target rank.  counts [D, B]."""
+    counts = np.asarray(counts, dtype=np.float64)
+    probs = np.atleast_1d(np.asarray(probs, dtype=np.float64))
+    if np.any(probs < 0) or np.any(probs > 100):
+        raise ValueError("Percentiles must be in the range [0, 100]")
+    d, nb = counts.shape
+    out = np.full((probs.shape[0], d), np.nan)
+    cum = np.cumsum(counts, axis=1)
+    for c in range(d):
+        total = cum[c, -1]
+        if total <= 0:
+            continue
+        for j, p in enumerate(probs):
+            target = p / 100.0 * total
+            b = int(np.searchsorted(cum[c], target, side="left"))
+            b = min(b, nb - 1)
+            if b == 0 or b == nb - 1 or counts[c, b] == 0:
+                continue                      # edge bins collect everything beyond the range
+            below = cum[c, b - 1]
+            out[j, c] = lo[c] + (b + (target - below) / counts[c, b]) * width[c]
+    return out
 
 
 def USVt_hat_extraction(U, S, Vt, components_kept):
@@ -155,6 +190,10 @@ class ConjugateSampler:
 
     def __init__(self, y, X, prior_info, device=None, reduce=None):
         self.dev = D.device(device)
+        with D.on(self.dev):
+            self._setup(y, X, prior_info, reduce)
+
+    def _setup(self, y, X, prior_info, reduce):
         b0, B0, nu0, sigma20 = prior_info
         yd, Xd = _as_design(y, X, self.dev)
         self.n, self.k = Xd.shape
@@ -189,19 +228,41 @@ class ConjugateSampler:
         self.lam, self.b0, self.nu0, self.sigma20 = lam, b0, float(nu0), float(sigma20)
         self.w, self.d, self.g_ols, self.pull = w, d, g_ols, pull
         wflat = w.reshape(-1) if self.dense_w else np.diag(w).copy()
-        self._consts = D.to_device(np.concatenate([d, pull, g_ols, wflat]), self.dev)
+        self.hist_lo, self.hist_width = self.histogram_range()
+        self._consts = D.to_device(np.concatenate([d, pull, g_ols, self.hist_lo, 1.0 / self.hist_width, wflat]),
+                                   self.dev)
         self._Xd, self._yd = Xd, yd
 
-    def problem(self):
+    def histogram_range(self, span=10.0):
+        """Binned range of [b, sigma] for the marginal histograms: centre +- ``span`` posterior standard
+        deviations, both taken at sigma^2 = sigma2_init from the conditional law of :41-45 (b) and from the
+        Inverse-Gamma law of :50-52 (sigma); _lib.HIST_BINS equal bins.  Returns (lo [K+1], width [K+1])."""
+        k, s2 = self.k, self.sigma2_init
+        var_e = s2 / (self.d + s2)                                # 1 / p_k
+        centre = self.w @ (self.g_ols + self.pull * var_e)
+        sd = np.sqrt((self.w ** 2) @ var_e)
+        a = 0.5 * (self.nu0 + self.n)
+        sig_c = np.sqrt((self.nu0 * self.sigma20 + self.rss_min + k * s2) / (2.0 * a))
+        spread = np.exp(span / (2.0 * np.sqrt(a)))                # sd of log sigma^2 ~ 1 / sqrt(a)
+        lo = np.concatenate([centre - span * sd, [sig_c / spread]])
+        hi = np.concatenate([centre + span * sd, [sig_c * spread]])
+        width = np.maximum(hi - lo, 1e-300) / _lib.HIST_BINS
+        return lo, width
+
+    def problem(self, layout=None):
         base = self._consts.data_ptr()
         k = self.k
-        return _lib.GibbsProblem(k=k, d=base, pull=base + 8 * k, g_ols=base + 16 * k, w=base + 24 * k,
+        return _lib.GibbsProblem(k=k, d=base, pull=base + 8 * k, g_ols=base + 16 * k, w=base + 8 * (5 * k + 2),
                                  dense_w=int(self.dense_w), rss_min=self.rss_min, n_obs=float(self.n),
-                                 nu0=self.nu0, sigma20=self.sigma20, sigma2_init=self.sigma2_init)
+                                 nu0=self.nu0, sigma20=self.sigma20, sigma2_init=self.sigma2_init,
+                                 layout=_lib.LAYOUTS[layout])
 
+    @D.on_own_device
     def run(self, iterations, n_chains=1, seed=0, dtype="float64", thin=1, discard=0, keep_samples=True,
-            stats="auto", chain_offset=0):
-        """Launch the sampler; returns device tensors (samples [n_kept, K+1, C] or None, chain_stats)."""
+            stats="auto", chain_offset=0, layout=None, hist_every=0):
+        """Launch the sampler; returns device tensors (samples [n_kept, K+1, C] or None, chain_stats) and a
+        dict with the launch's layout constants (and ``hist``: uint64 counts [K+1, HIST_BINS] as an int64
+        tensor when ``hist_every`` > 0).  ``layout``: None/"auto", "thread", "group", "warp"."""
         lib = _lib.load()
         tdt, code = D.resolve_dtype(dtype)
         iterations, n_chains, thin, discard = int(iterations), int(n_chains), int(thin), int(discard)
@@ -218,12 +279,22 @@ class ConjugateSampler:
                    if keep_samples else None)
         n_stat = lib.bmc_gibbs_n_stat(kp, mode)
         cstats = torch.empty((n_stat, n_chains), dtype=torch.float64, device=self.dev) if mode else None
-        prob = self.problem()
+        prob = self.problem(layout)
+        hist_every = int(hist_every)
+        if hist_every < 0:
+            raise ValueError("hist_every must be >= 0")
+        hist = hist_arg = None
+        if hist_every:
+            base, k = self._consts.data_ptr(), self.k
+            hist = torch.empty((k + 1, _lib.HIST_BINS), dtype=torch.int64, device=self.dev)
+            hist_arg = C.byref(_lib.GibbsHist(every=hist_every, lo=base + 24 * k, inv_width=base + 8 * (4 * k + 1),
+                                              counts=hist.data_ptr()))
         _lib.check(lib.bmc_gibbs_run(code, C.byref(prob), int(seed) & (2 ** 64 - 1), int(chain_offset), n_chains,
                                      iterations, discard, thin, n_kept, D.ptr(samples), D.ptr(cstats), mode,
-                                     D.stream_ptr(self.dev)), "bmc_gibbs_run")
-        return samples, cstats, dict(kp=kp, mode=mode, n_kept=n_kept)
+                                     hist_arg, D.stream_ptr(self.dev)), "bmc_gibbs_run")
+        return samples, cstats, dict(kp=kp, mode=mode, n_kept=n_kept, hist=hist)
 
+    @D.on_own_device
     def summarise(self, cstats, meta, iterations, n_chains):
         """Device moment sums -> posterior mean/cov of [b, sigma] and per-chain means (host, fp64)."""
         if cstats is None or iterations == 0:
@@ -294,18 +365,30 @@ def _finish_samples(samples, as_numpy):
 
 
 def run_gibbs(y, X, iterations, prior_info, *, n_chains=1, seed=None, dtype="float64", thin=1, discard=0,
-              keep_samples=True, stats="auto", device=None, chain_offset=0, as_numpy=True):
-    """Batched conjugate sampler: ``n_chains`` independent copies of the reference's chain."""
+              keep_samples=True, stats="auto", device=None, chain_offset=0, as_numpy=True, layout=None,
+              hist_every=0):
+    """Batched conjugate sampler: ``n_chains`` independent copies of the reference's chain.
+
+    The moment sums (``mean``, ``cov``, ``rhat``, ``ess``) and the histograms cover ALL iterations of all chains,
+    including the first ``discard`` ones -- ``discard`` / ``thin`` only select which iterates are *stored*; the
+    conjugate sampler starts at the OLS variance and has no burn-in upstream either (:37-39).
+    ``hist_every`` > 0 bins the state after every hist_every-th iteration into marginal histograms
+    (``GibbsResult.hist`` / ``.quantiles``); 64 coincides with the kernels' moment flushes and is free."""
     seed = D.fresh_seed() if seed is None else int(seed)
     sampler = ConjugateSampler(y, X, prior_info, device)
     samples, cstats, meta = sampler.run(iterations, n_chains, seed, dtype, thin, discard, keep_samples, stats,
-                                        chain_offset)
+                                        chain_offset, layout, hist_every)
     mean, cov, chain_mean = sampler.summarise(cstats, meta, int(iterations), int(n_chains))
-    return GibbsResult(samples=_finish_samples(samples, as_numpy), mean=mean, cov=cov, chain_mean=chain_mean,
+    with D.on(sampler.dev):
+        hist = None if meta["hist"] is None else meta["hist"].cpu().numpy()
+        rows = _finish_samples(samples, as_numpy)
+    return GibbsResult(samples=rows, mean=mean, cov=cov, chain_mean=chain_mean,
                        n_chains=int(n_chains), iterations=int(iterations), n_kept=meta["n_kept"], seed=seed,
                        dtype=str(dtype), info=dict(rss_min=sampler.rss_min, b_ols=sampler.b_ols,
                                                    sigma2_init=sampler.sigma2_init),
-                       rhat=getattr(sampler, "last_rhat", None), ess=getattr(sampler, "last_ess", None))
+                       rhat=getattr(sampler, "last_rhat", None), ess=getattr(sampler, "last_ess", None),
+                       hist=hist, hist_lo=sampler.hist_lo if hist is not None else None,
+                       hist_width=sampler.hist_width if hist is not None else None)
 
 
 def gibbs_sampler(y, X, iterations, prior_info, *, n_chains=1, seed=None, dtype="float64", thin=1, discard=0,
@@ -335,6 +418,10 @@ class SimplexSampler:
 
     def __init__(self, y, X, Vt_hat, S_hat, prior_info, stepsize=0.001, device=None):
         self.dev = D.device(device)
+        with D.on(self.dev):
+            self._setup(y, X, Vt_hat, S_hat, prior_info, stepsize)
+
+    def _setup(self, y, X, Vt_hat, S_hat, prior_info, stepsize):
         nu0, sigma20 = prior_info
         Vt_hat = np.asarray(Vt_hat, dtype=np.float64)
         S_hat = np.asarray(S_hat, dtype=np.float64).reshape(-1)
@@ -353,14 +440,16 @@ class SimplexSampler:
         step = S_hat * float(stepsize)                            # sqrt of diag(S^2 step^2), :80
         self._consts = D.to_device(np.concatenate([gram.reshape(-1), b_ols, step, Vt_hat.reshape(-1)]), self.dev)
 
-    def problem(self):
+    def problem(self, layout=None):
         base, k = self._consts.data_ptr(), self.k
         return _lib.SimplexProblem(k=k, m=self.m, gram=base, b_ols=base + 8 * k * k, step=base + 8 * (k * k + k),
                                    vt_hat=base + 8 * (k * k + 2 * k), rss_min=self.rss_min, rss_zero=self.rss_zero,
-                                   n_obs=float(self.n), nu0=self.nu0, sigma20=self.sigma20)
+                                   n_obs=float(self.n), nu0=self.nu0, sigma20=self.sigma20,
+                                   layout=_lib.LAYOUTS[layout])
 
+    @D.on_own_device
     def run(self, iterations, burn, n_chains=1, seed=0, dtype="float64", thin=1, keep_samples=True,
-            stats="auto", chain_offset=0):
+            stats="auto", chain_offset=0, layout=None):
         lib = _lib.load()
         tdt, code = D.resolve_dtype(dtype)
         iterations, burn, n_chains, thin = int(iterations), int(burn), int(n_chains), int(thin)
@@ -373,13 +462,14 @@ class SimplexSampler:
         n_stat = lib.bmc_gibbs_n_stat(kp, mode)
         cstats = torch.empty((n_stat, n_chains), dtype=torch.float64, device=self.dev) if mode else None
         accepted = torch.empty(n_chains, dtype=torch.int32, device=self.dev)
-        prob = self.problem()
+        prob = self.problem(layout)
         _lib.check(lib.bmc_gibbs_simplex_run(code, C.byref(prob), int(seed) & (2 ** 64 - 1), int(chain_offset),
                                              n_chains, burn, iterations, thin, n_kept, D.ptr(samples),
                                              D.ptr(cstats), mode, D.ptr(accepted), D.stream_ptr(self.dev)),
                    "bmc_gibbs_simplex_run")
         return samples, cstats, accepted, dict(kp=kp, mode=mode, n_kept=n_kept)
 
+    @D.on_own_device
     def summarise(self, cstats, meta, iterations, n_chains):
         if cstats is None or iterations == 0:
             return None, None, None
@@ -399,7 +489,7 @@ class SimplexSampler:
 
 def run_gibbs_simplex(y, X, Vt_hat, S_hat, iterations, prior_info, burn=10000, stepsize=0.001, *, n_chains=1,
                       seed=None, dtype="float64", thin=1, keep_samples=True, stats="auto", device=None,
-                      chain_offset=0, as_numpy=True):
+                      chain_offset=0, as_numpy=True, layout=None):
     """Batched simplex-constrained sampler (every chain runs its own burn-in)."""
     # the reference validates after its set-up and before any iteration (:91-94)
     if burn < 0:
@@ -409,10 +499,12 @@ def run_gibbs_simplex(y, X, Vt_hat, S_hat, iterations, prior_info, burn=10000, s
     seed = D.fresh_seed() if seed is None else int(seed)
     sampler = SimplexSampler(y, X, Vt_hat, S_hat, prior_info, stepsize, device)
     samples, cstats, accepted, meta = sampler.run(iterations, burn, n_chains, seed, dtype, thin, keep_samples,
-                                                  stats, chain_offset)
+                                                  stats, chain_offset, layout)
     mean, cov, chain_mean = sampler.summarise(cstats, meta, int(iterations), int(n_chains))
-    acc = D.to_host(accepted).astype(np.float64) / max(int(iterations), 1)
-    return GibbsResult(samples=_finish_samples(samples, as_numpy), mean=mean, cov=cov, chain_mean=chain_mean,
+    with D.on(sampler.dev):
+        acc = D.to_host(accepted).astype(np.float64) / max(int(iterations), 1)
+        rows = _finish_samples(samples, as_numpy)
+    return GibbsResult(samples=rows, mean=mean, cov=cov, chain_mean=chain_mean,
                        n_chains=int(n_chains), iterations=int(iterations), n_kept=meta["n_kept"], seed=seed,
                        dtype=str(dtype), acceptance=acc, info=dict(rss_min=sampler.rss_min, b_ols=sampler.b_ols),
                        rhat=getattr(sampler, "last_rhat", None), ess=getattr(sampler, "last_ess", None))
@@ -441,6 +533,11 @@ def gibbs_sampler_literal(y, X, iterations, prior_info, *, n_chains=1, seed=None
     ``bmc_gibbs_literal_run`` in include/bmc_b200.h.  Returns ``[n_chains*iterations, K+1]``."""
     lib = _lib.load()
     dev = D.device(device)
+    with D.on(dev):
+        return _literal(lib, dev, y, X, iterations, prior_info, n_chains, seed, dtype, chain_offset)
+
+
+def _literal(lib, dev, y, X, iterations, prior_info, n_chains, seed, dtype, chain_offset):
     tdt, code = D.resolve_dtype(dtype)
     seed = D.fresh_seed() if seed is None else int(seed)
     b0, B0, nu0, sigma20 = prior_info

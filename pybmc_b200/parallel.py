@@ -18,6 +18,19 @@ def _world(group=None):
     return 0, 1
 
 
+def all_ranks_agree(ok, what, group=None, device=None):
+    """Raise ValueError(what) on EVERY rank if ``ok`` is false on any of them (one MIN all-reduce), so that
+    a rank with an unusable share -- no chains, no rows -- can never leave the others waiting inside a later
+    collective."""
+    flag = 1 if ok else 0
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.tensor([flag], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        flag = int(t.item())
+    if not flag:
+        raise ValueError(what)
+
+
 def chain_range(n_chains_total, rank=None, world=None, group=None):
     """Global chain ids [start, stop) owned by ``rank``: contiguous, sizes differ by at most one."""
     if rank is None or world is None:
@@ -82,6 +95,7 @@ def sum_over_ranks(group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         return t
+    reduce.rank, reduce.world = _world(group)      # lets callers lay out an all-gather as a sum of slots
     return reduce
 
 
@@ -95,8 +109,12 @@ def sharded_orthogonalize(preds_rows, truth_rows, components_kept, *, group=None
     local centring and partial Gram, one all-reduce of the M-by-M matrix (512 KB at M = 256), the
     same small eigenproblem on every rank, local projection.  Returns this rank's y, mu, U_hat rows
     and the replicated S_hat, Vt_hat, Vt_hat_normalized."""
+    from . import _device as D
     from .bmc import orthogonalize_arrays
-    return orthogonalize_arrays(preds_rows, truth_rows, components_kept, method="gram", device=device,
+    n_rows = int(np.asarray(preds_rows).shape[0])
+    all_ranks_agree(n_rows >= 1, "sharded_orthogonalize: every rank needs at least one row of the table", group,
+                    D.device(device))
+    return orthogonalize_arrays(preds_rows, truth_rows, components_kept, method="auto", device=device,
                                 reduce=sum_over_ranks(group))
 
 
@@ -118,58 +136,122 @@ def posterior_from_sums(sums, count, k):
 # the two sharded entry points (one process per GPU; call them from every rank)
 # ------------------------------------------------------------------------------------------------
 def sharded_gibbs(y, X, iterations, prior_info, n_chains_total, *, seed, dtype="float32", thin=1, discard=0,
-                  keep_samples=False, group=None, device=None, rows_sharded=False):
+                  keep_samples=False, group=None, device=None, rows_sharded=False, hist_every=0, as_numpy=True,
+                  sampler=None):
     """Run this rank's share of ``n_chains_total`` conjugate chains and all-reduce the moment sums.
 
     Every rank returns the same posterior mean / covariance of [b, sigma] (what a single GPU running
     all chains would report) plus its own ``GibbsResult`` (samples of its chains, if kept).
     ``rows_sharded=True``: (y, X) are this rank's rows (from ``sharded_orthogonalize``); X'X, X'y,
-    y'y and RSS_min are all-reduced first, so every rank samples the same posterior."""
+    y'y and RSS_min are all-reduced first, so every rank samples the same posterior.
+    ``hist_every`` > 0: marginal histograms of [b, sigma] are collected on every rank and summed by a second
+    all-reduce (uint64 counts as int64: exact); the local result then carries the GLOBAL histograms, so
+    ``local.quantiles(q)`` are the credible-interval endpoints of the whole run on every rank.
+    ``sampler``: a ``ConjugateSampler`` already built for (y, X, prior_info) on this rank (skips the set-up).
+
+    Collectives: all-reduce(sum, fp64) of [moment sums, count] -- 55 doubles at K = 8 -- and, with histograms,
+    all-reduce(sum, int64) of (K+1) x 512 counts (36 KB at K = 8)."""
+    from . import _device as D
     from .inference_utils import ConjugateSampler, GibbsResult, _finish_samples, _moments_from_stats
     rank, world = _world(group)
     lo, hi = chain_range(n_chains_total, rank, world)
-    sampler = ConjugateSampler(y, X, prior_info, device, reduce=sum_over_ranks(group) if rows_sharded else None)
+    dev = D.device(device) if sampler is None else sampler.dev
+    all_ranks_agree(hi - lo >= 1 and (not rows_sharded or int(np.asarray(y).shape[0]) >= 1),
+                    f"sharded_gibbs: {n_chains_total} chains (or the rows of the table) do not cover all {world} ranks",
+                    group, dev)
+    if sampler is None:
+        sampler = ConjugateSampler(y, X, prior_info, dev, reduce=sum_over_ranks(group) if rows_sharded else None)
     stats = "full" if sampler.k <= 8 else "auto"           # cross moments only while they fit in registers
-    samples, cstats, meta = sampler.run(iterations, hi - lo, seed, dtype, thin, discard, keep_samples, stats, lo)
-    total, count = merge_moment_sums(cstats.sum(dim=1), float(iterations) * (hi - lo), group)
-    k, kp = sampler.k, meta["kp"]
-    mean_e, cov_e = _moments_from_stats(total.cpu().numpy(), k, kp, meta["mode"], count)
+    samples, cstats, meta = sampler.run(iterations, hi - lo, seed, dtype, thin, discard, keep_samples, stats, lo,
+                                        None, hist_every)
+    with D.on(dev):
+        total, count = merge_moment_sums(cstats.sum(dim=1), float(iterations) * (hi - lo), group)
+        hist = meta["hist"]
+        if hist is not None and world > 1:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        k, kp = sampler.k, meta["kp"]
+        mean_e, cov_e = _moments_from_stats(total.cpu().numpy(), k, kp, meta["mode"], count)
+        rows = _finish_samples(samples, as_numpy)
+        hist = None if hist is None else hist.cpu().numpy()
     jac = np.zeros((k + 1, k + 1))
     jac[:k, :k] = sampler.w
     jac[k, k] = 1.0
     base = np.concatenate([sampler.w @ sampler.g_ols, [np.sqrt(sampler.sigma2_init)]])
-    local = GibbsResult(samples=_finish_samples(samples, True), mean=None, cov=None, chain_mean=None,
+    local = GibbsResult(samples=rows, mean=None, cov=None, chain_mean=None,
                         n_chains=hi - lo, iterations=int(iterations), n_kept=meta["n_kept"], seed=int(seed),
-                        dtype=str(dtype), info=dict(chain_range=(lo, hi)))
+                        dtype=str(dtype), info=dict(chain_range=(lo, hi)), hist=hist,
+                        hist_lo=sampler.hist_lo if hist is not None else None,
+                        hist_width=sampler.hist_width if hist is not None else None)
     return base + jac @ mean_e, jac @ cov_e @ jac.T, local
 
 
+def broadcast_draws(theta, k, *, src=0, group=None, device=None):
+    """The posterior rows used for prediction, resident on every rank's GPU after ONE host upload:
+    rank ``src`` copies ``theta`` ([S, K+1] host array) to its device, the others receive it with a
+    broadcast over NVLink (13.6 MB at S = 1e5, K = 16) instead of each uploading its own copy over PCIe
+    (SURVEY.md section 8e).  ``theta`` is only read on ``src`` apart from its shape."""
+    from . import _device as D
+    rank, world = _world(group)
+    dev = D.device(device)
+    with D.on(dev):
+        if world == 1 or rank == src:
+            th = D.to_device(np.asarray(theta, dtype=np.float64), dev)
+        else:
+            th = torch.empty((int(np.shape(theta)[0]), k + 1), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.broadcast(th, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    return th
+
+
 def sharded_predictive_summary(preds, theta, Vt_hat, *, truth=None, percentiles=(2.5, 50.0, 97.5), seed=0,
-                               dtype="float32", group=None, device=None):
-    """Fused prediction with the nuclei split over ranks; every rank returns the full-length outputs
-    (all-gather).  ``theta`` are the posterior rows to use (already selected), identical on all ranks."""
+                               dtype="float32", group=None, device=None, gather=True, n_points_total=None):
+    """Fused prediction with the nuclei split over ranks.  ``preds`` / ``truth`` are the FULL tables (every
+    rank slices its own 4-aligned block of nuclei); ``theta`` are the posterior rows to use (already
+    selected), identical on all ranks -- only rank 0 uploads them, the others get them by ``broadcast_draws``.
+
+    ``gather=True``: every rank returns the full-length outputs (ONE all-gather of the packed per-nucleus block
+    [mean | var | percentiles | c_lt | c_le], (4 + Q) x 8 bytes per nucleus); ``gather=False``: each rank
+    returns its own block (``PredictiveResult`` over nuclei ``point_range(...)``), no collective after the
+    broadcast.  ``n_points_total``: ``preds`` / ``truth`` are ALREADY this rank's block ``point_range(n_points_total)``
+    (tables too large to replicate on every host process)."""
+    from . import _device as D
     from .sampling_utils import PredictiveProblem, PredictiveResult
     rank, world = _world(group)
-    n = int(np.asarray(preds).shape[0])
+    dev = D.device(device)
+    sliced = n_points_total is not None
+    n = int(n_points_total) if sliced else int(np.asarray(preds).shape[0])
     lo, hi = point_range(n, rank, world)
-    if hi > lo:
-        prob = PredictiveProblem(np.asarray(preds)[lo:hi], theta, Vt_hat,
-                                 truth=None if truth is None else np.asarray(truth)[lo:hi], dtype=dtype,
-                                 device=device, point0=lo)
-        res = prob.run(percentiles=percentiles, seed=seed, as_numpy=False)
-        dev = res.mean.device
-        parts = dict(mean=res.mean, var=res.var, percentiles=res.percentiles, c_lt=res.c_lt, c_le=res.c_le)
-        passes = res.passes
-    else:   # more ranks than 4-aligned blocks of nuclei
-        dev = torch.device("cuda", torch.cuda.current_device())
-        nq = len(tuple(percentiles))
-        parts = dict(mean=torch.zeros(0, dtype=torch.float64, device=dev),
-                     var=torch.zeros(0, dtype=torch.float64, device=dev),
-                     percentiles=torch.zeros((nq, 0), dtype=torch.float64, device=dev),
-                     c_lt=None if truth is None else torch.zeros(0, dtype=torch.int64, device=dev),
-                     c_le=None if truth is None else torch.zeros(0, dtype=torch.int64, device=dev))
+    if sliced and int(np.asarray(preds).shape[0]) != hi - lo:
+        raise ValueError(f"rank {rank} was given {np.asarray(preds).shape[0]} rows for its block [{lo}, {hi})")
+    k = int(np.asarray(Vt_hat).shape[0])
+    nq = len(tuple(percentiles))
+    th = broadcast_draws(theta, k, group=group, device=dev)
+    with D.on(dev):
+        rows = 2 + nq + 2
+        per = point_range(n, 0, world)[1]
+        block = torch.zeros((rows, per), dtype=torch.float64, device=dev)
         passes = 0
-    out = {k: (None if v is None else gather_points(v, n, group).cpu().numpy()) for k, v in parts.items()}
-    return PredictiveResult(mean=out["mean"], var=out["var"], percentiles=out["percentiles"], c_lt=out["c_lt"],
-                            c_le=out["c_le"], draws=None, n_draws=int(np.asarray(theta).shape[0]), passes=passes,
-                            seed=int(seed))
+        if hi > lo:
+            rows_ = slice(None) if sliced else slice(lo, hi)
+            prob = PredictiveProblem(np.asarray(preds)[rows_], th, Vt_hat,
+                                     truth=None if truth is None else np.asarray(truth)[rows_], dtype=dtype,
+                                     device=dev, point0=lo)
+            res = prob.run(percentiles=percentiles, seed=seed, as_numpy=False)
+            passes = res.passes
+            block[0, : hi - lo] = res.mean
+            block[1, : hi - lo] = res.var
+            block[2:2 + nq, : hi - lo] = res.percentiles
+            if truth is not None:       # int64 counts travel as their bit patterns
+                block[2 + nq, : hi - lo] = res.c_lt.view(torch.float64)
+                block[3 + nq, : hi - lo] = res.c_le.view(torch.float64)
+        if gather and world > 1:
+            parts = torch.empty((world, rows, per), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(parts, block, group=group)
+            block = parts.permute(1, 0, 2).reshape(rows, world * per)[:, :n]
+        else:
+            block = block[:, : hi - lo]
+        out = D.to_host(block.contiguous()) if block.numel() else block.cpu().numpy()
+    counts = None if truth is None else out[2 + nq:].view(np.int64)
+    return PredictiveResult(mean=out[0], var=out[1], percentiles=out[2:2 + nq],
+                            c_lt=None if counts is None else counts[0], c_le=None if counts is None else counts[1],
+                            draws=None, n_draws=int(np.shape(theta)[0]), passes=passes, seed=int(seed))

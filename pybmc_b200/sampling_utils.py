@@ -31,6 +31,16 @@ class PredictiveResult:
     seed: int
 
 
+def truth_for(truth, n_points, what="truth"):
+    """The first ``n_points`` truth values as a float64 vector.  Upstream indexes ``data_true[i]`` for every
+    point (pybmc/sampling_utils.py:26-33) and raises IndexError when the column is shorter; a longer one is
+    read only as far as the points go.  Checked on the host: the kernels read truth[n] for every n."""
+    t = np.asarray(truth, dtype=np.float64).reshape(-1)
+    if t.shape[0] < n_points:
+        raise IndexError(f"{what} has {t.shape[0]} entries for {n_points} points")
+    return t[:n_points]
+
+
 def coverage_indices(percentiles, n_draws):
     """Order-statistic indices exactly as the reference computes them
     (pybmc/sampling_utils.py:30-31): Python float arithmetic on each element of ``percentiles``,
@@ -46,17 +56,21 @@ def coverage_from_counts(percentiles, n_draws, c_lt, c_le, device=None):
     lib = _lib.load()
     dev = D.device(device)
     lo, hi = coverage_indices(percentiles, n_draws)
-    c_lt = c_lt if isinstance(c_lt, torch.Tensor) else torch.from_numpy(np.asarray(c_lt, dtype=np.int64)).to(dev)
-    c_le = c_le if isinstance(c_le, torch.Tensor) else torch.from_numpy(np.asarray(c_le, dtype=np.int64)).to(dev)
-    n = int(c_lt.numel())
-    if n == 0:
-        raise ZeroDivisionError("division by zero")     # upstream divides by the number of points (:35)
-    lo_d = torch.tensor(lo, dtype=torch.int64, device=dev)
-    hi_d = torch.tensor(hi, dtype=torch.int64, device=dev)
-    out = torch.empty(len(lo), dtype=torch.int64, device=dev)
-    _lib.check(lib.bmc_coverage_levels(D.ptr(c_lt), D.ptr(c_le), n, D.ptr(lo_d), D.ptr(hi_d), len(lo), D.ptr(out),
-                                       D.stream_ptr(dev)), "bmc_coverage_levels")
-    return [int(c) / n * 100 for c in out.cpu().tolist()]
+    with D.on(dev):
+        c_lt = c_lt if isinstance(c_lt, torch.Tensor) else torch.from_numpy(np.asarray(c_lt, dtype=np.int64))
+        c_le = c_le if isinstance(c_le, torch.Tensor) else torch.from_numpy(np.asarray(c_le, dtype=np.int64))
+        c_lt, c_le = c_lt.to(dev).contiguous(), c_le.to(dev).contiguous()
+        n = int(c_lt.numel())
+        if n == 0:
+            raise ZeroDivisionError("division by zero")     # upstream divides by the number of points (:35)
+        if int(c_le.numel()) != n:
+            raise ValueError("c_lt and c_le must have one entry per point")
+        lo_d = torch.tensor(lo, dtype=torch.int64, device=dev)
+        hi_d = torch.tensor(hi, dtype=torch.int64, device=dev)
+        out = torch.empty(len(lo), dtype=torch.int64, device=dev)
+        _lib.check(lib.bmc_coverage_levels(D.ptr(c_lt), D.ptr(c_le), n, D.ptr(lo_d), D.ptr(hi_d), len(lo),
+                                           D.ptr(out), D.stream_ptr(dev)), "bmc_coverage_levels")
+        return [int(c) / n * 100 for c in out.cpu().tolist()]
 
 
 def coverage(percentiles, rndm_m, models_output, truth_column, *, device=None):
@@ -79,29 +93,34 @@ def coverage(percentiles, rndm_m, models_output, truth_column, *, device=None):
     mat = np.asarray(rndm_m, dtype=np.float64)
     if mat.ndim != 2:
         raise ValueError("rndm_m must be [n_draws, n_points]")
-    truth = np.asarray(models_output[truth_column].tolist(), dtype=np.float64)
     s_rows, n_cols = mat.shape
+    truth = truth_for(models_output[truth_column].tolist(), n_cols, f"column {truth_column!r}")   # :26-33
+    with D.on(dev):
+        c_lt, c_le = _order_counts_device(lib, dev, mat, truth)
+    return coverage_from_counts(percentiles, s_rows, c_lt, c_le, dev)
+
+
+def _order_counts_device(lib, dev, mat, truth):
     md = D.to_device(mat, dev)
     td = D.to_device(truth, dev)
+    s_rows, n_cols = md.shape
     c_lt = torch.empty(n_cols, dtype=torch.int64, device=dev)
     c_le = torch.empty(n_cols, dtype=torch.int64, device=dev)
     _lib.check(lib.bmc_coverage_counts(D.ptr(md), s_rows, n_cols, md.stride(0), D.ptr(td), D.ptr(c_lt), D.ptr(c_le),
                                        D.stream_ptr(dev)), "bmc_coverage_counts")
-    return coverage_from_counts(percentiles, s_rows, c_lt, c_le, dev)
+    return c_lt, c_le
 
 
 def order_counts(rndm_m, truth, *, device=None):
     """#(x < t), #(x <= t) per column of a materialised matrix (``bmc_coverage_counts``)."""
     lib = _lib.load()
     dev = D.device(device)
-    md = D.to_device(np.asarray(rndm_m, dtype=np.float64), dev)
-    td = D.to_device(np.asarray(truth, dtype=np.float64), dev)
-    s_rows, n_cols = md.shape
-    c_lt = torch.empty(n_cols, dtype=torch.int64, device=dev)
-    c_le = torch.empty(n_cols, dtype=torch.int64, device=dev)
-    _lib.check(lib.bmc_coverage_counts(D.ptr(md), s_rows, n_cols, md.stride(0), D.ptr(td), D.ptr(c_lt), D.ptr(c_le),
-                                       D.stream_ptr(dev)), "bmc_coverage_counts")
-    return c_lt.cpu().numpy(), c_le.cpu().numpy()
+    mat = np.asarray(rndm_m, dtype=np.float64)
+    if mat.ndim != 2:
+        raise ValueError("rndm_m must be [n_draws, n_points]")
+    with D.on(dev):
+        c_lt, c_le = _order_counts_device(lib, dev, mat, truth_for(truth, mat.shape[1]))
+        return c_lt.cpu().numpy(), c_le.cpu().numpy()
 
 
 def column_percentiles(matrix, percentiles, *, truth=None, device=None):
@@ -110,22 +129,26 @@ def column_percentiles(matrix, percentiles, *, truth=None, device=None):
     ``PredictiveResult`` (draws=None)."""
     lib = _lib.load()
     dev = D.device(device)
-    md = D.to_device(np.asarray(matrix, dtype=np.float64), dev)
-    s_rows, n_cols = md.shape
-    center = torch.empty(n_cols, dtype=torch.float64, device=dev)
-    scale = torch.empty(n_cols, dtype=torch.float64, device=dev)
-    _lib.check(lib.bmc_column_moments(D.ptr(md), s_rows, n_cols, md.stride(0), D.ptr(center), D.ptr(scale),
-                                      D.stream_ptr(dev)), "bmc_column_moments")
-    td = D.to_device(np.asarray(truth, dtype=np.float64), dev) if truth is not None else None
-    return _launch_fused(dev, "float64", n_points=n_cols, point0=0, n_draws=s_rows, k=0, u=None, mu=None, truth=td,
-                         theta=None, noise_mode=_lib.NOISE_EXTERNAL, seed=0, noise=md, ld_noise=md.stride(0),
-                         percentiles=percentiles, theta_mean=None, theta_cov=None, center=center, scale=scale,
-                         return_draws=False)
+    mat = np.asarray(matrix, dtype=np.float64)
+    if mat.ndim != 2:
+        raise ValueError("matrix must be [n_draws, n_points]")
+    with D.on(dev):
+        md = D.to_device(mat, dev)
+        s_rows, n_cols = md.shape
+        center = torch.empty(n_cols, dtype=torch.float64, device=dev)
+        scale = torch.empty(n_cols, dtype=torch.float64, device=dev)
+        _lib.check(lib.bmc_column_moments(D.ptr(md), s_rows, n_cols, md.stride(0), D.ptr(center), D.ptr(scale),
+                                          D.stream_ptr(dev)), "bmc_column_moments")
+        td = D.to_device(truth_for(truth, n_cols), dev) if truth is not None else None
+        return _launch_fused(dev, "float64", n_points=n_cols, point0=0, n_draws=s_rows, k=0, u=None, mu=None,
+                             truth=td, theta=None, noise_mode=_lib.NOISE_EXTERNAL, seed=0, noise=md,
+                             ld_noise=md.stride(0), percentiles=percentiles, theta_mean=None, theta_cov=None,
+                             center=center, scale=scale, return_draws=False)
 
 
 def _launch_fused(dev, dtype, *, n_points, point0, n_draws, k, u, mu, truth, theta, noise_mode, seed, noise,
                   ld_noise, percentiles, theta_mean, theta_cov, center, scale, return_draws, as_numpy=True,
-                  workspace=None):
+                  workspace=None, tensor_min_k=0):
     lib = _lib.load()
     _, code = D.resolve_dtype(dtype)
     probs = np.asarray(percentiles, dtype=np.float64).reshape(-1)
@@ -141,11 +164,12 @@ def _launch_fused(dev, dtype, *, n_points, point0, n_draws, k, u, mu, truth, the
                                 c_le=None if truth is None else np.zeros(0, dtype=np.int64),
                                 draws=np.zeros((n_draws, 0)) if return_draws else None, n_draws=n_draws, passes=0,
                                 seed=int(seed))
-    mean = torch.empty(n_points, dtype=torch.float64, device=dev)
-    var = torch.empty(n_points, dtype=torch.float64, device=dev)
-    quant = torch.empty((nq_total, n_points), dtype=torch.float64, device=dev)
-    c_lt = torch.empty(n_points, dtype=torch.int64, device=dev) if truth is not None else None
-    c_le = torch.empty(n_points, dtype=torch.int64, device=dev) if truth is not None else None
+    # one fp64 block [mean | var | quantiles] and one int64 block [c_lt | c_le]: two device-to-host copies
+    outf = torch.empty((2 + nq_total, n_points), dtype=torch.float64, device=dev)
+    mean, var, quant = outf[0], outf[1], outf[2:]
+    outi = torch.empty((2, n_points), dtype=torch.int64, device=dev) if truth is not None else None
+    c_lt = outi[0] if truth is not None else None
+    c_le = outi[1] if truth is not None else None
     draws = torch.empty((n_draws, n_points), dtype=torch.float64, device=dev) if return_draws else None
     passes = 0
     # the kernel takes up to MAX_QUANTILES percentiles per call; longer lists go in batches
@@ -159,7 +183,8 @@ def _launch_fused(dev, dtype, *, n_points, point0, n_draws, k, u, mu, truth, the
             n_points=n_points, point0=point0, n_draws=n_draws, k=k, u=D.ptr(u), mu=D.ptr(mu), truth=D.ptr(truth),
             theta=D.ptr(theta), noise_mode=noise_mode, seed=int(seed) & (2 ** 64 - 1), noise=D.ptr(noise),
             ld_noise=ld_noise, nq=nq, probs=batch.ctypes.data_as(C.POINTER(C.c_double)),
-            theta_mean=D.ptr(theta_mean), theta_cov=D.ptr(theta_cov), center=D.ptr(center), scale=D.ptr(scale))
+            theta_mean=D.ptr(theta_mean), theta_cov=D.ptr(theta_cov), center=D.ptr(center), scale=D.ptr(scale),
+            tensor_min_k=int(tensor_min_k))
         n_pass = C.c_int(0)
         first = q0 == 0
         _lib.check(lib.bmc_predict_fused(code, C.byref(prob), D.ptr(mean), D.ptr(var), quant[q0:].data_ptr(),
@@ -167,22 +192,29 @@ def _launch_fused(dev, dtype, *, n_points, point0, n_draws, k, u, mu, truth, the
                                          n_points, D.ptr(ws), ws.numel(), C.byref(n_pass), D.stream_ptr(dev)),
                    "bmc_predict_fused")
         passes = max(passes, n_pass.value)
-    conv = D.to_host if as_numpy else (lambda t: t)
-    return PredictiveResult(mean=conv(mean), var=conv(var), percentiles=conv(quant),
-                            c_lt=None if c_lt is None else conv(c_lt), c_le=None if c_le is None else conv(c_le),
-                            draws=None if draws is None else conv(draws), n_draws=n_draws, passes=passes,
-                            seed=int(seed))
+    if as_numpy:
+        outf = D.to_host(outf)
+        outi = None if outi is None else D.to_host(outi)
+        draws = None if draws is None else D.to_host(draws)
+    return PredictiveResult(mean=outf[0], var=outf[1], percentiles=outf[2:],
+                            c_lt=None if outi is None else outi[0], c_le=None if outi is None else outi[1],
+                            draws=draws, n_draws=n_draws, passes=passes, seed=int(seed))
 
 
 class PredictiveProblem:
     """Device-resident inputs of the fused kernel: K-space coordinates of the points and the
     transposed posterior draws.  ``run`` only launches kernels (what bench.py times)."""
 
-    def __init__(self, preds, theta, Vt_hat, truth=None, dtype="float64", device=None, point0=0):
-        lib = _lib.load()
+    def __init__(self, preds, theta, Vt_hat, truth=None, dtype="float64", device=None, point0=0, tensor_min_k=0):
         self.dev = D.device(device)
         self.dtype = dtype
-        tdt, _ = D.resolve_dtype(dtype)
+        self.tensor_min_k = int(tensor_min_k)      # bmc_predict_problem.tensor_min_k (0 default, < 0 FFMA kernels)
+        with D.on(self.dev):
+            self._setup(preds, theta, Vt_hat, truth, point0)
+
+    def _setup(self, preds, theta, Vt_hat, truth, point0):
+        lib = _lib.load()
+        tdt, _ = D.resolve_dtype(self.dtype)
         Vt_hat = np.asarray(Vt_hat, dtype=np.float64)
         preds = np.asarray(preds, dtype=np.float64)
         if preds.ndim != 2 or Vt_hat.ndim != 2 or preds.shape[1] != Vt_hat.shape[1]:
@@ -192,6 +224,8 @@ class PredictiveProblem:
             raise ValueError(f"at most {_lib.MAX_COMPONENTS} components are supported")
         self.n_points = preds.shape[0]
         self.point0 = int(point0)
+        if truth is not None:
+            truth = truth_for(truth, self.n_points)
         if self.n_points == 0:
             self.mu = torch.zeros(0, dtype=torch.float64, device=self.dev)
             self.u = torch.zeros((0, self.k), dtype=tdt, device=self.dev)
@@ -208,9 +242,10 @@ class PredictiveProblem:
         _lib.check(lib.bmc_project_rows(D.ptr(pd_), self.n_points, self.m, pd_.stride(0), None, D.ptr(vd), self.k,
                                         D.ptr(u64), self.k, D.stream_ptr(self.dev)), "bmc_project_rows")
         self.u = u64.to(tdt).contiguous()
-        self.truth = D.to_device(np.asarray(truth, dtype=np.float64), self.dev) if truth is not None else None
+        self.truth = D.to_device(truth, self.dev) if truth is not None else None
         self.set_draws(theta)
 
+    @D.on_own_device
     def set_draws(self, theta):
         """theta: [S, K+1] rows [beta, sigma] (host array or device tensor)."""
         tdt, _ = D.resolve_dtype(self.dtype)
@@ -237,6 +272,7 @@ class PredictiveProblem:
         padded[:, stride - 4] = th[:, self.k].to(tdt)
         self.theta = padded
 
+    @D.on_own_device
     def run(self, percentiles=DEFAULT_PERCENTILES, noise="philox", seed=0, return_draws=False, as_numpy=True,
             workspace=None):
         noise_t, ld = None, 0
@@ -253,7 +289,7 @@ class PredictiveProblem:
                              theta=self.theta, noise_mode=mode, seed=seed, noise=noise_t, ld_noise=ld,
                              percentiles=percentiles, theta_mean=self.theta_mean, theta_cov=self.theta_cov,
                              center=None, scale=None, return_draws=return_draws, as_numpy=as_numpy,
-                             workspace=workspace)
+                             workspace=workspace, tensor_min_k=self.tensor_min_k)
 
 
 def select_draws(samples, n_draws, rng):
@@ -266,7 +302,7 @@ def select_draws(samples, n_draws, rng):
 
 def predictive_summary(filtered_model_predictions, samples, Vt_hat, *, truth=None, n_draws=DEFAULT_DRAWS,
                        percentiles=DEFAULT_PERCENTILES, seed=None, dtype="float64", noise="philox",
-                       return_draws=False, subsample=True, device=None, point0=0):
+                       return_draws=False, subsample=True, device=None, point0=0, tensor_min_k=0):
     """Fused prediction + UQ for ``N`` points (see module docstring).
 
     ``subsample=True`` draws ``n_draws`` posterior rows without replacement like the reference;
@@ -278,7 +314,7 @@ def predictive_summary(filtered_model_predictions, samples, Vt_hat, *, truth=Non
     else:
         theta = np.asarray(samples, dtype=np.float64)
     prob = PredictiveProblem(filtered_model_predictions, theta, Vt_hat, truth=truth, dtype=dtype, device=device,
-                             point0=point0)
+                             point0=point0, tensor_min_k=tensor_min_k)
     return prob.run(percentiles=percentiles, noise=noise, seed=seed, return_draws=return_draws)
 
 

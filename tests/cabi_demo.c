@@ -43,9 +43,10 @@ int main(int argc, char** argv) {
     bmc_gibbs_problem p;
     p.k = 2; p.d = dconst; p.pull = dconst + 2; p.g_ols = dconst + 4; p.w = dconst + 6; p.dense_w = 1;
     p.rss_min = c[10]; p.n_obs = 3.0; p.nu0 = 1.0; p.sigma20 = 1.0; p.sigma2_init = c[11];
+    p.layout = BMC_LAYOUT_AUTO;
     const int chains = 4, iters = 5;
     double* dsamples = (double*)to_dev(NULL, sizeof(double) * iters * 3 * chains);
-    CK(bmc_gibbs_run(BMC_F64, &p, 42, 0, chains, iters, 0, 1, iters, dsamples, NULL, BMC_STATS_NONE, NULL));
+    CK(bmc_gibbs_run(BMC_F64, &p, 42, 0, chains, iters, 0, 1, iters, dsamples, NULL, BMC_STATS_NONE, NULL, NULL));
     double samples[5 * 3 * 4];
     CU(cudaMemcpy(samples, dsamples, sizeof samples, cudaMemcpyDeviceToHost));
     for (int ch = 0; ch < chains; ++ch)
@@ -66,7 +67,7 @@ int main(int argc, char** argv) {
     printf("counts %lld %lld %lld %lld\n", (long long)lt[0], (long long)le[0], (long long)lt[1], (long long)le[1]);
 
     /* 4. argument errors come back as codes + messages, not crashes */
-    int rc = bmc_gibbs_run(BMC_F64, &p, 42, 0, 0, iters, 0, 1, iters, dsamples, NULL, BMC_STATS_NONE, NULL);
+    int rc = bmc_gibbs_run(BMC_F64, &p, 42, 0, 0, iters, 0, 1, iters, dsamples, NULL, BMC_STATS_NONE, NULL, NULL);
     printf("bad call -> %d (%s)\n", rc, bmc_last_error());
     CU(cudaDeviceSynchronize());
     return 0;

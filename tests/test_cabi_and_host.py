@@ -58,7 +58,7 @@ def test_argument_errors_surface_as_value_errors_without_a_gpu():
     with pytest.raises(ValueError):
         _lib.check(rc)
     gp = _lib.GibbsProblem(k=65)
-    assert lib.bmc_gibbs_run(_lib.F32, ctypes.byref(gp), 0, 0, 1, 1, 0, 1, 1, None, None, 0, None) == _lib.ERR_ARG
+    assert lib.bmc_gibbs_run(_lib.F32, ctypes.byref(gp), 0, 0, 1, 1, 0, 1, 1, None, None, 0, None, None) == _lib.ERR_ARG
     assert "k=65" in lib.bmc_last_error().decode()
 
 

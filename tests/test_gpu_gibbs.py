@@ -337,18 +337,14 @@ def test_simplex_few_model_kernels_match_general_group_kernel():
     per-iteration dot products, so fp64 round-off apart -- with the same moment sums and acceptance counts;
     chain counts that leave groups of the last warp idle, burn-in that ends inside a batch, thinning."""
     import pybmc_b200 as pb
-    from pybmc_b200 import _lib
-    lib = _lib.load()
     y, X, Vt, S = _simplex_case()
+    layouts = {1: "warp", 0: "group"}          # bmc_simplex_problem.layout: precomputed rows / general group kernel
     for n_chains, T, burn, thin in ((37, 500, 70, 3), (1, 203, 0, 1), (64, 61, 11, 7)):
         out = {}
         for mode in (1, 0):
-            before = lib.bmc_simplex_set_group16(mode)
-            try:
-                out[mode] = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02,
-                                                 n_chains=n_chains, seed=5, thin=thin, stats="full")
-            finally:
-                lib.bmc_simplex_set_group16(before)
+            out[mode] = pb.run_gibbs_simplex(y, X, Vt, S, T, [1.0, 0.02], burn=burn, stepsize=0.02,
+                                             n_chains=n_chains, seed=5, thin=thin, stats="full",
+                                             layout=layouts[mode])
         b = out[0]
         for mode in (1,):
             a = out[mode]
@@ -358,12 +354,9 @@ def test_simplex_few_model_kernels_match_general_group_kernel():
             np.testing.assert_allclose(a.cov, b.cov, rtol=1e-7, atol=1e-12)
     f32 = {}
     for mode in (1, 0):
-        before = lib.bmc_simplex_set_group16(mode)
-        try:
-            f32[mode] = pb.run_gibbs_simplex(y, X, Vt, S, 4000, [1.0, 0.02], burn=500, stepsize=0.02, n_chains=512,
-                                             seed=9, dtype="float32", keep_samples=False, stats="full")
-        finally:
-            lib.bmc_simplex_set_group16(before)
+        f32[mode] = pb.run_gibbs_simplex(y, X, Vt, S, 4000, [1.0, 0.02], burn=500, stepsize=0.02, n_chains=512,
+                                         seed=9, dtype="float32", keep_samples=False, stats="full",
+                                         layout=layouts[mode])
     # fp32: same law (chains may part ways after a borderline decision); moments of 2e6 draws agree
     np.testing.assert_allclose(f32[1].mean, f32[0].mean, rtol=2e-3, atol=2e-4)
     assert abs(f32[1].acceptance.mean() - f32[0].acceptance.mean()) < 5e-3

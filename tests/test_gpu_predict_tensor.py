@@ -24,25 +24,17 @@ def _problem(k, n, s, m=None, seed=0, bimodal=False):
     return preds, vt, theta, truth
 
 
-@pytest.fixture
-def tensor_switch():
-    from pybmc_b200 import _lib
-    lib = _lib.load()
-    yield lib.bmc_predict_set_tensor_path
-    lib.bmc_predict_set_tensor_path(1)
-
-
 @pytest.mark.parametrize("k,n,s", [(17, 300, 3000), (40, 129, 1000), (64, 700, 2500), (32, 128, 128), (64, 5, 130),
                                    (3, 200, 1000), (8, 131, 900), (12, 64, 515), (16, 400, 2000)])
-def test_contraction_accuracy_and_agreement_with_ffma(k, n, s, tensor_switch):
+def test_contraction_accuracy_and_agreement_with_ffma(k, n, s):
     from pybmc_b200.sampling_utils import PredictiveProblem
     preds, vt, theta, truth = _problem(k, n, s)
     prob = PredictiveProblem(preds, theta, vt, truth=truth, dtype="float32")
     m = preds.shape[1]
     want = (theta[:, :k] @ vt + 1.0 / m) @ preds.T                   # sampling_utils.py:64-72 in fp64
-    tensor_switch(1)
+    prob.tensor_min_k = 0                     # bmc_predict_problem.tensor_min_k: the default, tensor cores for every k
     tc = prob.run(noise="none", return_draws=True)
-    tensor_switch(0)
+    prob.tensor_min_k = -1                    # the FFMA kernels
     ff = prob.run(noise="none", return_draws=True)
     # error budget of the fp32 path: inputs rounded to fp32 once, then K products
     u = preds @ vt.T
@@ -55,9 +47,8 @@ def test_contraction_accuracy_and_agreement_with_ffma(k, n, s, tensor_switch):
 
 
 @pytest.mark.parametrize("k", [6, 16, 24, 64])
-def test_noise_counts_and_percentiles_are_exact_functions_of_the_draws(k, tensor_switch):
+def test_noise_counts_and_percentiles_are_exact_functions_of_the_draws(k):
     from pybmc_b200.sampling_utils import PredictiveProblem
-    tensor_switch(1)
     n, s = 333, 4000
     preds, vt, theta, truth = _problem(k, n, s, seed=1)
     q = [2.5, 16, 50, 84, 97.5]
