@@ -131,14 +131,18 @@ int64_t bmc_gibbs_n_stat(int kp, int stats_mode);
  * binned into BMC_HIST_BINS equal bins per coordinate, bin = floor((v - lo[c]) * inv_width[c]) clamped to the
  * edge bins.  Blocks count in shared memory (uint32) and merge into `counts` with 64-bit atomics when they
  * finish, so the result does not depend on the layout or the sharding.  `counts` is zeroed by the call; sum it
- * over ranks with one all-reduce.  k <= 16.  every = 64 coincides with the kernels' moment flushes and costs
- * nothing in the iteration loop. */
+ * over ranks with one all-reduce.  k <= 16.  `every` must be a multiple of 64: the kernels bin where they flush
+ * their moment sums, outside the arithmetic-only inner loop. */
 typedef struct {
     int64_t every;             /* 0 = off                                                          */
     const double* lo;          /* dev [k+1]  lower edge of bin 0 per coordinate                   */
     const double* inv_width;   /* dev [k+1]  1 / bin width                                        */
     uint64_t* counts;          /* dev [k+1][BMC_HIST_BINS]                                        */
+    void* workspace;           /* dev, bmc_gibbs_hist_workspace_bytes(k): replicas the blocks merge into (they all
+                                  finish together; without it they queue on the words of `counts`)  */
+    size_t workspace_bytes;
 } bmc_gibbs_hist;
+size_t bmc_gibbs_hist_workspace_bytes(int k);
 
 int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* problem /*host*/, uint64_t seed, uint64_t chain0,
                   int64_t n_chains, int64_t iterations, int64_t store_from, int64_t thin, int64_t n_kept,

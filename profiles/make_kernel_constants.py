@@ -29,7 +29,9 @@ CAPTURES = {
     "gibbs_conjugate_f64_k8_full": ("gibbs_f64", r"gibbs_conjugate_kernel<double, ?8, ?2", 65536 * 10000, "chain-iteration"),
     "gibbs_conjugate_f32_k64_diag": ("gibbs_k64", r"gibbs_conjugate_kernel<float, ?64, ?1", 16384 * 1000, "chain-iteration"),
     "gibbs_simplex_group16_f32_k4": ("simplex_f32", r"gibbs_simplex_group16_kernel<float", 4096 * 6000, "chain-iteration"),
-    "predict_pass_tc_f32_k16_q5": ("predict_f32", r"predict_pass_tc_kernel<16, ?5", None, "sample x point"),
+    # one launch = one chunk of 25,088 nuclei (1e5 in four equal chunks, rounded up to 256) x all 1e5 draws; the
+    # launch with the largest grid is a full chunk
+    "predict_pass_tc_f32_k16_q5": ("predict_f32", r"predict_pass_tc_kernel<16, ?5", 25088 * 100000, "sample x point"),
     "predict_select_f32": ("predict_f32", r"predict_select_kernel<float", None, "nucleus x percentile"),
 }
 
@@ -73,8 +75,22 @@ def _num(v):
         return None
 
 
+def _page(path, page):
+    """CSV text of a report page: from the .ncu-rep, or from the export ncu_capture.sh made on the GPU box
+    (<stem>_raw.csv / <stem>_source.csv.gz) when the report itself was too large to bring back."""
+    if os.path.exists(path):
+        return subprocess.run(["ncu", "-i", path, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    stem = path[:-len(".ncu-rep")]
+    if page == "raw" and os.path.exists(stem + "_raw.csv"):
+        return open(stem + "_raw.csv").read()
+    if page == "source" and os.path.exists(stem + "_source.csv.gz"):
+        import gzip
+        return gzip.open(stem + "_source.csv.gz", "rt").read()
+    return ""
+
+
 def raw_rows(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = _page(path, "raw")
     rows = list(csv.reader(io.StringIO(out)))
     if len(rows) < 3:
         return []
@@ -84,7 +100,7 @@ def raw_rows(path):
 
 def opcode_mix(path, kernel_re):
     """Executed warp-instructions by opcode from the source page (last launch whose kernel matches)."""
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    out = _page(path, "source")
     rows = list(csv.reader(io.StringIO(out)))
     blocks, cur = [], None
     for r in rows:
@@ -115,12 +131,14 @@ def opcode_mix(path, kernel_re):
 
 def summarise(key, stem, kernel_re, units, unit_name, directory, tag):
     path = os.path.join(directory, f"{tag}_{stem}.ncu-rep")
-    if not os.path.exists(path):
+    evidence = path if os.path.exists(path) else path[:-len(".ncu-rep")] + "_raw.csv"
+    if not os.path.exists(evidence):
         return None
     rows = [(d, u) for d, u in raw_rows(path) if re.search(kernel_re, d.get("Kernel Name", ""))]
     if not rows:
         return None
-    d, u = rows[-1]                                   # the last captured launch (warm)
+    # the last captured launch (warm); for chunked kernels the one with the largest grid (a full chunk)
+    d, u = max(reversed(rows), key=lambda du: _num(du[0].get("launch__grid_size", "0")) or 0.0)
     counters = {}
     for name in COUNTERS:
         v = _num(d.get(name, ""))
@@ -131,9 +149,9 @@ def summarise(key, stem, kernel_re, units, unit_name, directory, tag):
               if "pcsamp_warps_issue_stalled" in k and _num(v) is not None and not k.endswith("not_issued")}
     tot = sum(stalls.values()) or 1.0
     entry = {
-        "kernel": d.get("Kernel Name"), "report": os.path.relpath(path, ROOT),
-        "report_bytes": os.path.getsize(path),
-        "report_mtime": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime(os.path.getmtime(path))),
+        "kernel": d.get("Kernel Name"), "report": os.path.relpath(evidence, ROOT),
+        "report_bytes": os.path.getsize(evidence),
+        "report_mtime": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime(os.path.getmtime(evidence))),
         "launches_in_report": len(rows), "counters": counters,
         "stall_share_pct": {k: round(100 * v / tot, 1) for k, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:8]},
         "dram_bytes_per_launch": (counters.get("dram__bytes_read.sum", 0.0) + counters.get("dram__bytes_write.sum", 0.0)),
@@ -143,6 +161,9 @@ def summarise(key, stem, kernel_re, units, unit_name, directory, tag):
     if units and inst:
         entry["units_per_launch"] = units
         entry["warp_inst_per_warp_unit"] = inst * 32.0 / units      # warp-instructions per 32 units (one warp's worth)
+        tinst = counters.get("smsp__thread_inst_executed.sum")
+        if tinst:
+            entry["thread_inst_per_unit"] = tinst / units
     mix = opcode_mix(path, kernel_re)
     if mix:
         total = sum(mix.values())

@@ -20,9 +20,22 @@ KEYS = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active
         "smsp__thread_inst_executed_per_inst_executed.ratio"]
 
 
+EXTRA = ["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+         "smsp__pipe_fma_cycles_active.max.pct_of_peak_sustained_active",
+         "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
+         "sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active",
+         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+         "smsp__issue_active.max.pct_of_peak_sustained_active"]
+KEYS = KEYS + EXTRA
+
+
 def main(paths):
     for path in paths:
-        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if path.endswith(".csv"):        # the export profiles/ncu_capture.sh made on the GPU box
+            raw = open(path).read()
+        else:
+            raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units = rows[0], rows[1]
         for vals in rows[2:]:

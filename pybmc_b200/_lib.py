@@ -35,7 +35,8 @@ class GibbsProblem(C.Structure):
 
 
 class GibbsHist(C.Structure):
-    _fields_ = [("every", _i64), ("lo", _p), ("inv_width", _p), ("counts", _p)]
+    _fields_ = [("every", _i64), ("lo", _p), ("inv_width", _p), ("counts", _p), ("workspace", _p),
+                ("workspace_bytes", _sz)]
 
 
 class SimplexProblem(C.Structure):
@@ -64,6 +65,7 @@ SIGNATURES = {
     "bmc_residual_ss": (_int, [_p, _i64, _int, _i64, _p, _p, _p, _p, _sz, _p]),
     "bmc_padded_components": (_int, [_int]),
     "bmc_gibbs_n_stat": (_i64, [_int, _int]),
+    "bmc_gibbs_hist_workspace_bytes": (_sz, [_int]),
     "bmc_gibbs_run": (_int, [_int, C.POINTER(GibbsProblem), _u64, _u64, _i64, _i64, _i64, _i64, _i64, _p, _p,
                              _int, C.POINTER(GibbsHist), _p]),
     "bmc_gibbs_simplex_run": (_int, [_int, C.POINTER(SimplexProblem), _u64, _u64, _i64, _i64, _i64, _i64, _i64,

@@ -15,6 +15,8 @@ constexpr long long kConjGroupBelow = 16384;
 // 23.5 -> 16.2 ms; break-even near 2,048 chains (profiles/warp_sweep.py)
 constexpr long long kConjWarpBelow = 1536;
 
+constexpr int kHistReplicas = 64;          // copies of the histograms the blocks of a launch merge into
+
 // dynamic shared memory of a launch: the block's marginal histograms, when they are on
 size_t hist_smem(const GibbsArgs& a) {
     return a.hist_every ? sizeof(unsigned) * static_cast<size_t>(a.k + 1) * kHistBins : 0;
@@ -68,15 +70,30 @@ int launch_group(const GibbsArgs& a, int stats_mode, cudaStream_t stream) {
     BMC_REQUIRE(a.iterations < (1ll << 31) && a.thin < (1ll << 31) && a.store_from < (1ll << 31),
                 "bmc_gibbs_run: iterations, thin and store_from must fit 31 bits with fewer than %lld chains "
                 "(eight lanes / a warp per chain)", kConjGroupBelow);
+    if (a.hist_every) {
+        // static variate buffer + the block's histograms can pass 48 KB in fp64: opt in to the larger carve-out
+#define BMC_GROUP_HIST(MODE)                                                                                   \
+    do {                                                                                                       \
+        auto kern = gibbs_conjugate_group_kernel<real, KP, MODE, GEN, true>;                                   \
+        BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        kern<<<blocks, wpb * 32, smem, stream>>>(a);                                                           \
+    } while (0)
+        if (stats_mode == BMC_STATS_NONE) BMC_GROUP_HIST(0);
+        else if (stats_mode == BMC_STATS_DIAG) BMC_GROUP_HIST(1);
+        else BMC_GROUP_HIST(2);
+#undef BMC_GROUP_HIST
+        BMC_LAUNCH_CHECK();
+        return BMC_OK;
+    }
     switch (stats_mode) {
         case BMC_STATS_NONE:
-            gibbs_conjugate_group_kernel<real, KP, 0, GEN><<<blocks, wpb * 32, smem, stream>>>(a);
+            gibbs_conjugate_group_kernel<real, KP, 0, GEN><<<blocks, wpb * 32, 0, stream>>>(a);
             break;
         case BMC_STATS_DIAG:
-            gibbs_conjugate_group_kernel<real, KP, 1, GEN><<<blocks, wpb * 32, smem, stream>>>(a);
+            gibbs_conjugate_group_kernel<real, KP, 1, GEN><<<blocks, wpb * 32, 0, stream>>>(a);
             break;
         default:
-            gibbs_conjugate_group_kernel<real, KP, 2, GEN><<<blocks, wpb * 32, smem, stream>>>(a);
+            gibbs_conjugate_group_kernel<real, KP, 2, GEN><<<blocks, wpb * 32, 0, stream>>>(a);
     }
     BMC_LAUNCH_CHECK();
     return BMC_OK;
@@ -104,23 +121,6 @@ int dispatch_conjugate(const GibbsArgs& a, int layout, int stats_mode, int threa
     return launch_conjugate<real, 64>(a, stats_mode, threads, stream);
 }
 
-// d and pull travel inside the kernel parameters as well (constant-bank operands of the thread-per-chain
-// kernel): 2 k doubles read back from the caller's device arrays -- the only synchronisation of the call,
-// a few microseconds against launches of milliseconds.
-int fill_consts(GibbsArgs& a, const bmc_gibbs_problem* p, cudaStream_t st) {
-    double host[2 * BMC_MAX_COMPONENTS];
-    BMC_CUDA(cudaMemcpyAsync(host, p->d, sizeof(double) * p->k, cudaMemcpyDeviceToHost, st));
-    BMC_CUDA(cudaMemcpyAsync(host + BMC_MAX_COMPONENTS, p->pull, sizeof(double) * p->k, cudaMemcpyDeviceToHost, st));
-    BMC_CUDA(cudaStreamSynchronize(st));
-    for (int k = 0; k < BMC_MAX_COMPONENTS; ++k) {
-        a.d_d[k] = k < p->k ? host[k] : 0.0;
-        a.pull_d[k] = k < p->k ? host[BMC_MAX_COMPONENTS + k] : 0.0;
-        a.d_f[k] = static_cast<float>(a.d_d[k]);
-        a.pull_f[k] = static_cast<float>(a.pull_d[k]);
-    }
-    return BMC_OK;
-}
-
 int pick_threads(long long n_chains) {
     // small blocks spread few chains over all SMs; 128 once there is plenty of work
     const long long sms = sm_count();
@@ -134,6 +134,10 @@ int pick_threads(long long n_chains) {
 extern "C" {
 
 int bmc_padded_components(int k) { return k <= 4 ? 4 : k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 64; }
+
+size_t bmc_gibbs_hist_workspace_bytes(int k) {
+    return sizeof(uint64_t) * static_cast<size_t>(kHistReplicas) * (k + 1) * kHistBins;
+}
 
 int64_t bmc_gibbs_n_stat(int k, int stats_mode) {
     const int64_t d = k + 1;
@@ -162,7 +166,9 @@ int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t
                 "bmc_gibbs_run: the group layouts hold one component per lane (k <= 8), k=%d", p->k);
     if (hist && hist->every > 0) {
         BMC_REQUIRE(hist->lo && hist->inv_width && hist->counts, "bmc_gibbs_run: histogram arrays missing");
-        BMC_REQUIRE(hist->every < (1ll << 31), "bmc_gibbs_run: hist.every must fit 31 bits");
+        BMC_REQUIRE(hist->every < (1ll << 31) && hist->every % kFlushEvery == 0,
+                    "bmc_gibbs_run: hist.every must be a multiple of %d (the kernels bin where they flush their moment "
+                    "sums) and fit 31 bits, got %lld", kFlushEvery, (long long)hist->every);
         BMC_REQUIRE(p->k <= 16, "bmc_gibbs_run: marginal histograms need k <= 16 (one block's bins live in "
                                 "shared memory), k=%d", p->k);
     }
@@ -195,7 +201,6 @@ int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t
         a.keys.k0[r] = a.key0 + static_cast<uint32_t>(r) * kPhiloxW0;
         a.keys.k1[r] = a.key1 + static_cast<uint32_t>(r) * kPhiloxW1;
     }
-    if (fill_consts(a, p, st) != BMC_OK) return BMC_ERR_CUDA;
     a.chain0 = chain0;
     a.n_chains = n_chains;
     a.iterations = iterations;
@@ -209,8 +214,15 @@ int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t
         a.hist_every = static_cast<uint32_t>(hist->every);
         a.hist_lo = hist->lo;
         a.hist_inv = hist->inv_width;
-        a.hist = reinterpret_cast<unsigned long long*>(hist->counts);
-        BMC_CUDA(cudaMemsetAsync(hist->counts, 0, sizeof(uint64_t) * static_cast<size_t>(p->k + 1) * kHistBins, st));
+        const size_t words = static_cast<size_t>(p->k + 1) * kHistBins;
+        if (hist->workspace && hist->workspace_bytes >= bmc_gibbs_hist_workspace_bytes(p->k)) {
+            a.hist = static_cast<unsigned long long*>(hist->workspace);
+            a.hist_replicas = kHistReplicas;
+        } else {
+            a.hist = reinterpret_cast<unsigned long long*>(hist->counts);      // correct, but the merge serialises
+            a.hist_replicas = 1;
+        }
+        BMC_CUDA(cudaMemsetAsync(a.hist, 0, sizeof(uint64_t) * words * a.hist_replicas, st));
     }
     if (stats_mode != 0) {
         // the kernel accumulates with the padded component count kp = bmc_padded_components(k)
@@ -218,10 +230,20 @@ int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t
         BMC_CUDA(cudaMemsetAsync(chain_stats, 0,
                                  sizeof(double) * static_cast<size_t>(bmc_gibbs_n_stat(kp, stats_mode)) * n_chains, st));
     }
-    if (iterations == 0) return BMC_OK;
+    if (iterations == 0) {
+        if (a.hist_every) BMC_CUDA(cudaMemsetAsync(hist->counts, 0, sizeof(uint64_t) * (p->k + 1) * kHistBins, st));
+        return BMC_OK;
+    }
     const int threads = pick_threads(n_chains);
-    return dtype == BMC_F32 ? dispatch_conjugate<float>(a, p->layout, stats_mode, threads, st)
-                            : dispatch_conjugate<double>(a, p->layout, stats_mode, threads, st);
+    const int rc = dtype == BMC_F32 ? dispatch_conjugate<float>(a, p->layout, stats_mode, threads, st)
+                                    : dispatch_conjugate<double>(a, p->layout, stats_mode, threads, st);
+    if (rc == BMC_OK && a.hist_every && a.hist_replicas > 1) {
+        const int words = (p->k + 1) * kHistBins;
+        hist_reduce_kernel<<<(words + 255) / 256, 256, 0, st>>>(a.hist, a.hist_replicas, words,
+                                                                reinterpret_cast<unsigned long long*>(hist->counts));
+        BMC_LAUNCH_CHECK();
+    }
+    return rc;
 }
 
 }  // extern "C"

@@ -23,10 +23,6 @@
 #pragma once
 #include "rng.cuh"
 
-#ifndef BMC_CONST_BANK_D
-#define BMC_CONST_BANK_D 1
-#endif
-
 namespace bmc {
 
 struct GibbsArgs {
@@ -41,10 +37,6 @@ struct GibbsArgs {
     double sigma2_init, sigma_ref;
     RunConsts<float> cf;                  // the same scalars + Gamma constants, ready in either type
     RunConsts<double> cd;
-    // d and pull once more, in either type, inside the kernel parameters: the thread-per-chain kernel reads
-    // them as constant-bank operands instead of holding 2 KP registers per thread
-    float d_f[BMC_MAX_COMPONENTS], pull_f[BMC_MAX_COMPONENTS];
-    double d_d[BMC_MAX_COMPONENTS], pull_d[BMC_MAX_COMPONENTS];
     int gamma_boost;                      // shape < 1
     uint32_t key0, key1;
     PhiloxKeys keys;                      // the ten round keys of (key0, key1): constant-bank operands in the kernels
@@ -60,7 +52,8 @@ struct GibbsArgs {
     uint32_t hist_every;                  // 0 = off
     const double* hist_lo;                // [k+1] lower edge of bin 0
     const double* hist_inv;               // [k+1] 1 / bin width
-    unsigned long long* hist;             // [k+1][kHistBins]
+    unsigned long long* hist;             // [hist_replicas][k+1][kHistBins]; block b merges into replica b % hist_replicas
+    int hist_replicas;
 };
 
 constexpr int kHistBins = BMC_HIST_BINS;
@@ -78,12 +71,28 @@ __device__ __forceinline__ void hist_zero(unsigned* hist_s, int coords) {
     for (int i = threadIdx.x; i < coords * kHistBins; i += blockDim.x) hist_s[i] = 0u;
     __syncthreads();
 }
-__device__ __forceinline__ void hist_merge(const unsigned* hist_s, int coords, unsigned long long* hist) {
+// The blocks of a launch finish together: merging straight into one histogram would put ~1000 atomics on each
+// of its words at once (measured: +0.9 ms on a 9.3 ms launch).  Block b adds to replica b % replicas instead;
+// hist_reduce_kernel sums the replicas afterwards.
+// `n_active`: the threads 0 .. n_active-1 of the block are the ones that did not return early (threads past the
+// last chain leave right after the zeroing barrier; from Volta on __syncthreads() waits for the non-exited
+// threads only), so the merge loop strides over them and still covers every bin.
+__device__ __forceinline__ void hist_merge(const unsigned* hist_s, int coords, unsigned long long* hist, int replicas,
+                                           int n_active) {
     __syncthreads();
-    for (int i = threadIdx.x; i < coords * kHistBins; i += blockDim.x) {
+    unsigned long long* mine = hist + static_cast<size_t>(blockIdx.x % replicas) * coords * kHistBins;
+    for (int i = threadIdx.x; i < coords * kHistBins; i += n_active) {
         const unsigned v = hist_s[i];
-        if (v) atomicAdd(hist + i, static_cast<unsigned long long>(v));
+        if (v) atomicAdd(mine + i, static_cast<unsigned long long>(v));
     }
+}
+static __global__ void hist_reduce_kernel(const unsigned long long* replicas, int n_replicas, int words,
+                                   unsigned long long* counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= words) return;
+    unsigned long long s = 0;
+    for (int r = 0; r < n_replicas; ++r) s += replicas[static_cast<size_t>(r) * words + i];
+    counts[i] = s;
 }
 
 constexpr int kFlushEvery = 64;           // iterations between fp64 flushes of the moment sums
@@ -94,52 +103,36 @@ __device__ __forceinline__ const RunConsts<real>& run_consts(const Args& a) {
     else return a.cd;
 }
 
-template <typename real, typename Args>
-__device__ __forceinline__ real d_const(const Args& a, int k) {
-    if constexpr (sizeof(real) == 4) return a.d_f[k];
-    else return a.d_d[k];
-}
-template <typename real, typename Args>
-__device__ __forceinline__ real pull_const(const Args& a, int k) {
-    if constexpr (sizeof(real) == 4) return a.pull_f[k];
-    else return a.pull_d[k];
-}
-
 template <int KP, int MODE>
 struct StatCount {
     static constexpr int D = KP + 1;
     static constexpr int value = MODE == 0 ? 0 : (MODE == 1 ? 2 * D : D + D * (D + 1) / 2);
 };
 
-// HIST: marginal histograms on (a second instantiation, so that the plain kernel's code is untouched by them)
+// HIST: marginal histograms on (a second instantiation, so that the plain kernel's code is untouched by them).
+// (Wrapping the walk in a device function called between zeroing and merging, so that no thread leaves the
+//  kernel early, was measured: 10.13 ms against 9.52 ms for this form -- the early EXIT keeps ptxas' schedule
+//  of the loop; profiles/r2_notes.md.)
 template <typename real, int KP, int MODE, bool HIST = false>
 __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugate_kernel(const GibbsArgs a) {
     using M = Math<real>;
     extern __shared__ unsigned hist_s[];                  // [k+1][kHistBins] when histograms are on
     if constexpr (HIST) hist_zero(hist_s, a.k + 1);
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if constexpr (!HIST) {
-        if (tid >= a.n_chains) return;
-    }
+    if (tid >= a.n_chains) return;
     const unsigned long long gchain = a.chain0 + static_cast<unsigned long long>(tid);
     const uint32_t chain = static_cast<uint32_t>(gchain);
     constexpr int D = KP + 1;
     constexpr int NS = StatCount<KP, MODE>::value;
 
-    // d[k], pull[k]: constant-bank operands (padded components hold 0)
-#if BMC_CONST_BANK_D
-#define BMC_D(k) d_const<real>(a, k)
-#define BMC_PULL(k) pull_const<real>(a, k)
-#else
-    real d_r[KP], pull_r[KP];
+    // (d and pull as constant-bank operands -- typed copies inside the kernel parameters -- were measured in
+    //  round 2: 9.25 vs 9.28 ms, no gain for a synchronising read-back of the constants; profiles/r2_notes.md)
+    real d[KP], pull[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
-        d_r[k] = k < a.k ? static_cast<real>(a.d[k]) : real(0);
-        pull_r[k] = k < a.k ? static_cast<real>(a.pull[k]) : real(0);
+        d[k] = k < a.k ? static_cast<real>(a.d[k]) : real(0);
+        pull[k] = k < a.k ? static_cast<real>(a.pull[k]) : real(0);
     }
-#define BMC_D(k) d_r[k]
-#define BMC_PULL(k) pull_r[k]
-#endif
     const RunConsts<real>& rc = run_consts<real>(a);
     const real rss_min = rc.rss_min;
     const real prior_scale = rc.prior_scale;
@@ -177,11 +170,9 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
 #pragma unroll
     for (int k = 0; k < KP; ++k) e[k] = real(0);
     real* const out = static_cast<real*>(a.samples);
-    // < 2^32 (checked by the host); threads past the last chain only take part in the histogram barriers
-    const uint32_t total = (!HIST || tid < a.n_chains) ? static_cast<uint32_t>(a.iterations) : 0u;
+    const uint32_t total = static_cast<uint32_t>(a.iterations);          // < 2^32 (checked by the host)
     long long next_store = a.samples ? a.store_from : -1;
     long long slot = 0;
-    uint32_t next_hist = HIST ? a.hist_every - 1u : 0xFFFFFFFFu;           // iteration whose state is binned next
 
     GammaPair<real> gp;                                 // first Gamma proposals of iterations 2m, 2m+1
     gp.x[1] = real(0);
@@ -195,9 +186,6 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         if (seg_end > total || seg_end == 0u) seg_end = total;
         if (next_store >= static_cast<long long>(it32) && next_store < static_cast<long long>(seg_end))
             seg_end = static_cast<uint32_t>(next_store) + 1u;
-        if constexpr (HIST) {
-            if (next_hist >= it32 && next_hist < seg_end) seg_end = next_hist + 1u;
-        }
         // one iteration; (gx, gu) = the first Gamma proposal of this iteration
         auto iterate = [&](const uint32_t it32, const real gx, const real gu) {
             real rss0 = rss_min, rss1 = real(0);
@@ -212,11 +200,11 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int k = 4 * j + 2 * h;
-                        const f32x2 dp = pack2(BMC_D(k), BMC_D(k + 1));
+                        const f32x2 dp = pack2(d[k], d[k + 1]);
                         float t0, t1;
                         unpack2(add2(dp, s2b), t0, t1);
                         const f32x2 sdp = mul2(pack2(M::rsqrt(t0), M::rsqrt(t1)), sigb);
-                        const f32x2 ep = mul2(sdp, fma2(pack2(BMC_PULL(k), BMC_PULL(k + 1)), sdp, zp[h]));
+                        const f32x2 ep = mul2(sdp, fma2(pack2(pull[k], pull[k + 1]), sdp, zp[h]));
                         rssp = fma2(mul2(dp, ep), ep, rssp);
                         unpack2(ep, e[k], e[k + 1]);
                     }
@@ -232,10 +220,10 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                         const int k = 4 * j + q;
                         if (k < KP) {
                             // 1/sqrt(p_k) = sigma / sqrt(d_k + s2): one MUFU on the s2 -> e -> RSS -> s2 dependency
-                            const real sd = sig * M::rsqrt(BMC_D(k) + s2);
-                            e[k] = sd * M::fma(BMC_PULL(k), sd, z[q]);      // pull/p + z/sqrt(p)
-                            if (k & 1) rss1 = M::fma(BMC_D(k) * e[k], e[k], rss1);
-                            else rss0 = M::fma(BMC_D(k) * e[k], e[k], rss0);
+                            const real sd = sig * M::rsqrt(d[k] + s2);
+                            e[k] = sd * M::fma(pull[k], sd, z[q]);      // pull/p + z/sqrt(p)
+                            if (k & 1) rss1 = M::fma(d[k] * e[k], e[k], rss1);
+                            else rss0 = M::fma(d[k] * e[k], e[k], rss0);
                         }
                     }
                 }
@@ -344,25 +332,36 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 }
             }
         }
-        if (HIST && it32 - 1u == next_hist) {
-            // marginal histograms: bin b = W (g_ols + e) and sigma of this iteration (shared-memory atomics)
-            for (int r = 0; r < a.k; ++r) {
-                real b = real(0);
-                if (a.dense_w) {
+        if (HIST && (it32 % a.hist_every) == 0u) {
+            // marginal histograms: bin b = W (g_ols + e) and sigma of this iteration (shared-memory atomics);
+            // hist_every is a multiple of kFlushEvery, so this is always the end of a segment.  Unrolled over
+            // the padded components so that the loads and conversions of all coordinates overlap.
+            real bv[KP];
+            if (a.dense_w) {
 #pragma unroll
-                    for (int k = 0; k < KP; ++k)
-                        if (k < a.k)
-                            b = M::fma(static_cast<real>(a.w[r * a.k + k]), static_cast<real>(a.g_ols[k]) + e[k], b);
-                } else {
+                for (int r = 0; r < KP; ++r) {
+                    real b = real(0);
+                    if (r < a.k) {
 #pragma unroll
-                    for (int k = 0; k < KP; ++k)
-                        if (k == r) b = static_cast<real>(a.w[k]) * (static_cast<real>(a.g_ols[k]) + e[k]);
+                        for (int k = 0; k < KP; ++k)
+                            if (k < a.k)
+                                b = M::fma(static_cast<real>(a.w[r * a.k + k]), static_cast<real>(a.g_ols[k]) + e[k], b);
+                    }
+                    bv[r] = b;
                 }
-                atomicAdd(hist_s + r * kHistBins + hist_bin<real>(a.hist_lo, a.hist_inv, r, b), 1u);
+            } else {
+#pragma unroll
+                for (int r = 0; r < KP; ++r)
+                    bv[r] = r < a.k ? static_cast<real>(a.w[r]) * (static_cast<real>(a.g_ols[r]) + e[r]) : real(0);
             }
-            atomicAdd(hist_s + a.k * kHistBins + hist_bin<real>(a.hist_lo, a.hist_inv, a.k, sig), 1u);
-            next_hist += a.hist_every;
-            if (next_hist < it32) next_hist = 0xFFFFFFFFu;             // wrapped: past the last iteration
+            unsigned bin[KP];
+#pragma unroll
+            for (int r = 0; r < KP; ++r) bin[r] = r < a.k ? hist_bin<real>(a.hist_lo, a.hist_inv, r, bv[r]) : 0u;
+            const unsigned bin_s = hist_bin<real>(a.hist_lo, a.hist_inv, a.k, sig);
+#pragma unroll
+            for (int r = 0; r < KP; ++r)
+                if (r < a.k) atomicAdd(hist_s + r * kHistBins + bin[r], 1u);
+            atomicAdd(hist_s + a.k * kHistBins + bin_s, 1u);
         }
         if (static_cast<long long>(it32) - 1 == next_store) {
             // b = W (g_ols + e);  row layout [slot][component][chain] keeps lanes coalesced
@@ -389,9 +388,10 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
             next_store += a.thin;
         }
     }
-    if constexpr (HIST) hist_merge(hist_s, a.k + 1, a.hist);
-#undef BMC_D
-#undef BMC_PULL
+    if constexpr (HIST) {
+        const long long left = a.n_chains - static_cast<long long>(blockIdx.x) * blockDim.x;
+        hist_merge(hist_s, a.k + 1, a.hist, a.hist_replicas, left < blockDim.x ? static_cast<int>(left) : blockDim.x);
+    }
 }
 
 // --------------------------------------------------------------------------------------
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
 constexpr int kConjGroup = 8;
 constexpr int kConjLanes = 8;             // lanes that hold state: one per component
 
-template <typename real, int KP, int MODE, int GEN = kConjGroup>
+template <typename real, int KP, int MODE, int GEN = kConjGroup, bool HIST = false>
 __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsArgs a) {
     using M = Math<real>;
     static_assert(KP <= kConjLanes, "one lane per component");
@@ -417,13 +417,12 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
     constexpr int ROW = KP + 1;                                           // z[KP], 1 / gamma
     __shared__ real draws_s[WPB * CPW * 32 * ROW];
     extern __shared__ unsigned hist_s[];                  // [k+1][kHistBins] when histograms are on
-    if (a.hist_every) hist_zero(hist_s, a.k + 1);
+    if constexpr (HIST) hist_zero(hist_s, a.k + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane & (G - 1), grp = lane / G;
     const long long cid_raw = (static_cast<long long>(blockIdx.x) * WPB + warp) * CPW + grp;
     const bool chain_ok = cid_raw < a.n_chains;
-    const bool warp_ok = __any_sync(0xffffffffu, chain_ok);
-    if (!warp_ok && !a.hist_every) return;
+    if (!__any_sync(0xffffffffu, chain_ok)) return;
     const long long cid = chain_ok ? cid_raw : a.n_chains - 1;            // idle groups shadow a real chain
     const uint32_t chain = static_cast<uint32_t>(a.chain0 + static_cast<unsigned long long>(cid));
     real* const mine = draws_s + (static_cast<size_t>(warp) * CPW + grp) * 32 * ROW;
@@ -445,10 +444,9 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
     real s2 = run_consts<real>(a).sigma2_init;
     real sig = M::sqrt(s2);
     real* const out = static_cast<real*>(a.samples);
-    // counts fit 31 bits (checked by the host for this layout); a warp without chains only joins the barriers
-    const int total = warp_ok ? static_cast<int>(a.iterations) : 0;
+    const int total = static_cast<int>(a.iterations);                     // fits 31 bits (checked by the host)
     int next_store = a.samples ? static_cast<int>(a.store_from) : -1;
-    int next_hist = a.hist_every ? static_cast<int>(a.hist_every) - 1 : -1;
+    int next_hist = HIST ? static_cast<int>(a.hist_every) - 1 : -1;
     int slot = 0;
 
     for (int base = 0; base < total; base += 32) {
@@ -528,7 +526,7 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
                     for (int c = 0; c < KP; ++c) acc2[c] = real(0);
                 }
             }
-            if (it == next_store || it == next_hist) {
+            if (it == next_store || (HIST && it == next_hist)) {
                 // b = W (g_ols + e): lane r gathers the group's coordinates for its row of W
                 const real gam = g_ols + e;
                 real b;
@@ -542,7 +540,7 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
                 } else {
                     b = comp ? static_cast<real>(a.w[g]) * gam : real(0);
                 }
-                if (it == next_hist) {
+                if (HIST && it == next_hist) {
                     if (chain_ok && g < kConjLanes) {
                         if (comp) atomicAdd(hist_s + g * kHistBins + hist_bin<real>(a.hist_lo, a.hist_inv, g, b), 1u);
                         if (g == 0)
@@ -563,7 +561,12 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
         }
         __syncwarp();
     }
-    if (a.hist_every) hist_merge(hist_s, a.k + 1, a.hist);
+    if constexpr (HIST) {
+        // whole warps without a chain returned above: the first `warps` warps of the block are still here
+        const long long left = a.n_chains - static_cast<long long>(blockIdx.x) * WPB * CPW;
+        const int warps = left >= WPB * CPW ? WPB : static_cast<int>((left + CPW - 1) / CPW);
+        hist_merge(hist_s, a.k + 1, a.hist, a.hist_replicas, 32 * warps);
+    }
 }
 
 // --------------------------------------------------------------------------------------

@@ -287,8 +287,10 @@ class ConjugateSampler:
         if hist_every:
             base, k = self._consts.data_ptr(), self.k
             hist = torch.empty((k + 1, _lib.HIST_BINS), dtype=torch.int64, device=self.dev)
+            hws = torch.empty(int(lib.bmc_gibbs_hist_workspace_bytes(k)), dtype=torch.uint8, device=self.dev)
             hist_arg = C.byref(_lib.GibbsHist(every=hist_every, lo=base + 24 * k, inv_width=base + 8 * (4 * k + 1),
-                                              counts=hist.data_ptr()))
+                                              counts=hist.data_ptr(), workspace=hws.data_ptr(),
+                                              workspace_bytes=hws.numel()))
         _lib.check(lib.bmc_gibbs_run(code, C.byref(prob), int(seed) & (2 ** 64 - 1), int(chain_offset), n_chains,
                                      iterations, discard, thin, n_kept, D.ptr(samples), D.ptr(cstats), mode,
                                      hist_arg, D.stream_ptr(self.dev)), "bmc_gibbs_run")
@@ -372,8 +374,8 @@ def run_gibbs(y, X, iterations, prior_info, *, n_chains=1, seed=None, dtype="flo
     The moment sums (``mean``, ``cov``, ``rhat``, ``ess``) and the histograms cover ALL iterations of all chains,
     including the first ``discard`` ones -- ``discard`` / ``thin`` only select which iterates are *stored*; the
     conjugate sampler starts at the OLS variance and has no burn-in upstream either (:37-39).
-    ``hist_every`` > 0 bins the state after every hist_every-th iteration into marginal histograms
-    (``GibbsResult.hist`` / ``.quantiles``); 64 coincides with the kernels' moment flushes and is free."""
+    ``hist_every`` > 0 (a multiple of 64: the kernels bin where they flush their moment sums) bins the state
+    after every hist_every-th iteration into marginal histograms (``GibbsResult.hist`` / ``.quantiles``)."""
     seed = D.fresh_seed() if seed is None else int(seed)
     sampler = ConjugateSampler(y, X, prior_info, device)
     samples, cstats, meta = sampler.run(iterations, n_chains, seed, dtype, thin, discard, keep_samples, stats,

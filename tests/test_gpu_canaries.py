@@ -43,7 +43,7 @@ def test_sampler_buffers(dtype, n_chains):
     raw_c, stats = guarded((n_stat, n_chains), torch.float64, dev, -777.0)
     prob = cs.problem()
     _lib.check(lib.bmc_gibbs_run(code, C.byref(prob), 5, 0, n_chains, iters, 0, thin, n_kept, samples.data_ptr(),
-                                 stats.data_ptr(), _lib.STATS_FULL, D.stream_ptr(dev)))
+                                 stats.data_ptr(), _lib.STATS_FULL, None, D.stream_ptr(dev)))
     torch.cuda.synchronize()
     assert intact(raw_s, samples.numel(), -777.0) and intact(raw_c, stats.numel(), -777.0)
     assert bool(torch.isfinite(samples).all()) and bool((samples[:, k, :] > 0).all())
