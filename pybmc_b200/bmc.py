@@ -228,7 +228,10 @@ class BayesianModelCombination:
         return (rndm_m, *frames)
 
     def _check_trained(self):
-        if getattr(self, "samples", None) is None or getattr(self, "Vt_hat", None) is None:
+        # bmc.py:212-215 as written upstream.  Upstream's __init__ (bmc.py:73-77) never creates ``samples`` or
+        # ``Vt_hat``, so on a fresh object this line raises AttributeError before the ValueError can -- the
+        # de-facto behaviour, kept: neither attribute exists here either until orthogonalize() / train() ran.
+        if self.samples is None or self.Vt_hat is None:
             raise ValueError("Must call `orthogonalize()` and `train()` before predicting.")
 
     def predict(self, X, *, n_draws=DEFAULT_DRAWS, seed=None, dtype="float64", return_draws=True):

@@ -156,9 +156,12 @@ def sharded_gibbs(y, X, iterations, prior_info, n_chains_total, *, seed, dtype="
     rank, world = _world(group)
     lo, hi = chain_range(n_chains_total, rank, world)
     dev = D.device(device) if sampler is None else sampler.dev
-    all_ranks_agree(hi - lo >= 1 and (not rows_sharded or int(np.asarray(y).shape[0]) >= 1),
-                    f"sharded_gibbs: {n_chains_total} chains (or the rows of the table) do not cover all {world} ranks",
-                    group, dev)
+    # every rank can see that a share is empty from the totals alone: all of them raise, nobody enters a collective
+    if int(n_chains_total) < world:
+        raise ValueError(f"sharded_gibbs: {n_chains_total} chains do not cover all {world} ranks")
+    if rows_sharded and sampler is None:      # row counts are only known locally: agree on them first
+        all_ranks_agree(int(np.asarray(y).shape[0]) >= 1,
+                        f"sharded_gibbs: the rows of the table do not cover all {world} ranks", group, dev)
     if sampler is None:
         sampler = ConjugateSampler(y, X, prior_info, dev, reduce=sum_over_ranks(group) if rows_sharded else None)
     stats = "full" if sampler.k <= 8 else "auto"           # cross moments only while they fit in registers

@@ -181,3 +181,16 @@ def test_install_as_pybmc_makes_upstream_imports_resolve_here():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0, out.stderr
     assert out.stdout.strip() == "refused"
+
+
+def test_predict_before_train_raises_like_upstream():
+    """Upstream never initialises ``samples`` / ``Vt_hat`` (pybmc/bmc.py:73-77), so predicting on a fresh object
+    raises AttributeError at bmc.py:212 before its ValueError can; the drop-in does the same (no GPU involved)."""
+    import pandas as pd
+    import pybmc_b200 as pb
+    df = pd.DataFrame({"m1": [1.0, 2.0], "m2": [2.0, 3.0], "truth": [1.5, 2.5]})
+    bmc = pb.BayesianModelCombination(["m1", "m2"], {"p": df}, "truth")
+    with pytest.raises(AttributeError):
+        bmc.predict(df)
+    with pytest.raises(AttributeError):
+        bmc.evaluate()
