@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     GammaPair<real> gp;                                 // first Gamma proposals of iterations 2m, 2m+1
     gp.x[1] = real(0);
     gp.u[1] = real(1);
+    gp.lu[1] = real(0);
     // The iterations run in segments that end where something other than arithmetic happens (a flush
     // of the moment sums every kFlushEvery iterations, a kept draw, the end): the inner loop is pure
     // arithmetic with one 32-bit counter.
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         if (next_store >= static_cast<long long>(it32) && next_store < static_cast<long long>(seg_end))
             seg_end = static_cast<uint32_t>(next_store) + 1u;
         // one iteration; (gx, gu) = the first Gamma proposal of this iteration
-        auto iterate = [&](const uint32_t it32, const real gx, const real gu) {
+        auto iterate = [&](const uint32_t it32, const real gx, const real gu, const real glu) {
             real rss0 = rss_min, rss1 = real(0);
             if constexpr (PACK2) {
                 // two components at a time on packed fp32 instructions (same roundings as the scalar form)
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 }
             }
             const real scale = real(0.5) * (prior_scale + (rss0 + rss1));
-            const real gm = gamma_from_first<real>(gc, gx, gu, it32, chain, kTagGibbs, a.key0, a.key1);
+            const real gm = gamma_from_first<real>(gc, gx, gu, glu, it32, chain, kTagGibbs, a.key0, a.key1);
             s2 = M::div(scale, gm);
             s2 = s2 > real(1e-6) ? s2 : real(1e-6);
             sig = M::sqrt(s2);
@@ -279,24 +280,24 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         // overlap with it (9.98 -> 9.32 ms); fp64 has no registers to spare for that and is faster one by one.
         if constexpr (sizeof(real) == 4 && KP <= 16) {
             if ((it32 & 1u) != 0u) {
-                iterate(it32, gp.x[1], gp.u[1]);
+                iterate(it32, gp.x[1], gp.u[1], gp.lu[1]);
                 ++it32;
             }
             for (; it32 + 1u < seg_end; it32 += 2u) {
                 gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);
-                iterate(it32, gp.x[0], gp.u[0]);
-                iterate(it32 + 1u, gp.x[1], gp.u[1]);
+                iterate(it32, gp.x[0], gp.u[0], gp.lu[0]);
+                iterate(it32 + 1u, gp.x[1], gp.u[1], gp.lu[1]);
             }
             if (it32 < seg_end) {
                 gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);
-                iterate(it32, gp.x[0], gp.u[0]);
+                iterate(it32, gp.x[0], gp.u[0], gp.lu[0]);
                 ++it32;
             }
         } else {
             for (; it32 < seg_end; ++it32) {
                 const bool odd = (it32 & 1u) != 0u;
                 if (!odd) gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);
-                iterate(it32, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0]);
+                iterate(it32, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0], odd ? gp.lu[1] : gp.lu[0]);
             }
         }
 

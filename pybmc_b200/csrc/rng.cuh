@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "fp64_tables.cuh"
 
 namespace bmc {
 
@@ -126,6 +127,8 @@ struct Math<float> {
         asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
         return mul2(pack2(rad, rad), pack2(cs, sn));
     }
+    // log of the uniform a 32-bit word stands for
+    static __device__ __forceinline__ float log_u01(uint32_t r) { return log(u01(r)); }
     // natural log of a positive normal number: lg2.approx.ftz * ln 2 (what __logf does, minus its
     // denormal fix-up instructions)
     static __device__ __forceinline__ float log(float x) {
@@ -166,10 +169,52 @@ struct Math<double> {
     static __device__ __forceinline__ double u01(uint32_t r) {
         return (static_cast<double>(r) + 0.5) * 2.3283064365386963e-10;
     }
+    // ---- fp64 variates straight from the random WORD.  The uniform is u = x 2^-33 with x = 2r + 1 a 33-bit odd
+    // integer, so exponent, mantissa and a 7-bit table index come from integer instructions; what is left is a
+    // degree-6 series on |q| <= 2^-8 (log) and degree-7/8 series on |delta| <= 2 pi / 256 (sine, cosine), instead
+    // of libm's general-argument ::log (~40 instructions) and ::sincospi (~50).  Accuracy ~1e-16 absolute (the
+    // oracle's math.log / math.cos on the rounded angle differ from these by <= 3e-15): the 2e-9 value-by-value
+    // parity of the fp64 chains is untouched.  Tables: fp64_tables.cuh (generated, 2 x 2 KB, read through L1).
+    // log((r + 1/2) 2^-32)
+    static __device__ __forceinline__ double log_u01(uint32_t r) {
+        const unsigned long long x = 2ull * r + 1ull;
+        const int e = 63 - __clzll(static_cast<long long>(x));                       // floor(log2 x): 0 .. 32
+        const unsigned long long mant = (x << (52 - e)) & 0x000FFFFFFFFFFFFFull;     // fraction bits of m = x 2^-e
+        const int i = static_cast<int>(mant >> 45);
+        const int up = i >= 53;                                                      // centre above sqrt 2: take m / 2
+        const double m = __longlong_as_double(static_cast<long long>(
+            mant | (static_cast<unsigned long long>(1023 - up) << 52)));
+        const double2 t = __ldg(&kLogTab[i]);
+        const double q = ::fma(m, t.x, -1.0);                                        // m / c_i - 1, one rounding
+        double p = ::fma(q, -1.0 / 6.0, 0.2);
+        p = ::fma(q, p, -0.25);
+        p = ::fma(q, p, 1.0 / 3.0);
+        p = ::fma(q, p, -0.5);
+        const double k = static_cast<double>(e + up - 33);
+        return ::fma(k, 0.6931471805599453, t.y) + ::fma(q * q, p, q);               // (k ln 2 + ln c_i) + log1p(q)
+    }
+    // sine and cosine of 2 pi (r + 1/2) 2^-32
+    static __device__ __forceinline__ void sincos_u01(uint32_t r, double& sn, double& cs) {
+        const unsigned long long w = 2ull * r + 1ull;                                // angle = 2 pi w 2^-33
+        const int i = static_cast<int>(w >> 26);
+        const int d = static_cast<int>(w & 0x3FFFFFFull) - (1 << 25);                // offset from the centre of slot i
+        const double dl = static_cast<double>(d) * 0x1.921fb54442d18p-31;             // 2 pi 2^-33
+        const double d2 = dl * dl;
+        double ps = ::fma(d2, -1.0 / 5040.0, 1.0 / 120.0);
+        ps = ::fma(d2, ps, -1.0 / 6.0);
+        const double sd = ::fma(d2 * dl, ps, dl);                                    // sin(delta)
+        double pc = ::fma(d2, 1.0 / 40320.0, -1.0 / 720.0);
+        pc = ::fma(d2, pc, 1.0 / 24.0);
+        pc = ::fma(d2, pc, -0.5);
+        const double cd = ::fma(d2, pc, 1.0);                                        // cos(delta)
+        const double2 t = __ldg(&kSinCosTab[i]);                                     // (sin, cos) of the centre
+        sn = ::fma(t.x, cd, t.y * sd);
+        cs = ::fma(t.y, cd, -(t.x * sd));
+    }
     static __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, double& za, double& zb) {
-        const double rad = ::sqrt(-2.0 * ::log(u01(ra)));
+        const double rad = ::sqrt(-2.0 * log_u01(ra));
         double s, c;
-        sincospi(2.0 * u01(rb), &s, &c);
+        sincos_u01(rb, s, c);
         za = rad * c;
         zb = rad * s;
     }
@@ -257,7 +302,7 @@ constexpr uint32_t kBlockBoost = kBlockGamma + 0x8000u;
 
 template <typename real>
 struct GammaPair {
-    real x[2], u[2];
+    real x[2], u[2], lu[2];     // normal, uniform and log(uniform) of the first proposals of iterations 2m, 2m+1
 };
 
 template <typename real, typename Key>
@@ -267,19 +312,25 @@ __device__ __forceinline__ GammaPair<real> gamma_pair(uint32_t it_even, uint32_t
     Math<real>::box_muller(r.x, r.y, p.x[0], p.x[1]);
     p.u[0] = Math<real>::u01(r.z);
     p.u[1] = Math<real>::u01(r.w);
+    if constexpr (sizeof(real) == 8) {       // fp64: from the word (no general-argument log); fp32 takes lg2(u) on use
+        p.lu[0] = Math<real>::log_u01(r.z);
+        p.lu[1] = Math<real>::log_u01(r.w);
+    } else {
+        p.lu[0] = p.lu[1] = real(0);
+    }
     return p;
 }
 
 // accept / reject one proposal; on acceptance v holds (1 + c x)^3.  Squeeze and full test are both
 // evaluated (a warp nearly always has a lane that needs the full test) and combined without branches.
 template <typename real>
-__device__ __forceinline__ bool gamma_accept(const GammaConst<real>& g, real x, real u, real& v) {
+__device__ __forceinline__ bool gamma_accept(const GammaConst<real>& g, real x, real u, real log_u, real& v) {
     using M = Math<real>;
     const real t = M::fma(g.c, x, real(1));
     const real v3 = t * t * t;
     const real x2 = x * x;
     const bool squeeze = u < real(1) - real(0.0331) * x2 * x2;                 // almost always
-    const bool full = M::log(u) < real(0.5) * x2 + g.d * (real(1) - v3 + M::log(v3));   // NaN (t <= 0): false
+    const bool full = log_u < real(0.5) * x2 + g.d * (real(1) - v3 + M::log(v3));       // NaN (t <= 0): false
     const bool ok = (t > real(0)) & (squeeze | full);
     v = ok ? v3 : real(1);
     return ok;
@@ -294,17 +345,18 @@ __device__ __noinline__ void gamma_retry(const GammaConst<real>& g, uint32_t it,
         const Philox4 r = philox4x32_10(it, kBlockGamma + t, chain, tag, ks);
         real x, unused;
         Math<real>::box_muller(r.x, r.y, x, unused);
-        if (gamma_accept<real>(g, x, Math<real>::u01(r.z), v)) return;
+        if (gamma_accept<real>(g, x, Math<real>::u01(r.z), Math<real>::log_u01(r.z), v)) return;
     }
 }
 
 // finish a draw whose first proposal (x, u) is already known
 template <typename real>
-__device__ __forceinline__ real gamma_from_first(const GammaConst<real>& g, real x, real u, uint32_t it,
+__device__ __forceinline__ real gamma_from_first(const GammaConst<real>& g, real x, real u, real log_u, uint32_t it,
                                                  uint32_t chain, uint32_t tag, uint32_t k0, uint32_t k1) {
     using M = Math<real>;
     real v;
-    if (!gamma_accept<real>(g, x, u, v)) gamma_retry<real>(g, it, chain, tag, k0, k1, v);
+    if constexpr (sizeof(real) == 4) log_u = M::log(u);
+    if (!gamma_accept<real>(g, x, u, log_u, v)) gamma_retry<real>(g, it, chain, tag, k0, k1, v);
     real out = g.d * v;
     if (g.boost) out *= M::pow(M::u01(philox4x32_10(it, kBlockBoost, chain, tag, k0, k1).x), g.inv_shape);
     return out;
@@ -316,14 +368,16 @@ __device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint
                                                  uint32_t tag, const PhiloxKeys& ks, uint32_t k0, uint32_t k1) {
     const GammaPair<real> p = gamma_pair<real>(it & ~1u, chain, tag, ks);
     const int odd = static_cast<int>(it & 1u);
-    return gamma_from_first<real>(g, odd ? p.x[1] : p.x[0], odd ? p.u[1] : p.u[0], it, chain, tag, k0, k1);
+    return gamma_from_first<real>(g, odd ? p.x[1] : p.x[0], odd ? p.u[1] : p.u[0], odd ? p.lu[1] : p.lu[0], it, chain,
+                                  tag, k0, k1);
 }
 template <typename real>
 __device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
                                                  uint32_t tag, uint32_t k0, uint32_t k1) {
     const GammaPair<real> p = gamma_pair<real>(it & ~1u, chain, tag, philox_keys(k0, k1));
     const int odd = static_cast<int>(it & 1u);
-    return gamma_from_first<real>(g, odd ? p.x[1] : p.x[0], odd ? p.u[1] : p.u[0], it, chain, tag, k0, k1);
+    return gamma_from_first<real>(g, odd ? p.x[1] : p.x[0], odd ? p.u[1] : p.u[0], odd ? p.lu[1] : p.lu[0], it, chain,
+                                  tag, k0, k1);
 }
 
 }  // namespace bmc

@@ -230,3 +230,42 @@ def test_histogram_quantiles_match_reference_sampler():
             assert np.array_equal(np.bincount(idx, minlength=512), res.hist[c]), (layout, c)
     with pytest.raises(ValueError):
         pb.run_gibbs(y, X, 100, prior, n_chains=4, seed=4, hist_every=7)      # multiples of 64 only
+
+
+def test_fp64_normals_from_the_tables_match_the_oracle_to_rounding():
+    """The fp64 kernels take log and sine / cosine of the uniforms straight from the random word (integer exponent
+    and table index, short series: rng.cuh).  With d = 0 and pull = 0 the sampler's coefficient IS the standard
+    normal vector of the iteration, so the kept samples expose the device normals: they must equal
+    oracle/philox.py's math.log / math.cos evaluation to a few ulp of the intermediate quantities."""
+    import torch
+    from pybmc_b200 import _device as D
+    from pybmc_b200 import _lib
+    lib = _lib.load()
+    dev = D.device(None)
+    k, chains, iters, seed = 8, 96, 50, 4242
+    consts = torch.tensor([0.0] * k + [0.0] * k + [0.0] * k + [1.0] * k, dtype=torch.float64, device=dev)
+    base = consts.data_ptr()
+    for layout in ("thread", "group"):
+        prob = _lib.GibbsProblem(k=k, d=base, pull=base + 8 * k, g_ols=base + 16 * k, w=base + 24 * k, dense_w=0,
+                                 rss_min=10.0, n_obs=50.0, nu0=1.0, sigma20=0.02, sigma2_init=0.2,
+                                 layout=_lib.LAYOUTS[layout])
+        out = torch.empty((iters, k + 1, chains), dtype=torch.float64, device=dev)
+        _lib.check(lib.bmc_gibbs_run(_lib.F64, C.byref(prob), seed, 0, chains, iters, 0, 1, iters, out.data_ptr(), None,
+                                     _lib.STATS_NONE, None, D.stream_ptr(dev)))
+        z = out[:, :k, :].cpu().numpy()                           # [iteration, component, chain]
+        key = px.seed_key(seed)
+        worst = 0.0
+        for c in (0, 31, 95):
+            for it in range(iters):
+                want = np.array(px.normal_vector(k, it, c, px.TAG_GIBBS, key))
+                worst = max(worst, np.max(np.abs(z[it, :, c] - want)))
+        assert worst < 2e-14, (layout, worst)
+    # tails and the extreme words: u01 of 0 and of 2^32 - 1 through the same code (noise of the prediction path)
+    import pybmc_b200 as pb
+    theta = np.column_stack([np.zeros((64, 2)), np.ones(64)])      # beta = 0, sigma = 1: the draws are the noise
+    preds = np.array([[1.0, -1.0], [2.0, -2.0], [0.5, -0.5], [3.0, -3.0]])
+    vt = np.array([[0.5, -0.5], [0.25, -0.25]])
+    res = pb.predictive_summary(preds, theta, vt, seed=77, subsample=False, dtype="float64", return_draws=True)
+    key = px.seed_key(77)
+    want = np.array([[px.noise_block(sb, n, key)[j] for n in range(4)] for sb in range(16) for j in range(4)])
+    np.testing.assert_allclose(res.draws, want, rtol=0, atol=2e-14)
