@@ -23,6 +23,10 @@
 #pragma once
 #include "rng.cuh"
 
+#ifndef BMC_PHILOX_HOIST
+#define BMC_PHILOX_HOIST 0     // A/B switch (profiles/build_ab.sh): loop-invariant Philox products kept in registers (measured: 9.47 vs 9.27 ms, the nine registers cost more than the 7.5 multiplies save)
+#endif
+
 namespace bmc {
 
 struct GibbsArgs {
@@ -97,6 +101,13 @@ static __global__ void hist_reduce_kernel(const unsigned long long* replicas, in
 
 constexpr int kFlushEvery = 64;           // iterations between fp64 flushes of the moment sums
 
+// Add to a slot of the fp64 moment rows WITHOUT reading it back: a reduction (RED.E.ADD.F64) instead of
+// load - add - store.  A slot belongs to one thread, so the sum is the same either way; but `*p += v` made a
+// flush a chain of 54 dependent L2 round trips (the compiler may not move a load above the previous store:
+// LDG DADD STG x 54 in SASS, ~270 cycles each = 12 % of the kernel's stall samples as long_scoreboard), where
+// the reduction is 54 fire-and-forget instructions.
+__device__ __forceinline__ void stat_add(double* p, double v) { atomicAdd(p, v); }
+
 template <typename real, typename Args>
 __device__ __forceinline__ const RunConsts<real>& run_consts(const Args& a) {
     if constexpr (sizeof(real) == 4) return a.cf;
@@ -139,6 +150,25 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     const real sig_ref = rc.sigma_ref;
     const GammaConst<real> gc = gamma_const_of(rc, a.gamma_boost);
 
+    // Philox calls of this chain differ in counter word 0 (the iteration) only: the products of the first two
+    // rounds that do not involve it are kept in registers (rng.cuh, PhiloxFixed).  fp32, K <= 8: three call sites.
+    constexpr bool HOIST = BMC_PHILOX_HOIST && sizeof(real) == 4 && KP <= 8;
+    constexpr int NB = (KP + 3) / 4;
+    PhiloxFixed fx[HOIST ? NB + 1 : 1];
+    if constexpr (HOIST) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) fx[j] = philox_fix(static_cast<uint32_t>(j), chain, kTagGibbs, a.keys);
+        fx[NB] = philox_fix(kBlockGamma, chain, kTagGibbs, a.keys);
+    }
+    // words of block j (j = NB: the Gamma block) at iteration it
+    auto words = [&](const uint32_t it, const int j) {
+        if constexpr (HOIST) {
+            return philox4x32_10_fixed(static_cast<uint64_t>(kPhiloxM0) * it, kTagGibbs, fx[j], a.keys);
+        } else {
+            return philox4x32_10(it, j == NB ? kBlockGamma : static_cast<uint32_t>(j), chain, kTagGibbs, a.keys);
+        }
+    };
+
     // fp32: Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2) take two components at a time.
     // With all cross moments, the 45 + 9 sums are kept as register pairs (30 instructions instead of 54 for
     // K = 8): pair (i, c), c = 2i+1 .. KP, holds the products of e_2i and e_2i+1 with e_c (e_KP = sigma
@@ -161,7 +191,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     auto row_of = [&](int r, int c) { return D + r * D - r * (r - 1) / 2 + (c - r); };
     auto flush = [&](int row, real v) {
         double* p = a.chain_stats + static_cast<long long>(row) * a.n_chains + tid;
-        *p += static_cast<double>(v);
+        stat_add(p, static_cast<double>(v));
     };
 
     real s2 = rc.sigma2_init;
@@ -196,7 +226,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 const f32x2 s2b = pack2(s2, s2), sigb = pack2(sig, sig);
 #pragma unroll
                 for (int j = 0; j < KP / 4; ++j) {
-                    const Philox4 r = philox4x32_10(it32, static_cast<uint32_t>(j), chain, kTagGibbs, a.keys);
+                    const Philox4 r = words(it32, j);
                     const f32x2 zp[2] = {M::box_muller2(r.x, r.y), M::box_muller2(r.z, r.w)};
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -215,7 +245,9 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
 #pragma unroll
                 for (int j = 0; j < (KP + 3) / 4; ++j) {
                     real z[4];
-                    normals4_k<real>(it32, static_cast<uint32_t>(j), chain, kTagGibbs, a.keys, z);
+                    const Philox4 r = words(it32, j);
+                    M::box_muller(r.x, r.y, z[0], z[1]);
+                    M::box_muller(r.z, r.w, z[2], z[3]);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int k = 4 * j + q;
@@ -284,19 +316,19 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 ++it32;
             }
             for (; it32 + 1u < seg_end; it32 += 2u) {
-                gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);
+                gp = gamma_pair_of<real>(words(it32, NB));
                 iterate(it32, gp.x[0], gp.u[0], gp.lu[0]);
                 iterate(it32 + 1u, gp.x[1], gp.u[1], gp.lu[1]);
             }
             if (it32 < seg_end) {
-                gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);
+                gp = gamma_pair_of<real>(words(it32, NB));
                 iterate(it32, gp.x[0], gp.u[0], gp.lu[0]);
                 ++it32;
             }
         } else {
             for (; it32 < seg_end; ++it32) {
                 const bool odd = (it32 & 1u) != 0u;
-                if (!odd) gp = gamma_pair<real>(it32, chain, kTagGibbs, a.keys);
+                if (!odd) gp = gamma_pair_of<real>(words(it32, NB));
                 iterate(it32, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0], odd ? gp.lu[1] : gp.lu[0]);
             }
         }
@@ -501,7 +533,7 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
                     auto flush = [&](int row_out, real& v) {
                         if (chain_ok) {
                             double* q = a.chain_stats + static_cast<long long>(row_out) * a.n_chains + cid;
-                            *q += static_cast<double>(v);
+                            stat_add(q, static_cast<double>(v));
                         }
                         v = real(0);
                     };
@@ -738,7 +770,7 @@ __global__ void __launch_bounds__(128) gibbs_simplex_kernel(const SimplexArgs a)
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
                     double* p = a.chain_stats + static_cast<long long>(j) * a.n_chains + tid;
-                    *p += static_cast<double>(acc[j]);
+                    stat_add(p, static_cast<double>(acc[j]));
                     acc[j] = real(0);
                 }
             }
@@ -931,7 +963,7 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group_kernel(const SimplexA
                         auto flush = [&](int row_out, real& v) {
                             if (chain_ok) {
                                 double* p = a.chain_stats + static_cast<long long>(row_out) * a.n_chains + cid;
-                                *p += static_cast<double>(v);
+                                stat_add(p, static_cast<double>(v));
                             }
                             v = real(0);
                         };
@@ -1181,7 +1213,7 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group16_kernel(const Simple
                         auto flush = [&](int row_out, real& v) {
                             if (chain_ok) {
                                 double* p = a.chain_stats + static_cast<long long>(row_out) * a.n_chains + cid;
-                                *p += static_cast<double>(v);
+                                stat_add(p, static_cast<double>(v));
                             }
                             v = real(0);
                         };

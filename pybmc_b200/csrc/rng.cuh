@@ -12,6 +12,9 @@
 
 namespace bmc {
 
+#ifndef BMC_PHILOX_ROUNDS
+#define BMC_PHILOX_ROUNDS 10     // timing experiments only (profiles/build_ab.sh): the contract is ten rounds
+#endif
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
 constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
@@ -47,7 +50,7 @@ __device__ __forceinline__ PhiloxKeys philox_keys(uint32_t key0, uint32_t key1) 
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                  const PhiloxKeys& ks) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < BMC_PHILOX_ROUNDS; ++r) {
         const uint64_t p0 = static_cast<uint64_t>(kPhiloxM0) * c0;
         const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;
         const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ ks.k0[r];
@@ -62,6 +65,47 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                  uint32_t k0, uint32_t k1) {
     return philox4x32_10(c0, c1, c2, c3, philox_keys(k0, k1));
+}
+
+// A kernel that walks the iterations of one chain calls Philox with counter (iteration, block, chain, tag): only
+// word 0 changes.  Round 0 multiplies word 2 (the chain) and round 1 multiplies what round 0 made of it, so
+// those two products -- and every XOR that involves only them and the keys -- are loop invariants; the third,
+// M0 * iteration, is shared by all the calls of an iteration.  A call then costs 17 of its 20 multiplies.
+// (IMAD.WIDE holds the FMA pipe for four cycles on B200: the Philox multiplies are the largest item of the
+// thread-per-chain samplers, profiles/README.md.)  Same function as philox4x32_10, bit for bit.
+struct PhiloxFixed {
+    uint32_t x, y, z;
+};
+__device__ __forceinline__ PhiloxFixed philox_fix(uint32_t c1, uint32_t c2, uint32_t c3_unused, const PhiloxKeys& ks) {
+    (void)c3_unused;
+    const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;                       // round 0, second product
+    const uint32_t a0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ ks.k0[0];             // word 0 after round 0
+    const uint64_t q0 = static_cast<uint64_t>(kPhiloxM0) * a0;                       // round 1, first product
+    return PhiloxFixed{static_cast<uint32_t>(p1) ^ ks.k0[1], static_cast<uint32_t>(q0 >> 32) ^ ks.k1[1],
+                       static_cast<uint32_t>(q0)};
+}
+// m0c0 = M0 * (counter word 0); c3 = counter word 3
+__device__ __forceinline__ Philox4 philox4x32_10_fixed(uint64_t m0c0, uint32_t c3, const PhiloxFixed& f,
+                                                       const PhiloxKeys& ks) {
+    uint32_t c2 = static_cast<uint32_t>(m0c0 >> 32) ^ c3 ^ ks.k1[0];                 // state after round 0 ...
+    uint32_t c3n = static_cast<uint32_t>(m0c0);
+    const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;                       // ... round 1
+    uint32_t c0 = static_cast<uint32_t>(p1 >> 32) ^ f.x;
+    uint32_t c1 = static_cast<uint32_t>(p1);
+    c2 = f.y ^ c3n;
+    c3n = f.z;
+#pragma unroll
+    for (int r = 2; r < 10; ++r) {
+        const uint64_t p0 = static_cast<uint64_t>(kPhiloxM0) * c0;
+        const uint64_t q1 = static_cast<uint64_t>(kPhiloxM1) * c2;
+        const uint32_t n0 = static_cast<uint32_t>(q1 >> 32) ^ c1 ^ ks.k0[r];
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3n ^ ks.k1[r];
+        c1 = static_cast<uint32_t>(q1);
+        c3n = static_cast<uint32_t>(p0);
+        c0 = n0;
+        c2 = n2;
+    }
+    return Philox4{c0, c1, c2, c3n};
 }
 
 template <typename real>
@@ -175,11 +219,8 @@ struct Math<double> {
     // of libm's general-argument ::log (~40 instructions) and ::sincospi (~50).  Accuracy ~1e-16 absolute (the
     // oracle's math.log / math.cos on the rounded angle differ from these by <= 3e-15): the 2e-9 value-by-value
     // parity of the fp64 chains is untouched.  Tables: fp64_tables.cuh (generated, 2 x 2 KB, read through L1).
-    // log((r + 1/2) 2^-32)
-    static __device__ __forceinline__ double log_u01(uint32_t r) {
-        const unsigned long long x = 2ull * r + 1ull;
-        const int e = 63 - __clzll(static_cast<long long>(x));                       // floor(log2 x): 0 .. 32
-        const unsigned long long mant = (x << (52 - e)) & 0x000FFFFFFFFFFFFFull;     // fraction bits of m = x 2^-e
+    // log of m 2^k: `mant` = the 52 fraction bits of m in [1, 2)
+    static __device__ __forceinline__ double log_parts(unsigned long long mant, int k2) {
         const int i = static_cast<int>(mant >> 45);
         const int up = i >= 53;                                                      // centre above sqrt 2: take m / 2
         const double m = __longlong_as_double(static_cast<long long>(
@@ -190,8 +231,19 @@ struct Math<double> {
         p = ::fma(q, p, -0.25);
         p = ::fma(q, p, 1.0 / 3.0);
         p = ::fma(q, p, -0.5);
-        const double k = static_cast<double>(e + up - 33);
+        const double k = static_cast<double>(k2 + up);
         return ::fma(k, 0.6931471805599453, t.y) + ::fma(q * q, p, q);               // (k ln 2 + ln c_i) + log1p(q)
+    }
+    // log((r + 1/2) 2^-32)
+    static __device__ __forceinline__ double log_u01(uint32_t r) {
+        const unsigned long long x = 2ull * r + 1ull;
+        const int e = 63 - __clzll(static_cast<long long>(x));                       // floor(log2 x): 0 .. 32
+        return log_parts((x << (52 - e)) & 0x000FFFFFFFFFFFFFull, e - 33);
+    }
+    // natural log of a positive normal double, the same way (exponent and fraction straight from its bits)
+    static __device__ __forceinline__ double log(double x) {
+        const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
+        return log_parts(b & 0x000FFFFFFFFFFFFFull, static_cast<int>(b >> 52) - 1023);
     }
     // sine and cosine of 2 pi (r + 1/2) 2^-32
     static __device__ __forceinline__ void sincos_u01(uint32_t r, double& sn, double& cs) {
@@ -212,18 +264,42 @@ struct Math<double> {
         cs = ::fma(t.y, cd, -(t.x * sd));
     }
     static __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, double& za, double& zb) {
-        const double rad = ::sqrt(-2.0 * log_u01(ra));
+        const double rad = sqrt(-2.0 * log_u01(ra));
         double s, c;
         sincos_u01(rb, s, c);
         za = rad * c;
         zb = rad * s;
     }
-    static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
-    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
-    static __device__ __forceinline__ double rsqrt(double x) { return ::rsqrt(x); }
-    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
-    static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+    // ---- roots and quotients of POSITIVE NORMAL arguments, branch-free.  libm's ::sqrt / ::rsqrt / a / b test the
+    // exponent range and call a slow path; 17 such call sites and 21 reconvergence points cut an fp64 iteration
+    // into ~40 basic blocks that ptxas cannot schedule across (the fp64 sampler runs two warps per scheduler and
+    // lives on instruction-level parallelism).  Every argument here is a variance, a Gamma variate, a Cholesky
+    // pivot or -2 ln u: never zero, negative or subnormal.  MUFU seed (2^-20: it reads the upper word only) and one
+    // step of third order, error ~ 0.3 (2^-20)^3 below the rounding of the last multiply: results within ~1.5 ulp
+    // of the correctly rounded ones (the oracle's math.sqrt), against a 2e-9 parity requirement.
+    static __device__ __forceinline__ double rsqrt(double x) {
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        const double e = ::fma(-(x * y), y, 1.0);                     // 1 - x y^2
+        return ::fma(y * e, ::fma(e, 0.375, 0.5), y);                 // y (1 + e/2 + 3 e^2/8)
+    }
+    static __device__ __forceinline__ double sqrt(double x) {
+        const double y = rsqrt(x);
+        const double g = x * y;
+        return ::fma(::fma(-g, g, x), 0.5 * y, g);                    // one correction: the residual is exact in the fma
+    }
+    static __device__ __forceinline__ double rcp(double x) {
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        const double e = ::fma(-x, y, 1.0);
+        return ::fma(y, ::fma(e, e, e), y);                           // y (1 + e + e^2)
+    }
+    static __device__ __forceinline__ double div(double a, double b) {
+        const double y = rcp(b);
+        const double q = a * y;
+        return ::fma(::fma(-b, q, a), y, q);                          // residual correction
+    }
     static __device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }
     static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
 };
@@ -305,9 +381,9 @@ struct GammaPair {
     real x[2], u[2], lu[2];     // normal, uniform and log(uniform) of the first proposals of iterations 2m, 2m+1
 };
 
-template <typename real, typename Key>
-__device__ __forceinline__ GammaPair<real> gamma_pair(uint32_t it_even, uint32_t chain, uint32_t tag, const Key& ks) {
-    const Philox4 r = philox4x32_10(it_even, kBlockGamma, chain, tag, ks);
+// the pair from the words of block (it_even, kBlockGamma)
+template <typename real>
+__device__ __forceinline__ GammaPair<real> gamma_pair_of(const Philox4& r) {
     GammaPair<real> p;
     Math<real>::box_muller(r.x, r.y, p.x[0], p.x[1]);
     p.u[0] = Math<real>::u01(r.z);
@@ -319,6 +395,10 @@ __device__ __forceinline__ GammaPair<real> gamma_pair(uint32_t it_even, uint32_t
         p.lu[0] = p.lu[1] = real(0);
     }
     return p;
+}
+template <typename real, typename Key>
+__device__ __forceinline__ GammaPair<real> gamma_pair(uint32_t it_even, uint32_t chain, uint32_t tag, const Key& ks) {
+    return gamma_pair_of<real>(philox4x32_10(it_even, kBlockGamma, chain, tag, ks));
 }
 
 // accept / reject one proposal; on acceptance v holds (1 + c x)^3.  Squeeze and full test are both
