@@ -224,8 +224,8 @@ def pred_config(n_gpus):
     return {"workload": "BASELINE configs[3]: synthetic posterior prediction, 1e5 nuclei x 1e5 posterior draws x K=16, fused "
                         "mean / variance / 5 percentiles / coverage counts, no materialised S x N matrix",
             "n_points": PRED_POINTS, "n_draws": PRED_DRAWS, "components": PRED_K, "percentiles": PRED_Q,
-            "sharding": f"nuclei over {n_gpus} GPU(s); e2e: rank 0 uploads the posterior rows once, NCCL broadcast, one "
-                        "all-gather of the packed per-nucleus outputs",
+            "sharding": f"nuclei over {n_gpus} GPU(s); e2e: each rank uploads 1/N of the posterior rows, one all-gather "
+                        "over NVLink completes them everywhere, one all-gather of the packed per-nucleus outputs",
             "l2": "512 MiB buffer rewritten between timed steps"}
 
 
@@ -563,8 +563,8 @@ class PredictWorkload:
         self.last = self.prob.run(percentiles=PRED_Q, seed=SEED, as_numpy=False, workspace=self.ws)
 
     def step_e2e(self):
-        """Host arrays in (this rank's block of predictions and truth; the posterior rows -- uploaded once by rank
-        0 and broadcast), host results out: every rank ends with the full-length outputs."""
+        """Host arrays in (this rank's block of predictions and truth; the posterior rows -- 1/N uploaded per rank,
+        all-gathered), host results out: every rank ends with the full-length outputs."""
         from pybmc_b200 import parallel as par
         return par.sharded_predictive_summary(self.p_h, self.theta, self.vt, truth=self.t_h, percentiles=PRED_Q,
                                               seed=SEED, dtype="float32", device=self.b.dev,
@@ -577,12 +577,12 @@ class PredictWorkload:
         value = units / (ms * 1e-3)
         e2e_s, res = b.wall(self.step_e2e, steps, max(2, warmup))
         assert res.mean.shape[0] == PRED_POINTS
-        h2d = self.p_h.nbytes + self.t_h.nbytes + self.vt.nbytes + (self.theta.nbytes if b.rank == 0 else 0)
+        h2d = self.p_h.nbytes + self.t_h.nbytes + self.vt.nbytes + -(-self.theta.shape[0] // b.world) * self.theta.shape[1] * 8
         block = {"metric": PRED_METRIC, "value": value, "unit": PRED_UNIT, "ms_per_step": ms, "dtype": "f32",
                  "higher_is_better": True, "passes": self.last.passes, "config": pred_config(b.world),
                  "e2e": {"value": units / e2e_s, "unit": PRED_UNIT, "ms_per_step": 1e3 * e2e_s,
                          "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(PRED_POINTS * 8 * (4 + len(PRED_Q))),
-                         "collectives": "broadcast(theta 13.6 MB fp64, src 0) + all_gather(9 x nuclei fp64)" if b.world > 1
+                         "collectives": "all_gather(theta: each rank uploads 1/N of the 13.6 MB fp64 rows) + all_gather(9 x nuclei fp64)" if b.world > 1
                          else "none (1 GPU)",
                          "api": "pybmc_b200.parallel.sharded_predictive_summary from host NumPy arrays"},
                  "roofline": self.roofline(value / b.world)}
@@ -825,8 +825,8 @@ def extras_config4(out, b):
         ms_g, (mean, cov, local) = wall(lambda: par.sharded_gibbs(
             orth["y"], orth["U_hat"], iters, prior, chains_total, seed=SEED + 5, dtype="float32", thin=iters // keep,
             keep_samples=True, device=dev, rows_sharded=True))
-        # 1e4 posterior rows for the prediction: the kept draws of this rank's first chains (same rows on every
-        # rank would need an all-gather; rank 0's are broadcast by sharded_predictive_summary)
+        # 1e4 posterior rows for the prediction: rank r contributes rows [r S/N, (r+1) S/N) of ITS kept draws; the
+        # all-gather inside sharded_predictive_summary makes the table the same on every rank
         theta = np.ascontiguousarray(local.samples[:n_draws]).astype(np.float64)
         ms_p, pred = wall(lambda: par.sharded_predictive_summary(
             preds, theta, orth["Vt_hat"], truth=truth, percentiles=[2.5, 50.0, 97.5], seed=SEED + 6, dtype="float32",
@@ -842,7 +842,7 @@ def extras_config4(out, b):
         "gibbs_chain_iters_per_sec": chains_total * iters / (res["gibbs_ms"] * 1e-3),
         "predict_samples_x_points_per_sec": float(n_total) * n_draws / (res["predict_ms"] * 1e-3),
         "collectives": "all_reduce(Gram 256x256 fp64 = 512 KB); all_reduce([X|y]'[X|y] 65x65, n, RSS_min); "
-                       "all_reduce(moment sums); broadcast(theta 5.2 MB); all_gather(7 x nuclei fp64)" if world > 1
+                       "all_reduce(moment sums); all_gather(theta 5.2 MB, 1/N uploaded per rank); all_gather(7 x nuclei fp64)" if world > 1
         else "none (1 GPU)",
         "check": {"sigma_posterior_mean": float(mean[-1]), "S_hat_first_last": [float(orth["S_hat"][0]), float(orth["S_hat"][-1])],
                   "coverage_68_95_pct": cover}}

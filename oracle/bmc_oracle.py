@@ -72,12 +72,14 @@ class PhiloxDraws:
         self.tag = int(tag)
         self.factor = factor
         self.it = 0
+        self.k = None          # component count of the sampler (set by the first gaussian draw)
 
     def start(self, it):
         self.it = int(it)
 
     def gaussian(self, mean, cov):
         k = len(mean)
+        self.k = k
         z = np.array(px.normal_vector(k, self.it, self.chain, self.tag, self.key))
         f = np.linalg.cholesky(cov) if self.factor is None else self.factor(cov)
         # a wrong factor would silently sample another law: refuse it
@@ -86,7 +88,7 @@ class PhiloxDraws:
         return np.asarray(mean, dtype=float) + f @ z
 
     def gamma(self, shape, scale):
-        return scale * px.gamma_unit_scale(shape, self.it, self.chain, self.tag, self.key)
+        return scale * px.gamma_unit_scale(shape, self.it, self.chain, self.tag, self.key, self.k)
 
     def uniform(self):
         return px.metropolis_uniform(self.it, self.chain, self.tag, self.key)

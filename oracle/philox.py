@@ -18,8 +18,13 @@ Stream layout (DESIGN.md "RNG contract"):
   key      = (seed & 0xffffffff, seed >> 32)
   counter  = (c0, c1, c2, c3)
      sampler : c0 = iteration index, c1 = block, c2 = global chain id, c3 = tag
-               block j < 0x10000   -> normals 4j .. 4j+3 of the K-vector draw
-               block 0x10000       -> first Marsaglia-Tsang proposal of iterations 2m AND 2m+1 (counter
+               blocks 0, 1, ...    -> the iteration's word stream W[4 b + w].  With kp = K padded to 4, 8, 16, 32, 64
+                                      and P = kp/2 Box-Muller pairs: pair p (normals 2p, 2p+1) takes its radius from
+                                      W[p] and a 16-bit angle index from half (p & 1) of W[P + p//2] (48 bits a pair).
+                                      kp = 8 only: W[6] = uniform of the first Gamma proposal, W[7] = Gamma word
+                                      (iterations 2m, 2m+1 share one pair: radius W[7] of 2m, angle = low half of
+                                      W[7] of 2m+1; even = cosine branch, odd = sine branch)
+               block 0x10000       -> kp != 8: first Marsaglia-Tsang proposal of iterations 2m AND 2m+1 (counter
                                       c0 = 2m): even iteration = cosine branch + word 2, odd = sine branch + word 3
                block 0x10000 + t   -> attempt t >= 1 of the gamma draw of iteration c0 (after a rejection)
                block 0x18000       -> boost uniform for shapes < 1
@@ -82,23 +87,62 @@ def normals4(ctr, key):
     return za, zb, zc, zd
 
 
+def box_muller_h(ra, h):
+    """A 32-bit radius word and a 16-bit angle index -> two independent N(0,1): angle 2 pi (h + 1/2) 2^-16."""
+    rad = math.sqrt(-2.0 * math.log(u01(ra)))
+    ang = 2.0 * math.pi * (int(h) + 0.5) * 2.0 ** -16
+    return rad * math.cos(ang), rad * math.sin(ang)
+
+
+def padded_components(k):
+    """bmc_padded_components (pybmc_b200/csrc/gibbs.cu): the component count the kernels are instantiated for."""
+    for kp in (4, 8, 16, 32, 64):
+        if k <= kp:
+            return kp
+    raise ValueError("k > 64")
+
+
+def variate_layout(kp):
+    """(pairs, words, calls, gamma_inline) of an iteration's word stream -- rng.cuh VariateLayout<KP>."""
+    pairs = kp // 2
+    words = pairs + pairs // 2
+    calls = (words + 3) // 4
+    return pairs, words, calls, 4 * calls - words >= 2
+
+
+def iteration_words(kp, it, chain, tag, key):
+    calls = variate_layout(kp)[2]
+    w = []
+    for b in range(calls):
+        w.extend(philox4x32_10((it, b, chain, tag), key))
+    return w
+
+
 def normal_vector(k, it, chain, tag, key):
+    """The K standard normals of sampler iteration ``it`` (the first K of the kp the layout provides)."""
+    kp = padded_components(k)
+    pairs = variate_layout(kp)[0]
+    w = iteration_words(kp, it, chain, tag, key)
     out = []
-    for j in range((k + 3) // 4):
-        out.extend(normals4((it, j, chain, tag), key))
+    for p in range(pairs):
+        aw = w[pairs + p // 2]
+        out.extend(box_muller_h(w[p], (aw >> 16) if p & 1 else (aw & 0xFFFF)))
     return out[:k]
 
 
 BLOCK_BOOST = BLOCK_GAMMA + 0x8000
 
 
-def gamma_unit_scale(shape, it, chain, tag, key):
-    """Gamma(shape, 1) by Marsaglia & Tsang (2000).
+def gamma_unit_scale(shape, it, chain, tag, key, k=None):
+    """Gamma(shape, 1) by Marsaglia & Tsang (2000) for a sampler with ``k`` components.
 
-    The first proposals of iterations 2m and 2m+1 share Philox block (2m, BLOCK_GAMMA): the even
-    iteration uses the cosine branch of its Box-Muller pair and word 2 as the uniform, the odd one the
-    sine branch and word 3.  Attempt t >= 1 (after a rejection) has block (it, BLOCK_GAMMA + t).  For
-    shape < 1 the usual boost Gamma(a) = Gamma(a+1) * U^(1/a) takes U from block (it, BLOCK_BOOST).
+    The first proposals of iterations 2m and 2m+1 share one Box-Muller pair: the even iteration uses its
+    cosine branch, the odd one its sine branch.  When the iteration's word stream leaves two words over
+    (padded k = 8) the pair's radius is word 7 of iteration 2m, its angle index the low half of word 7 of
+    iteration 2m+1, and each iteration's uniform its own word 6.  Otherwise (``k`` None or another padded
+    size) they share Philox block (2m, BLOCK_GAMMA): words 0, 1 the pair, word 2 / word 3 the uniforms.
+    Attempt t >= 1 (after a rejection) has block (it, BLOCK_GAMMA + t).  For shape < 1 the usual boost
+    Gamma(a) = Gamma(a+1) * U^(1/a) takes U from block (it, BLOCK_BOOST).
     """
     a = float(shape)
     boost = a < 1.0
@@ -109,7 +153,14 @@ def gamma_unit_scale(shape, it, chain, tag, key):
     odd = it & 1
     v = 1.0
     for t in range(GAMMA_MAX_ATTEMPTS):
-        if t == 0:
+        if t == 0 and k is not None and variate_layout(padded_components(k))[3]:
+            kp = padded_components(k)
+            _, words, _, _ = variate_layout(kp)
+            even = iteration_words(kp, it - odd, chain, tag, key)
+            nxt = iteration_words(kp, it - odd + 1, chain, tag, key)
+            x = box_muller_h(even[words + 1], nxt[words + 1] & 0xFFFF)[odd]
+            u = u01((nxt if odd else even)[words])
+        elif t == 0:
             r = philox4x32_10((it - odd, BLOCK_GAMMA, chain, tag), key)
             x = box_muller(r[0], r[1])[odd]
             u = u01(r[2 + odd])

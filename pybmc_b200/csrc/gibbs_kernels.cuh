@@ -23,9 +23,6 @@
 #pragma once
 #include "rng.cuh"
 
-#ifndef BMC_PHILOX_HOIST
-#define BMC_PHILOX_HOIST 0     // A/B switch (profiles/build_ab.sh): loop-invariant Philox products kept in registers (measured: 9.47 vs 9.27 ms, the nine registers cost more than the 7.5 multiplies save)
-#endif
 
 namespace bmc {
 
@@ -150,24 +147,9 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     const real sig_ref = rc.sigma_ref;
     const GammaConst<real> gc = gamma_const_of(rc, a.gamma_boost);
 
-    // Philox calls of this chain differ in counter word 0 (the iteration) only: the products of the first two
-    // rounds that do not involve it are kept in registers (rng.cuh, PhiloxFixed).  fp32, K <= 8: three call sites.
-    constexpr bool HOIST = BMC_PHILOX_HOIST && sizeof(real) == 4 && KP <= 8;
-    constexpr int NB = (KP + 3) / 4;
-    PhiloxFixed fx[HOIST ? NB + 1 : 1];
-    if constexpr (HOIST) {
-#pragma unroll
-        for (int j = 0; j < NB; ++j) fx[j] = philox_fix(static_cast<uint32_t>(j), chain, kTagGibbs, a.keys);
-        fx[NB] = philox_fix(kBlockGamma, chain, kTagGibbs, a.keys);
-    }
-    // words of block j (j = NB: the Gamma block) at iteration it
-    auto words = [&](const uint32_t it, const int j) {
-        if constexpr (HOIST) {
-            return philox4x32_10_fixed(static_cast<uint64_t>(kPhiloxM0) * it, kTagGibbs, fx[j], a.keys);
-        } else {
-            return philox4x32_10(it, j == NB ? kBlockGamma : static_cast<uint32_t>(j), chain, kTagGibbs, a.keys);
-        }
-    };
+    using VL = VariateLayout<KP>;                        // word stream of an iteration (rng.cuh)
+    constexpr int NC = VL::kCalls;
+    constexpr bool GIN = VL::kGammaInline;               // K = 8: the Gamma variates ride in the angle call
 
     // fp32: Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2) take two components at a time.
     // With all cross moments, the 45 + 9 sums are kept as register pairs (30 instructions instead of 54 for
@@ -208,6 +190,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     gp.x[1] = real(0);
     gp.u[1] = real(1);
     gp.lu[1] = real(0);
+    Philox4 held{0u, 0u, 0u, 0u};
     // The iterations run in segments that end where something other than arithmetic happens (a flush
     // of the moment sums every kFlushEvery iterations, a kept draw, the end): the inner loop is pure
     // arithmetic with one 32-bit counter.
@@ -217,48 +200,39 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         if (seg_end > total || seg_end == 0u) seg_end = total;
         if (next_store >= static_cast<long long>(it32) && next_store < static_cast<long long>(seg_end))
             seg_end = static_cast<uint32_t>(next_store) + 1u;
-        // one iteration; (gx, gu) = the first Gamma proposal of this iteration
-        auto iterate = [&](const uint32_t it32, const real gx, const real gu, const real glu) {
+        // one iteration; w = its Philox calls, (gx, gu, glu) = its first Gamma proposal
+        auto iterate = [&](const uint32_t it32, const Philox4 (&w)[NC], const real gx, const real gu, const real glu) {
             real rss0 = rss_min, rss1 = real(0);
             if constexpr (PACK2) {
                 // two components at a time on packed fp32 instructions (same roundings as the scalar form)
                 f32x2 rssp = pack2(rss_min, 0.f);
                 const f32x2 s2b = pack2(s2, s2), sigb = pack2(sig, sig);
+                constexpr int P = VL::kPairs;
 #pragma unroll
-                for (int j = 0; j < KP / 4; ++j) {
-                    const Philox4 r = words(it32, j);
-                    const f32x2 zp[2] = {M::box_muller2(r.x, r.y), M::box_muller2(r.z, r.w)};
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int k = 4 * j + 2 * h;
-                        const f32x2 dp = pack2(d[k], d[k + 1]);
-                        float t0, t1;
-                        unpack2(add2(dp, s2b), t0, t1);
-                        const f32x2 sdp = mul2(pack2(M::rsqrt(t0), M::rsqrt(t1)), sigb);
-                        const f32x2 ep = mul2(sdp, fma2(pack2(pull[k], pull[k + 1]), sdp, zp[h]));
-                        rssp = fma2(mul2(dp, ep), ep, rssp);
-                        unpack2(ep, e[k], e[k + 1]);
-                    }
+                for (int p = 0; p < P; ++p) {
+                    const uint32_t ra = philox_word(w[p / 4], p % 4);
+                    const uint32_t aw = philox_word(w[(P + p / 2) / 4], (P + p / 2) % 4);
+                    const f32x2 zp = M::box_muller2_h(ra, (p & 1) ? aw >> 16 : aw & 0xFFFFu);
+                    const int k = 2 * p;
+                    const f32x2 dp = pack2(d[k], d[k + 1]);
+                    float t0, t1;
+                    unpack2(add2(dp, s2b), t0, t1);
+                    const f32x2 sdp = mul2(pack2(M::rsqrt(t0), M::rsqrt(t1)), sigb);
+                    const f32x2 ep = mul2(sdp, fma2(pack2(pull[k], pull[k + 1]), sdp, zp));
+                    rssp = fma2(mul2(dp, ep), ep, rssp);
+                    unpack2(ep, e[k], e[k + 1]);
                 }
                 unpack2(rssp, rss0, rss1);
             } else {
+                real z[KP];
+                normals_of_words<real, KP>(w, z);
 #pragma unroll
-                for (int j = 0; j < (KP + 3) / 4; ++j) {
-                    real z[4];
-                    const Philox4 r = words(it32, j);
-                    M::box_muller(r.x, r.y, z[0], z[1]);
-                    M::box_muller(r.z, r.w, z[2], z[3]);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int k = 4 * j + q;
-                        if (k < KP) {
-                            // 1/sqrt(p_k) = sigma / sqrt(d_k + s2): one MUFU on the s2 -> e -> RSS -> s2 dependency
-                            const real sd = sig * M::rsqrt(d[k] + s2);
-                            e[k] = sd * M::fma(pull[k], sd, z[q]);      // pull/p + z/sqrt(p)
-                            if (k & 1) rss1 = M::fma(d[k] * e[k], e[k], rss1);
-                            else rss0 = M::fma(d[k] * e[k], e[k], rss0);
-                        }
-                    }
+                for (int k = 0; k < KP; ++k) {
+                    // 1/sqrt(p_k) = sigma / sqrt(d_k + s2): one MUFU on the s2 -> e -> RSS -> s2 dependency
+                    const real sd = sig * M::rsqrt(d[k] + s2);
+                    e[k] = sd * M::fma(pull[k], sd, z[k]);      // pull/p + z/sqrt(p)
+                    if (k & 1) rss1 = M::fma(d[k] * e[k], e[k], rss1);
+                    else rss0 = M::fma(d[k] * e[k], e[k], rss0);
                 }
             }
             const real scale = real(0.5) * (prior_scale + (rss0 + rss1));
@@ -307,29 +281,54 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 }
             }
         };
-        // iterations 2m and 2m+1 share one Gamma proposal block.  fp32 walks them in pairs where the segment
+        // iterations 2m and 2m+1 share one Gamma proposal pair.  fp32 walks them in pairs where the segment
         // allows: the Philox rounds of 2m+1 then sit in the same basic block as the MUFU work of 2m and
         // overlap with it (9.98 -> 9.32 ms); fp64 has no registers to spare for that and is faster one by one.
+        // `held`: with the inline layout, the angle call of iteration 2m+1 (needed at 2m for the shared pair).
+        auto pair_of = [&](const uint32_t it_even, const Philox4& last_even, const Philox4& last_odd) {
+            if constexpr (GIN) return gamma_pair_inline<real>(last_even, last_odd);
+            else return gamma_pair<real>(it_even, chain, kTagGibbs, a.keys);
+        };
         if constexpr (sizeof(real) == 4 && KP <= 16) {
             if ((it32 & 1u) != 0u) {
-                iterate(it32, gp.x[1], gp.u[1], gp.lu[1]);
+                Philox4 w[NC];
+                iteration_words<KP>(it32, chain, kTagGibbs, a.keys, w);
+                iterate(it32, w, gp.x[1], gp.u[1], gp.lu[1]);
                 ++it32;
             }
             for (; it32 + 1u < seg_end; it32 += 2u) {
-                gp = gamma_pair_of<real>(words(it32, NB));
-                iterate(it32, gp.x[0], gp.u[0], gp.lu[0]);
-                iterate(it32 + 1u, gp.x[1], gp.u[1], gp.lu[1]);
+                Philox4 wa[NC], wb[NC];
+                iteration_words<KP>(it32, chain, kTagGibbs, a.keys, wa);
+                iteration_words<KP>(it32 + 1u, chain, kTagGibbs, a.keys, wb);
+                gp = pair_of(it32, wa[NC - 1], wb[NC - 1]);
+                iterate(it32, wa, gp.x[0], gp.u[0], gp.lu[0]);
+                iterate(it32 + 1u, wb, gp.x[1], gp.u[1], gp.lu[1]);
             }
             if (it32 < seg_end) {
-                gp = gamma_pair_of<real>(words(it32, NB));
-                iterate(it32, gp.x[0], gp.u[0], gp.lu[0]);
+                Philox4 w[NC];
+                iteration_words<KP>(it32, chain, kTagGibbs, a.keys, w);
+                if constexpr (GIN) held = philox4x32_10(it32 + 1u, static_cast<uint32_t>(NC - 1), chain, kTagGibbs, a.keys);
+                gp = pair_of(it32, w[NC - 1], held);
+                iterate(it32, w, gp.x[0], gp.u[0], gp.lu[0]);
                 ++it32;
             }
         } else {
             for (; it32 < seg_end; ++it32) {
                 const bool odd = (it32 & 1u) != 0u;
-                if (!odd) gp = gamma_pair_of<real>(words(it32, NB));
-                iterate(it32, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0], odd ? gp.lu[1] : gp.lu[0]);
+                Philox4 w[NC];
+#pragma unroll
+                for (int b = 0; b < NC - (GIN ? 1 : 0); ++b)
+                    w[b] = philox4x32_10(it32, static_cast<uint32_t>(b), chain, kTagGibbs, a.keys);
+                if constexpr (GIN) {
+                    if (odd) {
+                        w[NC - 1] = held;
+                    } else {
+                        w[NC - 1] = philox4x32_10(it32, static_cast<uint32_t>(NC - 1), chain, kTagGibbs, a.keys);
+                        held = philox4x32_10(it32 + 1u, static_cast<uint32_t>(NC - 1), chain, kTagGibbs, a.keys);
+                    }
+                }
+                if (!odd) gp = pair_of(it32, w[NC - 1], held);
+                iterate(it32, w, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0], odd ? gp.lu[1] : gp.lu[0]);
             }
         }
 
@@ -489,16 +488,14 @@ __global__ void __launch_bounds__(128) gibbs_conjugate_group_kernel(const GibbsA
             const int j = g + G * t;
             const uint32_t it32 = static_cast<uint32_t>(base + j);
             real* row = mine + j * ROW;
+            Philox4 w[VariateLayout<KP>::kCalls];
+            iteration_words<KP>(it32, chain, kTagGibbs, a.keys, w);
+            real z[KP];
+            normals_of_words<real, KP>(w, z);
 #pragma unroll
-            for (int b = 0; b < (KP + 3) / 4; ++b) {
-                real z[4];
-                normals4_k<real>(it32, static_cast<uint32_t>(b), chain, kTagGibbs, a.keys, z);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (4 * b + q < KP) row[4 * b + q] = z[q];
-            }
+            for (int q = 0; q < KP; ++q) row[q] = z[q];
             // the reciprocal is taken here, in the parallel phase (a full division in fp64)
-            row[KP] = M::rcp(gamma_unit_scale<real>(gc, it32, chain, kTagGibbs, a.keys, a.key0, a.key1));
+            row[KP] = M::rcp(gamma_unit_scale_w<real, KP>(gc, w, it32, chain, kTagGibbs, a.keys, a.key0, a.key1));
         }
         __syncwarp();
         // ---- phase 2: the state updates, in order (:41-52)
@@ -688,13 +685,13 @@ __global__ void __launch_bounds__(128) gibbs_simplex_kernel(const SimplexArgs a)
     for (long long it = 0; it < total; ++it) {
         const uint32_t it32 = static_cast<uint32_t>(it);
         real delta[KP];
+        Philox4 w[VariateLayout<KP>::kCalls];
+        iteration_words<KP>(it32, chain, kTagSimplex, a.keys, w);
+        {
+            real z[KP];
+            normals_of_words<real, KP>(w, z);
 #pragma unroll
-        for (int j = 0; j < (KP + 3) / 4; ++j) {
-            real z[4];
-            normals4_k<real>(it32, static_cast<uint32_t>(j), chain, kTagSimplex, a.keys, z);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (4 * j + q < KP) delta[4 * j + q] = step[4 * j + q] * z[q];           // :98 / :121
+            for (int q = 0; q < KP; ++q) delta[q] = step[q] * z[q];                       // :98 / :121
         }
         // weights of the proposal, w = b' Vt_hat + 1/M  (:99); only their minimum matters (:102)
         real prop[KP];
@@ -739,7 +736,7 @@ __global__ void __launch_bounds__(128) gibbs_simplex_kernel(const SimplexArgs a)
             n_acc += it >= a.burn ? 1 : 0;
         }
         const real scale = real(0.5) * (prior_scale + rss);                              // :116 / :139
-        const real gm = gamma_unit_scale<real>(gc, it32, chain, kTagSimplex, a.keys, a.key0, a.key1);
+        const real gm = gamma_unit_scale_w<real, KP>(gc, w, it32, chain, kTagSimplex, a.keys, a.key0, a.key1);
         s2 = M::div(scale, gm);                                                          // no floor (:117)
         if (it < a.burn) continue;
         const real sig = M::sqrt(s2);
@@ -922,16 +919,16 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group_kernel(const SimplexA
             const int j = g + G * t;
             const uint32_t it32 = static_cast<uint32_t>(base + j);
             real* row = mine + j * ROW;
+            Philox4 w[VariateLayout<KP>::kCalls];
+            iteration_words<KP>(it32, chain, kTagSimplex, a.keys, w);
+            {
+                real z[KP];
+                normals_of_words<real, KP>(w, z);
 #pragma unroll
-            for (int b = 0; b < (KP + 3) / 4; ++b) {
-                real z[4];
-                normals4_k<real>(it32, static_cast<uint32_t>(b), chain, kTagSimplex, a.keys, z);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (4 * b + q < KP) row[4 * b + q] = z[q];
+                for (int q = 0; q < KP; ++q) row[q] = z[q];
             }
             row[KP] = M::u01(philox4x32_10(it32, kBlockUniform, chain, kTagSimplex, a.keys).x);
-            row[KP + 1] = gamma_unit_scale<real>(gc, it32, chain, kTagSimplex, a.keys, a.key0, a.key1);
+            row[KP + 1] = gamma_unit_scale_w<real, KP>(gc, w, it32, chain, kTagSimplex, a.keys, a.key0, a.key1);
         }
         __syncwarp();
         // ---- phase 2: the state updates, in order
@@ -1154,13 +1151,13 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group16_kernel(const Simple
             const uint32_t it32 = static_cast<uint32_t>(base + j);
             real* row = mine + j * ROW;
             real delta[KP];
+            Philox4 w[VariateLayout<KP>::kCalls];
+            iteration_words<KP>(it32, chain, kTagSimplex, a.keys, w);
+            {
+                real z[KP];
+                normals_of_words<real, KP>(w, z);
 #pragma unroll
-            for (int b = 0; b < (KP + 3) / 4; ++b) {
-                real z[4];
-                normals4_k<real>(it32, static_cast<uint32_t>(b), chain, kTagSimplex, a.keys, z);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (4 * b + q < KP) delta[4 * b + q] = step[4 * b + q] * z[q];            // :98 / :121
+                for (int q = 0; q < KP; ++q) delta[q] = step[q] * z[q];                       // :98 / :121
             }
             real dgd = real(0);
 #pragma unroll
@@ -1181,7 +1178,7 @@ __global__ void __launch_bounds__(128) gibbs_simplex_group16_kernel(const Simple
             }
             row[R::kScal] = dgd;
             row[R::kScal + 1] = M::u01(philox4x32_10(it32, kBlockUniform, chain, kTagSimplex, a.keys).x);
-            row[R::kScal + 2] = gamma_unit_scale<real>(gc, it32, chain, kTagSimplex, a.keys, a.key0, a.key1);
+            row[R::kScal + 2] = gamma_unit_scale_w<real, KP>(gc, w, it32, chain, kTagSimplex, a.keys, a.key0, a.key1);
         }
         __syncwarp();
         if (base > 0) rebuild(false);

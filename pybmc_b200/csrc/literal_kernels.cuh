@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) gibbs_literal_kernel(const LiteralArgs a)
     if (wid >= a.n_chains) return;
     const uint32_t chain = static_cast<uint32_t>(a.chain0 + static_cast<unsigned long long>(wid));
     const GammaConst<real> gc = make_gamma_const<real>(a.shape);
+    const PhiloxKeys ks = philox_keys(a.key0, a.key1);
     const real prior_scale = static_cast<real>(a.prior_scale);
     real s2 = static_cast<real>(a.sigma2_init);
     real* const out = static_cast<real*>(a.samples);
@@ -121,14 +122,9 @@ __global__ void __launch_bounds__(256) gibbs_literal_kernel(const LiteralArgs a)
             }
         }
         real z[KP];
-#pragma unroll
-        for (int j = 0; j < (KP + 3) / 4; ++j) {
-            real zz[4];
-            normals4<real>(it32, static_cast<uint32_t>(j), chain, kTagGibbs, a.key0, a.key1, zz);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (4 * j + q < KP) z[4 * j + q] = zz[q];
-        }
+        Philox4 w[VariateLayout<KP>::kCalls];
+        iteration_words<KP>(it32, chain, kTagGibbs, ks, w);
+        normals_of_words<real, KP>(w, z);
         // forward: t = L^-1 rhs + z ; backward: b = L^-T t
         real b[KP];
 #pragma unroll
@@ -159,7 +155,7 @@ __global__ void __launch_bounds__(256) gibbs_literal_kernel(const LiteralArgs a)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) rss += __shfl_xor_sync(0xffffffffu, rss, o);
         const real scale = real(0.5) * (prior_scale + rss);
-        const real gm = gamma_unit_scale<real>(gc, it32, chain, kTagGibbs, a.key0, a.key1);
+        const real gm = gamma_unit_scale_w<real, KP>(gc, w, it32, chain, kTagGibbs, ks, a.key0, a.key1);
         s2 = M::div(scale, gm);
         s2 = s2 > real(1e-6) ? s2 : real(1e-6);
         if (out && lane <= a.k) {

@@ -67,46 +67,9 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return philox4x32_10(c0, c1, c2, c3, philox_keys(k0, k1));
 }
 
-// A kernel that walks the iterations of one chain calls Philox with counter (iteration, block, chain, tag): only
-// word 0 changes.  Round 0 multiplies word 2 (the chain) and round 1 multiplies what round 0 made of it, so
-// those two products -- and every XOR that involves only them and the keys -- are loop invariants; the third,
-// M0 * iteration, is shared by all the calls of an iteration.  A call then costs 17 of its 20 multiplies.
-// (IMAD.WIDE holds the FMA pipe for four cycles on B200: the Philox multiplies are the largest item of the
-// thread-per-chain samplers, profiles/README.md.)  Same function as philox4x32_10, bit for bit.
-struct PhiloxFixed {
-    uint32_t x, y, z;
-};
-__device__ __forceinline__ PhiloxFixed philox_fix(uint32_t c1, uint32_t c2, uint32_t c3_unused, const PhiloxKeys& ks) {
-    (void)c3_unused;
-    const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;                       // round 0, second product
-    const uint32_t a0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ ks.k0[0];             // word 0 after round 0
-    const uint64_t q0 = static_cast<uint64_t>(kPhiloxM0) * a0;                       // round 1, first product
-    return PhiloxFixed{static_cast<uint32_t>(p1) ^ ks.k0[1], static_cast<uint32_t>(q0 >> 32) ^ ks.k1[1],
-                       static_cast<uint32_t>(q0)};
-}
-// m0c0 = M0 * (counter word 0); c3 = counter word 3
-__device__ __forceinline__ Philox4 philox4x32_10_fixed(uint64_t m0c0, uint32_t c3, const PhiloxFixed& f,
-                                                       const PhiloxKeys& ks) {
-    uint32_t c2 = static_cast<uint32_t>(m0c0 >> 32) ^ c3 ^ ks.k1[0];                 // state after round 0 ...
-    uint32_t c3n = static_cast<uint32_t>(m0c0);
-    const uint64_t p1 = static_cast<uint64_t>(kPhiloxM1) * c2;                       // ... round 1
-    uint32_t c0 = static_cast<uint32_t>(p1 >> 32) ^ f.x;
-    uint32_t c1 = static_cast<uint32_t>(p1);
-    c2 = f.y ^ c3n;
-    c3n = f.z;
-#pragma unroll
-    for (int r = 2; r < 10; ++r) {
-        const uint64_t p0 = static_cast<uint64_t>(kPhiloxM0) * c0;
-        const uint64_t q1 = static_cast<uint64_t>(kPhiloxM1) * c2;
-        const uint32_t n0 = static_cast<uint32_t>(q1 >> 32) ^ c1 ^ ks.k0[r];
-        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3n ^ ks.k1[r];
-        c1 = static_cast<uint32_t>(q1);
-        c3n = static_cast<uint32_t>(p0);
-        c0 = n0;
-        c2 = n2;
-    }
-    return Philox4{c0, c1, c2, c3n};
-}
+// (Keeping the loop-invariant products of the first two rounds in registers -- only counter word 0, the iteration,
+//  changes inside a chain's loop -- was measured in round 2: 17 instead of 20 multiplies per call, but 9.47 against
+//  9.27 ms: the nine registers cost more than the multiplies save.  profiles/r2_notes.md)
 
 template <typename real>
 struct Math;
@@ -167,6 +130,32 @@ struct Math<float> {
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(ua));
         unpack2(mul2(pack2(l2, ub), pack2(-1.3862943611198906f, 6.283185307179586f)), arg, ang);
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(arg));
+        asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+        asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+        return mul2(pack2(rad, rad), pack2(cs, sn));
+    }
+    // ---- sampler normals: radius from a 32-bit word, angle from a 16-bit half word, 2 pi (h + 1/2) 2^-16 -------
+    // (A Box-Muller pair with N equally spaced angles has exactly normal marginals up to angular harmonics of
+    //  order N, ~ (r/2)^N / N!: nothing at N = 65,536.  48 bits per pair instead of 64 is a quarter fewer Philox
+    //  calls, the largest item of the thread-per-chain sampler.)
+    static __device__ __forceinline__ void box_muller_h(uint32_t ra, uint32_t h, float& za, float& zb) {
+        float l2, rad, sn, cs;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u01(ra)));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(l2 * -1.3862943611198906f));
+        const float ang = fmaf(__uint2float_rn(h), 9.587379924285257e-05f, 4.7936899621426287e-05f);
+        asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+        asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+        za = rad * cs;
+        zb = rad * sn;
+    }
+    // the same pair, bit for bit, with the conversions packed: {za, zb}
+    static __device__ __forceinline__ f32x2 box_muller2_h(uint32_t ra, uint32_t h) {
+        float ua, ang, l2, rad, sn, cs;
+        unpack2(fma2(pack2(__uint2float_rn(ra), __uint2float_rn(h)),
+                     pack2(2.3283064365386963e-10f, 9.587379924285257e-05f),
+                     pack2(1.1641532182693481e-10f, 4.7936899621426287e-05f)), ua, ang);
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(ua));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(l2 * -1.3862943611198906f));
         asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
         asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
         return mul2(pack2(rad, rad), pack2(cs, sn));
@@ -245,12 +234,13 @@ struct Math<double> {
         const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
         return log_parts(b & 0x000FFFFFFFFFFFFFull, static_cast<int>(b >> 52) - 1023);
     }
-    // sine and cosine of 2 pi (r + 1/2) 2^-32
-    static __device__ __forceinline__ void sincos_u01(uint32_t r, double& sn, double& cs) {
-        const unsigned long long w = 2ull * r + 1ull;                                // angle = 2 pi w 2^-33
-        const int i = static_cast<int>(w >> 26);
-        const int d = static_cast<int>(w & 0x3FFFFFFull) - (1 << 25);                // offset from the centre of slot i
-        const double dl = static_cast<double>(d) * 0x1.921fb54442d18p-31;             // 2 pi 2^-33
+    // sine and cosine of 2 pi (r + 1/2) 2^-BITS for a BITS-bit integer r (32: a whole word, 16: half a word)
+    template <int BITS>
+    static __device__ __forceinline__ void sincos_index(uint32_t r, double& sn, double& cs) {
+        const unsigned long long w = 2ull * r + 1ull;                                // angle = 2 pi w 2^-(BITS+1)
+        const int i = static_cast<int>(w >> (BITS - 6));
+        const int d = static_cast<int>(w & ((1ull << (BITS - 6)) - 1ull)) - (1 << (BITS - 7));   // offset from the centre of slot i
+        const double dl = static_cast<double>(d) * (BITS == 32 ? 0x1.921fb54442d18p-31 : 0x1.921fb54442d18p-15);   // 2 pi 2^-(BITS+1)
         const double d2 = dl * dl;
         double ps = ::fma(d2, -1.0 / 5040.0, 1.0 / 120.0);
         ps = ::fma(d2, ps, -1.0 / 6.0);
@@ -263,10 +253,19 @@ struct Math<double> {
         sn = ::fma(t.x, cd, t.y * sd);
         cs = ::fma(t.y, cd, -(t.x * sd));
     }
+    static __device__ __forceinline__ void sincos_u01(uint32_t r, double& sn, double& cs) { sincos_index<32>(r, sn, cs); }
     static __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, double& za, double& zb) {
         const double rad = sqrt(-2.0 * log_u01(ra));
         double s, c;
         sincos_u01(rb, s, c);
+        za = rad * c;
+        zb = rad * s;
+    }
+    // sampler normals: radius from a word, angle 2 pi (h + 1/2) 2^-16 from half a word (see Math<float>)
+    static __device__ __forceinline__ void box_muller_h(uint32_t ra, uint32_t h, double& za, double& zb) {
+        const double rad = sqrt(-2.0 * log_u01(ra));
+        double s, c;
+        sincos_index<16>(h, s, c);
         za = rad * c;
         zb = rad * s;
     }
@@ -367,6 +366,50 @@ __device__ __forceinline__ GammaConst<T> gamma_const_of(const RunConsts<T>& c, i
     return g;
 }
 
+// ---- the variates of one sampler iteration (tags 1 and 2) ------------------------------------
+// With KP the padded component count (4, 8, 16, 32, 64) and P = KP/2 Box-Muller pairs, the iteration reads the
+// word stream W[4 b + w] = word w of Philox(iteration, block b, chain, tag), b = 0, 1, ...:
+//     pair p  (normals 2p, 2p+1):  radius from W[p], angle from half (p & 1) of W[P + p/2]      [48 bits a pair]
+//     KP = 8 only (the stream ends two words short of a call):  W[6] = uniform of the iteration's first Gamma
+//         proposal, W[7] = its Gamma word -- iterations 2m and 2m+1 share ONE Box-Muller pair, radius from W[7]
+//         of 2m, angle from the low half of W[7] of 2m+1; 2m takes the cosine branch, 2m+1 the sine branch.
+//     otherwise the Gamma block (2m, kBlockGamma) as described below.
+// Calls per iteration: 1 (KP = 4), 2 (8, Gamma included), 3, 6, 12 (+ 1/2 for the Gamma block).
+template <int KP>
+struct VariateLayout {
+    static constexpr int kPairs = KP / 2;
+    static constexpr int kWords = kPairs + kPairs / 2;
+    static constexpr int kCalls = (kWords + 3) / 4;
+    static constexpr bool kGammaInline = 4 * kCalls - kWords >= 2;       // KP == 8
+    static constexpr int kUniformWord = kWords, kGammaWord = kWords + 1;
+};
+__device__ __forceinline__ uint32_t philox_word(const Philox4& r, int w) {
+    return w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w;
+}
+template <int KP, typename Key>
+__device__ __forceinline__ void iteration_words(uint32_t it, uint32_t chain, uint32_t tag, const Key& ks,
+                                                Philox4 (&w)[VariateLayout<KP>::kCalls]) {
+#pragma unroll
+    for (int b = 0; b < VariateLayout<KP>::kCalls; ++b) w[b] = philox4x32_10(it, static_cast<uint32_t>(b), chain, tag, ks);
+}
+template <typename real, int KP>
+__device__ __forceinline__ void normals_of_words(const Philox4 (&w)[VariateLayout<KP>::kCalls], real (&z)[KP]) {
+    constexpr int P = VariateLayout<KP>::kPairs;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const uint32_t ra = philox_word(w[p / 4], p % 4);
+        const uint32_t aw = philox_word(w[(P + p / 2) / 4], (P + p / 2) % 4);
+        Math<real>::box_muller_h(ra, (p & 1) ? aw >> 16 : aw & 0xFFFFu, z[2 * p], z[2 * p + 1]);
+    }
+}
+template <typename real, int KP, typename Key>
+__device__ __forceinline__ void iteration_normals(uint32_t it, uint32_t chain, uint32_t tag, const Key& ks,
+                                                  real (&z)[KP]) {
+    Philox4 w[VariateLayout<KP>::kCalls];
+    iteration_words<KP>(it, chain, tag, ks, w);
+    normals_of_words<real, KP>(w, z);
+}
+
 // ---- Gamma(shape, 1) by Marsaglia & Tsang (2000) -------------------------------------------------
 // Variates used: a standard normal x and a uniform u per attempt.  The FIRST attempts of iterations
 // 2m and 2m+1 share one Philox block, (2m, kBlockGamma): the even iteration takes the cosine branch of
@@ -442,20 +485,59 @@ __device__ __forceinline__ real gamma_from_first(const GammaConst<real>& g, real
     return out;
 }
 
-// stand-alone draw for iteration `it` (kernels that do not walk the iterations in order)
+// KP = 8: the pair from the last words of the angle calls of iterations 2m (`even`) and 2m+1 (`odd`)
 template <typename real>
+__device__ __forceinline__ GammaPair<real> gamma_pair_inline(const Philox4& even, const Philox4& odd) {
+    GammaPair<real> p;
+    Math<real>::box_muller_h(even.w, odd.w & 0xFFFFu, p.x[0], p.x[1]);
+    p.u[0] = Math<real>::u01(even.z);
+    p.u[1] = Math<real>::u01(odd.z);
+    if constexpr (sizeof(real) == 8) {
+        p.lu[0] = Math<real>::log_u01(even.z);
+        p.lu[1] = Math<real>::log_u01(odd.z);
+    } else {
+        p.lu[0] = p.lu[1] = real(0);
+    }
+    return p;
+}
+
+// stand-alone draw for iteration `it` of a sampler with KP padded components (kernels that do not walk the
+// iterations in order)
+template <typename real, int KP>
 __device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
                                                  uint32_t tag, const PhiloxKeys& ks, uint32_t k0, uint32_t k1) {
-    const GammaPair<real> p = gamma_pair<real>(it & ~1u, chain, tag, ks);
+    GammaPair<real> p;
+    if constexpr (VariateLayout<KP>::kGammaInline) {
+        constexpr uint32_t blk = VariateLayout<KP>::kCalls - 1;
+        p = gamma_pair_inline<real>(philox4x32_10(it & ~1u, blk, chain, tag, ks), philox4x32_10(it | 1u, blk, chain, tag, ks));
+    } else {
+        p = gamma_pair<real>(it & ~1u, chain, tag, ks);
+    }
     const int odd = static_cast<int>(it & 1u);
     return gamma_from_first<real>(g, odd ? p.x[1] : p.x[0], odd ? p.u[1] : p.u[0], odd ? p.lu[1] : p.lu[0], it, chain,
                                   tag, k0, k1);
 }
-template <typename real>
+template <typename real, int KP>
 __device__ __forceinline__ real gamma_unit_scale(const GammaConst<real>& g, uint32_t it, uint32_t chain,
                                                  uint32_t tag, uint32_t k0, uint32_t k1) {
-    const GammaPair<real> p = gamma_pair<real>(it & ~1u, chain, tag, philox_keys(k0, k1));
-    const int odd = static_cast<int>(it & 1u);
+    return gamma_unit_scale<real, KP>(g, it, chain, tag, philox_keys(k0, k1), k0, k1);
+}
+// the same for a caller that already holds the iteration's own calls `w` (iteration_words): with the inline
+// layout only the partner iteration's angle call is still to be made
+template <typename real, int KP, typename Key>
+__device__ __forceinline__ real gamma_unit_scale_w(const GammaConst<real>& g,
+                                                   const Philox4 (&w)[VariateLayout<KP>::kCalls], uint32_t it,
+                                                   uint32_t chain, uint32_t tag, const Key& ks, uint32_t k0,
+                                                   uint32_t k1) {
+    GammaPair<real> p;
+    const bool odd = (it & 1u) != 0u;
+    if constexpr (VariateLayout<KP>::kGammaInline) {
+        constexpr int blk = VariateLayout<KP>::kCalls - 1;
+        const Philox4 other = philox4x32_10(it ^ 1u, static_cast<uint32_t>(blk), chain, tag, ks);
+        p = gamma_pair_inline<real>(odd ? other : w[blk], odd ? w[blk] : other);
+    } else {
+        p = gamma_pair<real>(it & ~1u, chain, tag, ks);
+    }
     return gamma_from_first<real>(g, odd ? p.x[1] : p.x[0], odd ? p.u[1] : p.u[0], odd ? p.lu[1] : p.lu[0], it, chain,
                                   tag, k0, k1);
 }

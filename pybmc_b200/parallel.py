@@ -188,21 +188,37 @@ def sharded_gibbs(y, X, iterations, prior_info, n_chains_total, *, seed, dtype="
     return base + jac @ mean_e, jac @ cov_e @ jac.T, local
 
 
-def broadcast_draws(theta, k, *, src=0, group=None, device=None):
-    """The posterior rows used for prediction, resident on every rank's GPU after ONE host upload:
-    rank ``src`` copies ``theta`` ([S, K+1] host array) to its device, the others receive it with a
-    broadcast over NVLink (13.6 MB at S = 1e5, K = 16) instead of each uploading its own copy over PCIe
-    (SURVEY.md section 8e).  ``theta`` is only read on ``src`` apart from its shape."""
+def broadcast_draws(theta, k, *, src=0, group=None, device=None, split_upload=True):
+    """The posterior rows used for prediction, resident on every rank's GPU after ONE trip of each row over PCIe
+    (SURVEY.md section 8e asks for one broadcast of ``samples`` over NVLink instead of N host uploads).
+
+    ``split_upload=True`` (``theta`` -- [S, K+1] host array -- is identical on all ranks, as
+    ``sharded_predictive_summary`` requires): rank r uploads rows [r S/N, (r+1) S/N) and one all-gather over
+    NVLink completes the table everywhere -- the staging and the PCIe copies of the N slices run side by side
+    (13.6 MB at S = 1e5, K = 16: 1.7 MB per rank at N = 8 instead of all of it on rank ``src``).
+    ``split_upload=False``: only rank ``src`` holds the values; it uploads them all and broadcasts."""
     from . import _device as D
     rank, world = _world(group)
     dev = D.device(device)
+    s_rows = int(np.shape(theta)[0])
     with D.on(dev):
-        if world == 1 or rank == src:
+        if world == 1:
+            return D.to_device(np.asarray(theta, dtype=np.float64), dev)
+        if split_upload:
+            per = -(-s_rows // world)
+            full = torch.empty((world * per, k + 1), dtype=torch.float64, device=dev)
+            lo, hi = min(rank * per, s_rows), min((rank + 1) * per, s_rows)
+            if hi > lo:
+                full[lo:hi].copy_(D.to_device(np.asarray(theta[lo:hi], dtype=np.float64), dev))
+            if hi - lo < per:
+                full[hi:(rank + 1) * per].zero_()
+            dist.all_gather_into_tensor(full, full[rank * per:(rank + 1) * per].clone(), group=group)
+            return full[:s_rows]
+        if rank == src:
             th = D.to_device(np.asarray(theta, dtype=np.float64), dev)
         else:
-            th = torch.empty((int(np.shape(theta)[0]), k + 1), dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.broadcast(th, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+            th = torch.empty((s_rows, k + 1), dtype=torch.float64, device=dev)
+        dist.broadcast(th, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
     return th
 
 
@@ -210,7 +226,8 @@ def sharded_predictive_summary(preds, theta, Vt_hat, *, truth=None, percentiles=
                                dtype="float32", group=None, device=None, gather=True, n_points_total=None):
     """Fused prediction with the nuclei split over ranks.  ``preds`` / ``truth`` are the FULL tables (every
     rank slices its own 4-aligned block of nuclei); ``theta`` are the posterior rows to use (already
-    selected), identical on all ranks -- only rank 0 uploads them, the others get them by ``broadcast_draws``.
+    selected), identical on all ranks -- each rank uploads 1/N of the rows and ``broadcast_draws`` completes the table
+    with one all-gather over NVLink.
 
     ``gather=True``: every rank returns the full-length outputs (ONE all-gather of the packed per-nucleus block
     [mean | var | percentiles | c_lt | c_le], (4 + Q) x 8 bytes per nucleus); ``gather=False``: each rank

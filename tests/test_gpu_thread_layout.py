@@ -149,9 +149,11 @@ def test_simplex_thread_per_chain_matches_reference_sampler_statistically():
         assert abs(res.acceptance.mean() - acc_ref.mean()) < 3.0 * se_acc + 1.0 / T, dtype
 
 
-def _gamma_only_run(dtype, shape, n_chains, iters, seed, layout):
+def _gamma_only_run(dtype, shape, n_chains, iters, seed, layout, k=1):
     """A conjugate-sampler problem whose RSS does not depend on the coefficient (d = 0): sigma^2 of iteration t is
-    exactly scale / Gamma_t, so the kept sigmas give back the device's Gamma(shape, 1) variates."""
+    exactly scale / Gamma_t, so the kept sigmas give back the device's Gamma(shape, 1) variates.  ``k`` picks the
+    variate layout: padded k = 8 takes the Gamma words from the iteration's own Philox calls, the others from the
+    Gamma block."""
     import torch
     from pybmc_b200 import _device as D
     from pybmc_b200 import _lib
@@ -159,33 +161,36 @@ def _gamma_only_run(dtype, shape, n_chains, iters, seed, layout):
     dev = D.device(None)
     tdt, code = D.resolve_dtype(dtype)
     nu0, sigma20, rss = 1.0, 0.02, 777.0
-    consts = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64, device=dev)        # d, pull, g_ols, w
+    consts = torch.tensor([0.0] * (3 * k) + [1.0] * k, dtype=torch.float64, device=dev)   # d, pull, g_ols, w
     base = consts.data_ptr()
-    prob = _lib.GibbsProblem(k=1, d=base, pull=base + 8, g_ols=base + 16, w=base + 24, dense_w=0, rss_min=rss,
-                             n_obs=2.0 * shape - nu0, nu0=nu0, sigma20=sigma20, sigma2_init=rss / (2.0 * shape),
-                             layout=_lib.LAYOUTS[layout])
-    out = torch.empty((iters, 2, n_chains), dtype=tdt, device=dev)
+    prob = _lib.GibbsProblem(k=k, d=base, pull=base + 8 * k, g_ols=base + 16 * k, w=base + 24 * k, dense_w=0,
+                             rss_min=rss, n_obs=2.0 * shape - nu0, nu0=nu0, sigma20=sigma20,
+                             sigma2_init=rss / (2.0 * shape), layout=_lib.LAYOUTS[layout])
+    out = torch.empty((iters, k + 1, n_chains), dtype=tdt, device=dev)
     _lib.check(lib.bmc_gibbs_run(code, C.byref(prob), seed, 0, n_chains, iters, 0, 1, iters, out.data_ptr(), None,
                                  _lib.STATS_NONE, None, D.stream_ptr(dev)))
-    sig = out[:, 1, :].double().cpu().numpy()                   # [iteration, chain]
+    sig = out[:, k, :].double().cpu().numpy()                   # [iteration, chain]
     return 0.5 * (nu0 * sigma20 + rss) / sig ** 2
 
 
+@pytest.mark.parametrize("k", [1, 8])
 @pytest.mark.parametrize("shape", [5.0e4, 1500.5, 14.5])
-def test_gamma_variates_at_large_shape(shape):
+def test_gamma_variates_at_large_shape(shape, k):
     """Marsaglia-Tsang on the device at shape (nu0 + n)/2 = 5e4 (configs[4]: n = 1e5), where the fp32 acceptance
     test 0.5 x^2 + d (1 - v + log v) cancels 30 times harder than at configs[2]'s 1500.5: value by value against
     oracle/philox.py::gamma_unit_scale (fp64 <= 1e-9; fp32 to fp32 rounding of sigma), and the moments of 2e6
     fp32 variates against Gamma(shape, 1) within 4 standard errors."""
     seed, key = 99, px.seed_key(99)
-    g64 = _gamma_only_run("float64", shape, 64, 40, seed, "thread")
-    want = np.array([[px.gamma_unit_scale(shape, it, c, px.TAG_GIBBS, key) for c in range(64)] for it in range(40)])
+    g64 = _gamma_only_run("float64", shape, 64, 40, seed, "thread", k)
+    want = np.array([[px.gamma_unit_scale(shape, it, c, px.TAG_GIBBS, key, k) for c in range(64)] for it in range(40)])
+    if k == 8:      # the eight-lane layout reads the same words through the stand-alone path
+        np.testing.assert_allclose(_gamma_only_run("float64", shape, 64, 40, seed, "group", k), want, rtol=1e-9)
     np.testing.assert_allclose(g64, want, rtol=1e-9)
-    g32 = _gamma_only_run("float32", shape, 64, 40, seed, "thread")
+    g32 = _gamma_only_run("float32", shape, 64, 40, seed, "thread", k)
     # the variate is recovered from a stored fp32 sigma (2^-24 relative, doubled by the square) on top of the
     # fp32 evaluation of d (1 + c x)^3; a different accept/reject decision would show as an O(1/sqrt(shape)) jump
     assert np.max(np.abs(g32 / want - 1.0)) < 3e-6
-    big = _gamma_only_run("float32", shape, 32768, 64, seed + 1, None)
+    big = _gamma_only_run("float32", shape, 32768, 64, seed + 1, None, k)
     n = big.size
     assert abs(big.mean() - shape) < 4.0 * np.sqrt(shape / n) + 2e-7 * shape
     assert abs(big.var() / shape - 1.0) < 4.0 * np.sqrt(2.0 / n) + 6.0 / shape      # kurtosis term 6/shape
