@@ -110,7 +110,13 @@ typedef struct {
     double nu0, sigma20;       /* prior_info[2], prior_info[3]                              (:21)  */
     double sigma2_init;        /* max(rss_min / n, 1e-6)                                  (:31,37) */
     int layout;                /* BMC_LAYOUT_*; 0 = choose by chain count                          */
+    void* workspace;           /* dev, optional: bmc_gibbs_workspace_bytes(n_chains).  With it, a thread-per-chain
+                                  launch whose chains would load the schedulers unevenly (65,536 chains: 3.46
+                                  warps each) runs as persistent workers that pass the chain groups round --
+                                  same chains, same results, no tail.  NULL: the plain launch.          */
+    size_t workspace_bytes;
 } bmc_gibbs_problem;
+size_t bmc_gibbs_workspace_bytes(int64_t n_chains);
 
 /* Runs chains [chain0, chain0 + n_chains) for `iterations` iterations each.
  * samples: real [n_kept][k+1][n_chains], iteration t is kept when t >= store_from and

@@ -31,7 +31,7 @@ _sz = C.c_size_t
 class GibbsProblem(C.Structure):
     _fields_ = [("k", _int), ("d", _p), ("pull", _p), ("g_ols", _p), ("w", _p), ("dense_w", _int),
                 ("rss_min", _dbl), ("n_obs", _dbl), ("nu0", _dbl), ("sigma20", _dbl), ("sigma2_init", _dbl),
-                ("layout", _int)]
+                ("layout", _int), ("workspace", _p), ("workspace_bytes", _sz)]
 
 
 class GibbsHist(C.Structure):
@@ -65,6 +65,7 @@ SIGNATURES = {
     "bmc_residual_ss": (_int, [_p, _i64, _int, _i64, _p, _p, _p, _p, _sz, _p]),
     "bmc_padded_components": (_int, [_int]),
     "bmc_gibbs_n_stat": (_i64, [_int, _int]),
+    "bmc_gibbs_workspace_bytes": (_sz, [_i64]),
     "bmc_gibbs_hist_workspace_bytes": (_sz, [_int]),
     "bmc_gibbs_run": (_int, [_int, C.POINTER(GibbsProblem), _u64, _u64, _i64, _i64, _i64, _i64, _i64, _p, _p,
                              _int, C.POINTER(GibbsHist), _p]),

@@ -1,5 +1,6 @@
 // C ABI: conjugate Gibbs sampler (see include/bmc_b200.h; pybmc/inference_utils.py:4-56).
 #include <algorithm>
+#include <cmath>
 #include "common.h"
 #include "gibbs_kernels.cuh"
 
@@ -22,43 +23,82 @@ size_t hist_smem(const GibbsArgs& a) {
     return a.hist_every ? sizeof(unsigned) * static_cast<size_t>(a.k + 1) * kHistBins : 0;
 }
 
-template <typename real, int KP>
-int launch_conjugate(const GibbsArgs& a, int stats_mode, int threads, cudaStream_t stream) {
+constexpr unsigned kItemIterations = 256;   // iterations per work item of the persistent launch (4 flush periods)
+
+// One instantiation of the thread-per-chain kernel: plain (a warp per group of 32 chains, the whole run) or
+// persistent (gibbs_kernels.cuh "Work items": every resident warp slot holds a worker, the chain groups rotate
+// through them).  The persistent form pays when the plain one would leave the schedulers unevenly loaded -- a
+// fractional number of warps per scheduler, or a partial last wave -- and needs the caller's workspace.
+template <typename real, int KP, int MODE, bool HIST>
+int launch_thread_kernel(GibbsArgs a, int threads, size_t smem, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream) {
+    auto kern = gibbs_conjugate_kernel<real, KP, MODE, HIST>;
+    const long long groups = (a.n_chains + 31) / 32;
+    const long long sched = 4ll * sm_count();
+    if (workspace && workspace_bytes >= bmc_gibbs_workspace_bytes(a.n_chains) && a.iterations >= 2 * kItemIterations &&
+        groups > sched) {
+        int per_sm = 0;
+        BMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64, smem));
+        // workers: a whole number of warps per scheduler, as many as fit and no more than there are groups for, so
+        // that every worker always finds its next item finished (measured, 65,536 fp32 chains: 3 per scheduler 7.98
+        // ms; 4 per scheduler, a sixth of them waiting at any time, 8.25; 3.5 -- two schedulers of an SM with 4 -- 9.09;
+        // the plain launch 9.06)
+        const long long per_sched = std::min<long long>(per_sm / 2, groups / sched);
+        const long long workers = per_sched * sched;
+        if (per_sched >= 1 && groups % workers != 0) {
+            const size_t flags = (static_cast<size_t>(groups) * sizeof(unsigned) + 255) / 256 * 256;
+            a.item_its = kItemIterations;
+            a.item_done = static_cast<unsigned*>(workspace);
+            a.item_state = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + flags);
+            BMC_CUDA(cudaMemsetAsync(a.item_done, 0, flags, stream));
+            // fewer blocks per SM than would fit: pad the dynamic shared memory so that exactly 2 per_sched blocks fit,
+            // or the block scheduler may give one SM eight blocks and another four
+            size_t smem_launch = smem;
+            const int nb = static_cast<int>(2 * per_sched);
+            if (nb < per_sm) {
+                const size_t each = (static_cast<size_t>(228) * 1024 / nb - 1024) / 128 * 128;
+                smem_launch = std::max(smem, each);
+                if (smem_launch > 48 * 1024)
+                    BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  static_cast<int>(smem_launch)));
+            }
+            void* params[] = {&a};
+            // cooperative: all workers are co-resident by construction, or the launch fails (never a deadlock)
+            BMC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern),
+                                                 dim3(static_cast<unsigned>(nb * sm_count())), dim3(64), params,
+                                                 smem_launch, stream));
+            return BMC_OK;
+        }
+    }
     const unsigned blocks = static_cast<unsigned>((a.n_chains + threads - 1) / threads);
+    kern<<<blocks, threads, smem, stream>>>(a);
+    BMC_LAUNCH_CHECK();
+    return BMC_OK;
+}
+
+template <typename real, int KP>
+int launch_conjugate(const GibbsArgs& a, int stats_mode, int threads, void* ws, size_t ws_bytes, cudaStream_t stream) {
     const size_t smem = hist_smem(a);
     if (a.hist_every) {
         if constexpr (KP <= 16) {
             switch (stats_mode) {
-                case BMC_STATS_NONE:
-                    gibbs_conjugate_kernel<real, KP, 0, true><<<blocks, threads, smem, stream>>>(a);
-                    break;
-                case BMC_STATS_DIAG:
-                    gibbs_conjugate_kernel<real, KP, 1, true><<<blocks, threads, smem, stream>>>(a);
-                    break;
-                default:
-                    gibbs_conjugate_kernel<real, KP, 2, true><<<blocks, threads, smem, stream>>>(a);
+                case BMC_STATS_NONE: return launch_thread_kernel<real, KP, 0, true>(a, threads, smem, ws, ws_bytes, stream);
+                case BMC_STATS_DIAG: return launch_thread_kernel<real, KP, 1, true>(a, threads, smem, ws, ws_bytes, stream);
+                default: return launch_thread_kernel<real, KP, 2, true>(a, threads, smem, ws, ws_bytes, stream);
             }
-            BMC_LAUNCH_CHECK();
-            return BMC_OK;
         }
     }
     switch (stats_mode) {
-        case BMC_STATS_NONE:
-            gibbs_conjugate_kernel<real, KP, 0><<<blocks, threads, 0, stream>>>(a);
-            break;
-        case BMC_STATS_DIAG:
-            gibbs_conjugate_kernel<real, KP, 1><<<blocks, threads, 0, stream>>>(a);
-            break;
+        case BMC_STATS_NONE: return launch_thread_kernel<real, KP, 0, false>(a, threads, 0, ws, ws_bytes, stream);
+        case BMC_STATS_DIAG: return launch_thread_kernel<real, KP, 1, false>(a, threads, 0, ws, ws_bytes, stream);
         default:
             if constexpr (KP <= 16) {
-                gibbs_conjugate_kernel<real, KP, 2><<<blocks, threads, 0, stream>>>(a);
+                return launch_thread_kernel<real, KP, 2, false>(a, threads, 0, ws, ws_bytes, stream);
             } else {
                 set_error("bmc_gibbs_run: BMC_STATS_FULL needs k <= 16");
                 return BMC_ERR_ARG;
             }
     }
-    BMC_LAUNCH_CHECK();
-    return BMC_OK;
 }
 
 template <typename real, int KP, int GEN>
@@ -100,7 +140,8 @@ int launch_group(const GibbsArgs& a, int stats_mode, cudaStream_t stream) {
 }
 
 template <typename real>
-int dispatch_conjugate(const GibbsArgs& a, int layout, int stats_mode, int threads, cudaStream_t stream) {
+int dispatch_conjugate(const GibbsArgs& a, int layout, int stats_mode, int threads, void* ws, size_t ws_bytes,
+                       cudaStream_t stream) {
     // (a two-lanes-per-chain variant was measured in round 1: 46 % more instructions for 70 % instead of
     //  61 % issue utilisation and register-limited to 16 warps/SM -- slower; see profiles/r1_notes.md)
     if (layout == BMC_LAYOUT_AUTO) {
@@ -114,11 +155,11 @@ int dispatch_conjugate(const GibbsArgs& a, int layout, int stats_mode, int threa
     if (layout == BMC_LAYOUT_GROUP)
         return a.k <= 4 ? launch_group<real, 4, 8>(a, stats_mode, stream)
                         : launch_group<real, 8, 8>(a, stats_mode, stream);
-    if (a.k <= 4) return launch_conjugate<real, 4>(a, stats_mode, threads, stream);
-    if (a.k <= 8) return launch_conjugate<real, 8>(a, stats_mode, threads, stream);
-    if (a.k <= 16) return launch_conjugate<real, 16>(a, stats_mode, threads, stream);
-    if (a.k <= 32) return launch_conjugate<real, 32>(a, stats_mode, threads, stream);
-    return launch_conjugate<real, 64>(a, stats_mode, threads, stream);
+    if (a.k <= 4) return launch_conjugate<real, 4>(a, stats_mode, threads, ws, ws_bytes, stream);
+    if (a.k <= 8) return launch_conjugate<real, 8>(a, stats_mode, threads, ws, ws_bytes, stream);
+    if (a.k <= 16) return launch_conjugate<real, 16>(a, stats_mode, threads, ws, ws_bytes, stream);
+    if (a.k <= 32) return launch_conjugate<real, 32>(a, stats_mode, threads, ws, ws_bytes, stream);
+    return launch_conjugate<real, 64>(a, stats_mode, threads, ws, ws_bytes, stream);
 }
 
 int pick_threads(long long n_chains) {
@@ -134,6 +175,12 @@ int pick_threads(long long n_chains) {
 extern "C" {
 
 int bmc_padded_components(int k) { return k <= 4 ? 4 : k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 64; }
+
+size_t bmc_gibbs_workspace_bytes(int64_t n_chains) {
+    if (n_chains < 1) return 0;
+    const size_t groups = static_cast<size_t>((n_chains + 31) / 32);
+    return (groups * sizeof(unsigned) + 255) / 256 * 256 + static_cast<size_t>(n_chains) * sizeof(double);
+}
 
 size_t bmc_gibbs_hist_workspace_bytes(int k) {
     return sizeof(uint64_t) * static_cast<size_t>(kHistReplicas) * (k + 1) * kHistBins;
@@ -235,8 +282,9 @@ int bmc_gibbs_run(int dtype, const bmc_gibbs_problem* p, uint64_t seed, uint64_t
         return BMC_OK;
     }
     const int threads = pick_threads(n_chains);
-    const int rc = dtype == BMC_F32 ? dispatch_conjugate<float>(a, p->layout, stats_mode, threads, st)
-                                    : dispatch_conjugate<double>(a, p->layout, stats_mode, threads, st);
+    const int rc = dtype == BMC_F32
+                       ? dispatch_conjugate<float>(a, p->layout, stats_mode, threads, p->workspace, p->workspace_bytes, st)
+                       : dispatch_conjugate<double>(a, p->layout, stats_mode, threads, p->workspace, p->workspace_bytes, st);
     if (rc == BMC_OK && a.hist_every && a.hist_replicas > 1) {
         const int words = (p->k + 1) * kHistBins;
         hist_reduce_kernel<<<(words + 255) / 256, 256, 0, st>>>(a.hist, a.hist_replicas, words,

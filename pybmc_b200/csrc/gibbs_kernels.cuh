@@ -55,6 +55,10 @@ struct GibbsArgs {
     const double* hist_inv;               // [k+1] 1 / bin width
     unsigned long long* hist;             // [hist_replicas][k+1][kHistBins]; block b merges into replica b % hist_replicas
     int hist_replicas;
+    // work items of the thread-per-chain kernel (see gibbs_conjugate_kernel): 0 = one item per warp, the whole run
+    uint32_t item_its;                    // iterations per item, a multiple of kFlushEvery
+    unsigned* item_done;                  // [groups] items finished per group of 32 chains (zeroed by the host)
+    double* item_state;                   // [n_chains] sigma^2 handed from one item of a chain to the next
 };
 
 constexpr int kHistBins = BMC_HIST_BINS;
@@ -117,19 +121,33 @@ struct StatCount {
     static constexpr int value = MODE == 0 ? 0 : (MODE == 1 ? 2 * D : D + D * (D + 1) / 2);
 };
 
+// Work items.  A launch is cut into items of (32 chains) x (item_its iterations); warp w of the grid takes items
+// w, w + W, w + 2W, ... of the list ordered by (iteration block, chain group) and hands the chains' state --
+// sigma^2, nothing else survives an iteration -- to whoever takes the group's next item, through global memory and
+// a per-group counter.  Why: one chain per thread gives 65,536 chains 2048 warps, 3.46 per scheduler -- four on
+// 46 % of the schedulers, three on the others, and the launch ran at the pace of the fours (9.06 ms, the same as
+// 75,776 chains; 56,832 chains, three everywhere, take 6.99 ms: profiles/r2_notes.md); the fp64 kernel (255
+// registers, two warps per scheduler) paid two full waves for 1.73.  With every resident warp slot filled by a
+// persistent worker and the chain groups rotating through them, every scheduler carries the same average load
+// and the tail disappears.  item_its = 0 (or a grid that covers all groups with one item each) is the plain launch:
+// no waiting, no state traffic.  The persistent form needs all W warps co-resident: the host launches it
+// cooperatively (gibbs.cu).
+//
 // HIST: marginal histograms on (a second instantiation, so that the plain kernel's code is untouched by them).
-// (Wrapping the walk in a device function called between zeroing and merging, so that no thread leaves the
-//  kernel early, was measured: 10.13 ms against 9.52 ms for this form -- the early EXIT keeps ptxas' schedule
-//  of the loop; profiles/r2_notes.md.)
 template <typename real, int KP, int MODE, bool HIST = false>
 __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugate_kernel(const GibbsArgs a) {
     using M = Math<real>;
     extern __shared__ unsigned hist_s[];                  // [k+1][kHistBins] when histograms are on
     if constexpr (HIST) hist_zero(hist_s, a.k + 1);
-    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (tid >= a.n_chains) return;
-    const unsigned long long gchain = a.chain0 + static_cast<unsigned long long>(tid);
-    const uint32_t chain = static_cast<uint32_t>(gchain);
+    const uint32_t total = static_cast<uint32_t>(a.iterations);          // < 2^32 (checked by the host)
+    const unsigned lane = threadIdx.x & 31u;
+    const long long worker = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long n_workers = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const long long n_groups = (a.n_chains + 31) >> 5;
+    const uint32_t item_its = a.item_its ? a.item_its : (total ? total : 1u);
+    const long long n_items = n_groups * static_cast<long long>((total + item_its - 1u) / item_its);
+    long long tid = 0;                                    // chain of the current item within this launch
+    uint32_t chain = 0;                                   // its global id (low word: Philox counter)
     constexpr int D = KP + 1;
     constexpr int NS = StatCount<KP, MODE>::value;
 
@@ -176,32 +194,55 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         stat_add(p, static_cast<double>(v));
     };
 
+    real* const out = static_cast<real*>(a.samples);
+    for (long long item = worker; item < n_items; item += n_workers) {
+    const long long blk = item / n_groups, grp = item - blk * n_groups;
+    tid = grp * 32 + lane;
+    const bool live = tid < a.n_chains;
+    chain = static_cast<uint32_t>(a.chain0 + static_cast<unsigned long long>(tid));
+    // opaque to the compiler from here on: it used to re-derive the chain id from S2R SR_TID.X inside the loop
+    // (once per pair of iterations, with the special-register latency) rather than keep it in a register
+    asm volatile("" : "+r"(chain));
+    const uint32_t it_begin = static_cast<uint32_t>(blk) * item_its;
+    const uint32_t it_end = (total - it_begin > item_its) ? it_begin + item_its : total;
     real s2 = rc.sigma2_init;
+    if (blk > 0) {
+        // the group's previous item: wait for its counter, then read the state it left (L2: another SM wrote it)
+        if (lane == 0) {
+            unsigned seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.item_done + grp) : "memory");
+                if (seen < static_cast<unsigned>(blk)) __nanosleep(256);
+            } while (seen < static_cast<unsigned>(blk));
+        }
+        __syncwarp();
+        if (live) s2 = static_cast<real>(__ldcg(a.item_state + tid));
+    }
     real sig = M::sqrt(s2);
     real e[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) e[k] = real(0);
-    real* const out = static_cast<real*>(a.samples);
-    const uint32_t total = static_cast<uint32_t>(a.iterations);          // < 2^32 (checked by the host)
-    long long next_store = a.samples ? a.store_from : -1;
-    long long slot = 0;
+    // first kept iteration at or after it_begin, and its slot
+    long long next_store = -1, slot = 0;
+    if (a.samples) {
+        slot = static_cast<long long>(it_begin) > a.store_from
+                   ? (static_cast<long long>(it_begin) - a.store_from + a.thin - 1) / a.thin : 0;
+        next_store = a.store_from + slot * a.thin;
+    }
 
-    GammaPair<real> gp;                                 // first Gamma proposals of iterations 2m, 2m+1
-    gp.x[1] = real(0);
-    gp.u[1] = real(1);
-    gp.lu[1] = real(0);
+    real gm_odd = real(1);                              // Gamma variate of iteration 2m+1, drawn with that of 2m
     Philox4 held{0u, 0u, 0u, 0u};
     // The iterations run in segments that end where something other than arithmetic happens (a flush
     // of the moment sums every kFlushEvery iterations, a kept draw, the end): the inner loop is pure
     // arithmetic with one 32-bit counter.
-    uint32_t it32 = 0;
-    while (it32 < total) {
+    uint32_t it32 = live ? it_begin : it_end;
+    while (it32 < it_end) {
         uint32_t seg_end = (it32 | static_cast<uint32_t>(kFlushEvery - 1)) + 1u;
-        if (seg_end > total || seg_end == 0u) seg_end = total;
+        if (seg_end > it_end || seg_end == 0u) seg_end = it_end;
         if (next_store >= static_cast<long long>(it32) && next_store < static_cast<long long>(seg_end))
             seg_end = static_cast<uint32_t>(next_store) + 1u;
-        // one iteration; w = its Philox calls, (gx, gu, glu) = its first Gamma proposal
-        auto iterate = [&](const uint32_t it32, const Philox4 (&w)[NC], const real gx, const real gu, const real glu) {
+        // one iteration; w = its Philox calls, gm = its Gamma(shape, 1) variate
+        auto iterate = [&](const Philox4 (&w)[NC], const real gm) {
             real rss0 = rss_min, rss1 = real(0);
             if constexpr (PACK2) {
                 // two components at a time on packed fp32 instructions (same roundings as the scalar form)
@@ -236,7 +277,6 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 }
             }
             const real scale = real(0.5) * (prior_scale + (rss0 + rss1));
-            const real gm = gamma_from_first<real>(gc, gx, gu, glu, it32, chain, kTagGibbs, a.key0, a.key1);
             s2 = M::div(scale, gm);
             s2 = s2 > real(1e-6) ? s2 : real(1e-6);
             sig = M::sqrt(s2);
@@ -281,35 +321,42 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 }
             }
         };
-        // iterations 2m and 2m+1 share one Gamma proposal pair.  fp32 walks them in pairs where the segment
-        // allows: the Philox rounds of 2m+1 then sit in the same basic block as the MUFU work of 2m and
-        // overlap with it (9.98 -> 9.32 ms); fp64 has no registers to spare for that and is faster one by one.
+        // iterations 2m and 2m+1 share one Gamma proposal pair: both variates are finished when 2m starts (one
+        // rare branch for the pair, rng.cuh).  fp32 walks the iterations in pairs where the segment allows: the
+        // Philox rounds of 2m+1 then sit in the same basic block as the MUFU work of 2m and overlap with it
+        // (9.98 -> 9.32 ms); fp64 has no registers to spare for that and is faster one by one.
         // `held`: with the inline layout, the angle call of iteration 2m+1 (needed at 2m for the shared pair).
-        auto pair_of = [&](const uint32_t it_even, const Philox4& last_even, const Philox4& last_odd) {
-            if constexpr (GIN) return gamma_pair_inline<real>(last_even, last_odd);
-            else return gamma_pair<real>(it_even, chain, kTagGibbs, a.keys);
+        // the Gamma variates of iterations it_even and it_even + 1 (a function of the words only)
+        auto gammas_of = [&](const uint32_t it_even, const Philox4& last_even, const Philox4& last_odd, real& g0,
+                             real& g1) {
+            GammaPair<real> gp;
+            if constexpr (GIN) gp = gamma_pair_inline<real>(last_even, last_odd);
+            else gp = gamma_pair<real>(it_even, chain, kTagGibbs, a.keys);
+            gamma_pair_finish<real>(gc, gp, it_even, chain, kTagGibbs, a.key0, a.key1, g0, g1);
         };
         if constexpr (sizeof(real) == 4 && KP <= 16) {
             if ((it32 & 1u) != 0u) {
                 Philox4 w[NC];
                 iteration_words<KP>(it32, chain, kTagGibbs, a.keys, w);
-                iterate(it32, w, gp.x[1], gp.u[1], gp.lu[1]);
+                iterate(w, gm_odd);
                 ++it32;
             }
             for (; it32 + 1u < seg_end; it32 += 2u) {
                 Philox4 wa[NC], wb[NC];
                 iteration_words<KP>(it32, chain, kTagGibbs, a.keys, wa);
                 iteration_words<KP>(it32 + 1u, chain, kTagGibbs, a.keys, wb);
-                gp = pair_of(it32, wa[NC - 1], wb[NC - 1]);
-                iterate(it32, wa, gp.x[0], gp.u[0], gp.lu[0]);
-                iterate(it32 + 1u, wb, gp.x[1], gp.u[1], gp.lu[1]);
+                real gm_even;
+                gammas_of(it32, wa[NC - 1], wb[NC - 1], gm_even, gm_odd);
+                iterate(wa, gm_even);
+                iterate(wb, gm_odd);
             }
             if (it32 < seg_end) {
                 Philox4 w[NC];
                 iteration_words<KP>(it32, chain, kTagGibbs, a.keys, w);
                 if constexpr (GIN) held = philox4x32_10(it32 + 1u, static_cast<uint32_t>(NC - 1), chain, kTagGibbs, a.keys);
-                gp = pair_of(it32, w[NC - 1], held);
-                iterate(it32, w, gp.x[0], gp.u[0], gp.lu[0]);
+                real gm_even;
+                gammas_of(it32, w[NC - 1], held, gm_even, gm_odd);
+                iterate(w, gm_even);
                 ++it32;
             }
         } else {
@@ -327,13 +374,14 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                         held = philox4x32_10(it32 + 1u, static_cast<uint32_t>(NC - 1), chain, kTagGibbs, a.keys);
                     }
                 }
-                if (!odd) gp = pair_of(it32, w[NC - 1], held);
-                iterate(it32, w, odd ? gp.x[1] : gp.x[0], odd ? gp.u[1] : gp.u[0], odd ? gp.lu[1] : gp.lu[0]);
+                real gm = gm_odd;
+                if (!odd) gammas_of(it32, w[NC - 1], held, gm, gm_odd);
+                iterate(w, gm);
             }
         }
 
         // ---- end of a segment: it32 iterations are done
-        if (MODE != 0 && ((it32 & static_cast<uint32_t>(kFlushEvery - 1)) == 0u || it32 == total)) {
+        if (MODE != 0 && ((it32 & static_cast<uint32_t>(kFlushEvery - 1)) == 0u || it32 == it_end)) {
             if constexpr (PACK) {
 #pragma unroll
                 for (int i = 0; i < H; ++i) {
@@ -420,10 +468,18 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
             next_store += a.thin;
         }
     }
-    if constexpr (HIST) {
-        const long long left = a.n_chains - static_cast<long long>(blockIdx.x) * blockDim.x;
-        hist_merge(hist_s, a.k + 1, a.hist, a.hist_replicas, left < blockDim.x ? static_cast<int>(left) : blockDim.x);
+    if (it_end < total) {
+        // hand the chains over: state first, then the group's counter (release: the stores of all lanes are
+        // ordered before it by the warp barrier and the fence)
+        if (live) __stcg(a.item_state + tid, static_cast<double>(s2));
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.item_done + grp), "r"(static_cast<unsigned>(blk) + 1u) : "memory");
+        }
     }
+    }   // items
+    if constexpr (HIST) hist_merge(hist_s, a.k + 1, a.hist, a.hist_replicas, blockDim.x);
 }
 
 // --------------------------------------------------------------------------------------

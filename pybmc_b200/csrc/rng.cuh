@@ -485,6 +485,37 @@ __device__ __forceinline__ real gamma_from_first(const GammaConst<real>& g, real
     return out;
 }
 
+// Both draws of an iteration pair at once, with ONE rarely-taken branch for everything that is rare (a rejected
+// first proposal: < 1e-3 at the sampler's shapes; the boost of shapes < 1).  The thread-per-chain kernels used to
+// branch twice per iteration (retry?, boost?): four basic-block cuts per pair that ptxas could not schedule
+// across, with instruction-fetch stalls behind each (profiles/r2_notes.md).  Same values as gamma_from_first.
+template <typename real>
+__device__ __noinline__ real gamma_finish_slow(const GammaConst<real> g, uint32_t it, uint32_t chain, uint32_t tag,
+                                               uint32_t k0, uint32_t k1, bool ok, real out) {
+    if (!ok) {
+        real v;
+        gamma_retry<real>(g, it, chain, tag, k0, k1, v);
+        out = g.d * v;
+    }
+    if (g.boost) out *= Math<real>::pow(Math<real>::u01(philox4x32_10(it, kBlockBoost, chain, tag, k0, k1).x), g.inv_shape);
+    return out;
+}
+template <typename real>
+__device__ __forceinline__ void gamma_pair_finish(const GammaConst<real>& g, const GammaPair<real>& p, uint32_t it_even,
+                                                  uint32_t chain, uint32_t tag, uint32_t k0, uint32_t k1, real& g0,
+                                                  real& g1) {
+    using M = Math<real>;
+    real v0, v1;
+    const bool ok0 = gamma_accept<real>(g, p.x[0], p.u[0], sizeof(real) == 4 ? M::log(p.u[0]) : p.lu[0], v0);
+    const bool ok1 = gamma_accept<real>(g, p.x[1], p.u[1], sizeof(real) == 4 ? M::log(p.u[1]) : p.lu[1], v1);
+    g0 = g.d * v0;
+    g1 = g.d * v1;
+    if (!(ok0 & ok1) || g.boost) {
+        g0 = gamma_finish_slow<real>(g, it_even, chain, tag, k0, k1, ok0, g0);      // by value: nothing of the
+        g1 = gamma_finish_slow<real>(g, it_even + 1u, chain, tag, k0, k1, ok1, g1); // hot path goes through memory
+    }
+}
+
 // KP = 8: the pair from the last words of the angle calls of iterations 2m (`even`) and 2m+1 (`odd`)
 template <typename real>
 __device__ __forceinline__ GammaPair<real> gamma_pair_inline(const Philox4& even, const Philox4& odd) {

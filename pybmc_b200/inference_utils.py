@@ -259,10 +259,11 @@ class ConjugateSampler:
 
     @D.on_own_device
     def run(self, iterations, n_chains=1, seed=0, dtype="float64", thin=1, discard=0, keep_samples=True,
-            stats="auto", chain_offset=0, layout=None, hist_every=0):
+            stats="auto", chain_offset=0, layout=None, hist_every=0, persistent=True):
         """Launch the sampler; returns device tensors (samples [n_kept, K+1, C] or None, chain_stats) and a
         dict with the launch's layout constants (and ``hist``: uint64 counts [K+1, HIST_BINS] as an int64
-        tensor when ``hist_every`` > 0).  ``layout``: None/"auto", "thread", "group", "warp"."""
+        tensor when ``hist_every`` > 0).  ``layout``: None/"auto", "thread", "group", "warp".  ``persistent=False``
+        withholds the workspace of the persistent launch (A/B runs: the plain one-warp-per-32-chains launch)."""
         lib = _lib.load()
         tdt, code = D.resolve_dtype(dtype)
         iterations, n_chains, thin, discard = int(iterations), int(n_chains), int(thin), int(discard)
@@ -280,6 +281,11 @@ class ConjugateSampler:
         n_stat = lib.bmc_gibbs_n_stat(kp, mode)
         cstats = torch.empty((n_stat, n_chains), dtype=torch.float64, device=self.dev) if mode else None
         prob = self.problem(layout)
+        # room for the persistent launch (chain groups handed round the resident warps: no uneven tail); the library
+        # only uses it for thread-per-chain launches that would load the schedulers unevenly
+        if persistent:
+            ws = torch.empty(int(lib.bmc_gibbs_workspace_bytes(n_chains)), dtype=torch.uint8, device=self.dev)
+            prob.workspace, prob.workspace_bytes = ws.data_ptr(), ws.numel()
         hist_every = int(hist_every)
         if hist_every < 0:
             raise ValueError("hist_every must be >= 0")

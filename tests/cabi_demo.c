@@ -44,6 +44,7 @@ int main(int argc, char** argv) {
     p.k = 2; p.d = dconst; p.pull = dconst + 2; p.g_ols = dconst + 4; p.w = dconst + 6; p.dense_w = 1;
     p.rss_min = c[10]; p.n_obs = 3.0; p.nu0 = 1.0; p.sigma20 = 1.0; p.sigma2_init = c[11];
     p.layout = BMC_LAYOUT_AUTO;
+    p.workspace = NULL; p.workspace_bytes = 0;          /* plain launch */
     const int chains = 4, iters = 5;
     double* dsamples = (double*)to_dev(NULL, sizeof(double) * iters * 3 * chains);
     CK(bmc_gibbs_run(BMC_F64, &p, 42, 0, chains, iters, 0, 1, iters, dsamples, NULL, BMC_STATS_NONE, NULL, NULL));
