@@ -135,7 +135,7 @@ struct StatCount {
 //
 // HIST: marginal histograms on (a second instantiation, so that the plain kernel's code is untouched by them).
 template <typename real, int KP, int MODE, bool HIST = false>
-__global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugate_kernel(const GibbsArgs a) {
+__global__ void __launch_bounds__(128, (sizeof(real) == 4 && KP <= 16) ? 4 : 2) gibbs_conjugate_kernel(const GibbsArgs a) {
     using M = Math<real>;
     extern __shared__ unsigned hist_s[];                  // [k+1][kHistBins] when histograms are on
     if constexpr (HIST) hist_zero(hist_s, a.k + 1);
@@ -153,11 +153,24 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
 
     // (d and pull as constant-bank operands -- typed copies inside the kernel parameters -- were measured in
     //  round 2: 9.25 vs 9.28 ms, no gain for a synchronising read-back of the constants; profiles/r2_notes.md)
-    real d[KP], pull[KP];
+    // K >= 32: d and pull live in shared memory (every lane reads the same word: a broadcast), the thread keeps its
+    // registers (255 of them: two blocks per SM) for e and the moment sums -- 64 + 64 + 64 + 130 values did not fit
+    // in 128 registers (2.5 KB of spills per thread, round 1).
+    constexpr bool BIGK = KP >= 32;
+    __shared__ __align__(16) real cons_s[BIGK ? 2 * KP : 2];
+    real d[BIGK ? 1 : KP], pull[BIGK ? 1 : KP];
+    if constexpr (BIGK) {
+        for (int k = threadIdx.x; k < KP; k += blockDim.x) {
+            cons_s[k] = k < a.k ? static_cast<real>(a.d[k]) : real(0);
+            cons_s[KP + k] = k < a.k ? static_cast<real>(a.pull[k]) : real(0);
+        }
+        __syncthreads();
+    } else {
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        d[k] = k < a.k ? static_cast<real>(a.d[k]) : real(0);
-        pull[k] = k < a.k ? static_cast<real>(a.pull[k]) : real(0);
+        for (int k = 0; k < KP; ++k) {
+            d[k] = k < a.k ? static_cast<real>(a.d[k]) : real(0);
+            pull[k] = k < a.k ? static_cast<real>(a.pull[k]) : real(0);
+        }
     }
     const RunConsts<real>& rc = run_consts<real>(a);
     const real rss_min = rc.rss_min;
@@ -219,9 +232,9 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         if (live) s2 = static_cast<real>(__ldcg(a.item_state + tid));
     }
     real sig = M::sqrt(s2);
-    real e[KP];
+    real e[BIGK ? 1 : KP];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) e[k] = real(0);
+    for (int k = 0; k < (BIGK ? 1 : KP); ++k) e[k] = real(0);
     // first kept iteration at or after it_begin, and its slot
     long long next_store = -1, slot = 0;
     if (a.samples) {
@@ -235,6 +248,62 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
     // The iterations run in segments that end where something other than arithmetic happens (a flush
     // of the moment sums every kFlushEvery iterations, a kept draw, the end): the inner loop is pure
     // arithmetic with one 32-bit counter.
+    // K >= 32.  One sweep over the components of iteration `it` from the state (s2v, sigv): e_k handed to `use` two at
+    // a time and NOT kept -- 64 more live registers would not fit beside the moment sums; a kept draw repeats the
+    // sweep of its iteration once more (same words, same arithmetic) to get its e back.  The Philox words are
+    // drawn where they are used, eight pairs (two radius calls, one angle call) at a time; d and pull come from
+    // shared memory.
+    real s2_in = real(0), sig_in = real(0);
+    auto big_update = [&](const uint32_t it, const real s2v, const real sigv, real& rss0, real& rss1, auto&& use) {
+        constexpr int P = VL::kPairs, R = P / 4;
+        f32x2 rssp = pack2(static_cast<float>(rss0), 0.f);
+        const f32x2 s2b = pack2(static_cast<float>(s2v), static_cast<float>(s2v));
+        const f32x2 sigb = pack2(static_cast<float>(sigv), static_cast<float>(sigv));
+#pragma unroll
+        for (int c = 0; c < P / 8; ++c) {
+            const Philox4 r0 = philox4x32_10(it, static_cast<uint32_t>(2 * c), chain, kTagGibbs, a.keys);
+            const Philox4 r1 = philox4x32_10(it, static_cast<uint32_t>(2 * c + 1), chain, kTagGibbs, a.keys);
+            const Philox4 ra = philox4x32_10(it, static_cast<uint32_t>(R + c), chain, kTagGibbs, a.keys);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = 2 * (8 * c + q);
+                const uint32_t rw = philox_word(q < 4 ? r0 : r1, q % 4);
+                const uint32_t aw = philox_word(ra, q / 2);
+                const uint32_t h = (q & 1) ? aw >> 16 : aw & 0xFFFFu;
+                real e0, e1;
+                if constexpr (sizeof(real) == 4) {
+                    const f32x2 zp = M::box_muller2_h(rw, h);
+                    const f32x2 dp = *reinterpret_cast<const f32x2*>(cons_s + k);
+                    const f32x2 pp = *reinterpret_cast<const f32x2*>(cons_s + KP + k);
+                    float t0, t1;
+                    unpack2(add2(dp, s2b), t0, t1);
+                    const f32x2 sdp = mul2(pack2(M::rsqrt(t0), M::rsqrt(t1)), sigb);
+                    const f32x2 ep = mul2(sdp, fma2(pp, sdp, zp));
+                    rssp = fma2(mul2(dp, ep), ep, rssp);
+                    float f0, f1;
+                    unpack2(ep, f0, f1);
+                    e0 = f0;
+                    e1 = f1;
+                } else {
+                    real z0, z1;
+                    M::box_muller_h(rw, h, z0, z1);
+                    const real d0 = cons_s[k], d1 = cons_s[k + 1];
+                    const real sd0 = sigv * M::rsqrt(d0 + s2v), sd1 = sigv * M::rsqrt(d1 + s2v);
+                    e0 = sd0 * M::fma(cons_s[KP + k], sd0, z0);
+                    e1 = sd1 * M::fma(cons_s[KP + k + 1], sd1, z1);
+                    rss0 = M::fma(d0 * e0, e0, rss0);
+                    rss1 = M::fma(d1 * e1, e1, rss1);
+                }
+                use(k, e0, e1);
+            }
+        }
+        if constexpr (sizeof(real) == 4) {
+            float r0f, r1f;
+            unpack2(rssp, r0f, r1f);
+            rss0 = r0f;
+            rss1 = r1f;
+        }
+    };
     uint32_t it32 = live ? it_begin : it_end;
     while (it32 < it_end) {
         uint32_t seg_end = (it32 | static_cast<uint32_t>(kFlushEvery - 1)) + 1u;
@@ -242,9 +311,20 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         if (next_store >= static_cast<long long>(it32) && next_store < static_cast<long long>(seg_end))
             seg_end = static_cast<uint32_t>(next_store) + 1u;
         // one iteration; w = its Philox calls, gm = its Gamma(shape, 1) variate
-        auto iterate = [&](const Philox4 (&w)[NC], const real gm) {
+        auto iterate = [&](const uint32_t it32, const Philox4 (&w)[NC], const real gm) {
             real rss0 = rss_min, rss1 = real(0);
-            if constexpr (PACK2) {
+            if constexpr (BIGK) {
+                s2_in = s2;                      // a kept draw re-derives e from these (big_update below)
+                sig_in = sig;
+                big_update(it32, s2, sig, rss0, rss1, [&](int k, real e0, real e1) {
+                    if constexpr (MODE != 0) {              // marginal moments (MODE 2 stops at K = 16)
+                        acc[k] += e0;
+                        acc[k + 1] += e1;
+                        acc[D + k] = M::fma(e0, e0, acc[D + k]);
+                        acc[D + k + 1] = M::fma(e1, e1, acc[D + k + 1]);
+                    }
+                });
+            } else if constexpr (PACK2) {
                 // two components at a time on packed fp32 instructions (same roundings as the scalar form)
                 f32x2 rssp = pack2(rss_min, 0.f);
                 const f32x2 s2b = pack2(s2, s2), sigb = pack2(sig, sig);
@@ -297,6 +377,12 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 }
                 m1s += es;
                 m2s = fmaf(es, es, m2s);
+            } else if constexpr (BIGK) {
+                if constexpr (MODE != 0) {
+                    const real es = sig - sig_ref;
+                    acc[KP] += es;
+                    acc[D + KP] = M::fma(es, es, acc[D + KP]);
+                }
             } else if (MODE != 0) {
                 const real es = sig - sig_ref;
 #pragma unroll
@@ -338,7 +424,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
             if ((it32 & 1u) != 0u) {
                 Philox4 w[NC];
                 iteration_words<KP>(it32, chain, kTagGibbs, a.keys, w);
-                iterate(w, gm_odd);
+                iterate(it32, w, gm_odd);
                 ++it32;
             }
             for (; it32 + 1u < seg_end; it32 += 2u) {
@@ -347,8 +433,8 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 iteration_words<KP>(it32 + 1u, chain, kTagGibbs, a.keys, wb);
                 real gm_even;
                 gammas_of(it32, wa[NC - 1], wb[NC - 1], gm_even, gm_odd);
-                iterate(wa, gm_even);
-                iterate(wb, gm_odd);
+                iterate(it32, wa, gm_even);
+                iterate(it32 + 1u, wb, gm_odd);
             }
             if (it32 < seg_end) {
                 Philox4 w[NC];
@@ -356,16 +442,18 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 if constexpr (GIN) held = philox4x32_10(it32 + 1u, static_cast<uint32_t>(NC - 1), chain, kTagGibbs, a.keys);
                 real gm_even;
                 gammas_of(it32, w[NC - 1], held, gm_even, gm_odd);
-                iterate(w, gm_even);
+                iterate(it32, w, gm_even);
                 ++it32;
             }
         } else {
             for (; it32 < seg_end; ++it32) {
                 const bool odd = (it32 & 1u) != 0u;
                 Philox4 w[NC];
+                if constexpr (!BIGK) {
 #pragma unroll
-                for (int b = 0; b < NC - (GIN ? 1 : 0); ++b)
-                    w[b] = philox4x32_10(it32, static_cast<uint32_t>(b), chain, kTagGibbs, a.keys);
+                    for (int b = 0; b < NC - (GIN ? 1 : 0); ++b)
+                        w[b] = philox4x32_10(it32, static_cast<uint32_t>(b), chain, kTagGibbs, a.keys);
+                }
                 if constexpr (GIN) {
                     if (odd) {
                         w[NC - 1] = held;
@@ -376,7 +464,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 }
                 real gm = gm_odd;
                 if (!odd) gammas_of(it32, w[NC - 1], held, gm, gm_odd);
-                iterate(w, gm);
+                iterate(it32, w, gm);
             }
         }
 
@@ -412,7 +500,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 }
             }
         }
-        if (HIST && (it32 % a.hist_every) == 0u) {
+        if constexpr (HIST) if ((it32 % a.hist_every) == 0u) {
             // marginal histograms: bin b = W (g_ols + e) and sigma of this iteration (shared-memory atomics);
             // hist_every is a multiple of kFlushEvery, so this is always the end of a segment.  Unrolled over
             // the padded components so that the loads and conversions of all coordinates overlap.
@@ -446,6 +534,17 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
         if (static_cast<long long>(it32) - 1 == next_store) {
             // b = W (g_ols + e);  row layout [slot][component][chain] keeps lanes coalesced
             real* row = out + (slot * static_cast<long long>(a.k + 1)) * a.n_chains + tid;
+            real ek[KP];                            // e of the iteration just done
+            if constexpr (BIGK) {
+                real t0 = real(0), t1 = real(0);
+                big_update(it32 - 1u, s2_in, sig_in, t0, t1, [&](int k, real e0, real e1) {
+                    ek[k] = e0;
+                    ek[k + 1] = e1;
+                });
+            } else {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) ek[k] = e[k];
+            }
             if (a.dense_w) {
                 for (int r = 0; r < a.k; ++r) {
                     real b = real(0);
@@ -453,7 +552,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                     for (int k = 0; k < KP; ++k)
                         if (k < a.k)
                             b = M::fma(static_cast<real>(a.w[r * a.k + k]),
-                                       static_cast<real>(a.g_ols[k]) + e[k], b);
+                                       static_cast<real>(a.g_ols[k]) + ek[k], b);
                     row[static_cast<long long>(r) * a.n_chains] = b;
                 }
             } else {
@@ -461,7 +560,7 @@ __global__ void __launch_bounds__(128, sizeof(real) == 4 ? 4 : 2) gibbs_conjugat
                 for (int k = 0; k < KP; ++k)
                     if (k < a.k)
                         row[static_cast<long long>(k) * a.n_chains] =
-                            static_cast<real>(a.w[k]) * (static_cast<real>(a.g_ols[k]) + e[k]);
+                            static_cast<real>(a.w[k]) * (static_cast<real>(a.g_ols[k]) + ek[k]);
             }
             row[static_cast<long long>(a.k) * a.n_chains] = sig;
             ++slot;
