@@ -48,6 +48,11 @@ int launch_thread_kernel(GibbsArgs a, int threads, size_t smem, void* workspace,
         if (per_sched >= 1 && groups % workers != 0) {
             const size_t flags = (static_cast<size_t>(groups) * sizeof(unsigned) + 255) / 256 * 256;
             a.item_its = kItemIterations;
+            // who takes which item (gibbs_kernels.cuh): list order, or owned groups with the left-over ones going
+            // round.  Measured on B200, fp32: 65,536 chains (left-over fraction 0.15 of W) 8.27 vs 8.40 ms, 100,000
+            // chains (0.32) 13.5 vs 12.9 ms, 40,000 chains and the fp64 launches: no difference
+            const double left = static_cast<double>(groups % workers) / static_cast<double>(workers);
+            a.item_order = left >= 0.25 && left <= 0.6;
             a.item_done = static_cast<unsigned*>(workspace);
             a.item_state = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + flags);
             BMC_CUDA(cudaMemsetAsync(a.item_done, 0, flags, stream));

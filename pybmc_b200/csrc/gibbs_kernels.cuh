@@ -56,6 +56,7 @@ struct GibbsArgs {
     unsigned long long* hist;             // [hist_replicas][k+1][kHistBins]; block b merges into replica b % hist_replicas
     int hist_replicas;
     // work items of the thread-per-chain kernel (see gibbs_conjugate_kernel): 0 = one item per warp, the whole run
+    int item_order;                       // 0: items w, w + W, ... of the (block, group) list; 1: owned groups + rotation
     uint32_t item_its;                    // iterations per item, a multiple of kFlushEvery
     unsigned* item_done;                  // [groups] items finished per group of 32 chains (zeroed by the host)
     double* item_state;                   // [n_chains] sigma^2 handed from one item of a chain to the next
@@ -121,10 +122,12 @@ struct StatCount {
     static constexpr int value = MODE == 0 ? 0 : (MODE == 1 ? 2 * D : D + D * (D + 1) / 2);
 };
 
-// Work items.  A launch is cut into items of (32 chains) x (item_its iterations); warp w of the grid takes items
-// w, w + W, w + 2W, ... of the list ordered by (iteration block, chain group) and hands the chains' state --
-// sigma^2, nothing else survives an iteration -- to whoever takes the group's next item, through global memory and
-// a per-group counter.  Why: one chain per thread gives 65,536 chains 2048 warps, 3.46 per scheduler -- four on
+// Work items.  A launch is cut into items of (32 chains) x (item_its iterations).  Worker (warp) w of the W in the
+// grid owns chain groups w, w + W, ...; the G mod W groups left over go round the workers -- in iteration block b
+// the j-th of them belongs to worker (j + (G mod W) b) mod W -- and a group's state (sigma^2: nothing else survives
+// an iteration) passes from one item to the next through global memory and a per-group counter.  (First version:
+// items w, w + W, ... of the list ordered by (block, group): nearly every item then waits for one that another
+// worker started at the same moment, the workers fall into lock-step and 9 % of the stall samples were the wait.)  Why: one chain per thread gives 65,536 chains 2048 warps, 3.46 per scheduler -- four on
 // 46 % of the schedulers, three on the others, and the launch ran at the pace of the fours (9.06 ms, the same as
 // 75,776 chains; 56,832 chains, three everywhere, take 6.99 ms: profiles/r2_notes.md); the fp64 kernel (255
 // registers, two warps per scheduler) paid two full waves for 1.73.  With every resident warp slot filled by a
@@ -145,7 +148,10 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4 && KP <= 16) ? 4 : 2) 
     const long long n_workers = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const long long n_groups = (a.n_chains + 31) >> 5;
     const uint32_t item_its = a.item_its ? a.item_its : (total ? total : 1u);
-    const long long n_items = n_groups * static_cast<long long>((total + item_its - 1u) / item_its);
+    const long long n_blk = static_cast<long long>((total + item_its - 1u) / item_its);
+    // worker w owns groups w, w + W, ... (q of them: their items never wait) and the `extra` = G - q W groups left
+    // over go round: in iteration block b, left-over group j belongs to worker (j + extra b) mod W
+    const long long own = n_groups / n_workers, extra = n_groups - own * n_workers;
     long long tid = 0;                                    // chain of the current item within this launch
     uint32_t chain = 0;                                   // its global id (low word: Philox counter)
     constexpr int D = KP + 1;
@@ -208,8 +214,23 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4 && KP <= 16) ? 4 : 2) 
     };
 
     real* const out = static_cast<real*>(a.samples);
-    for (long long item = worker; item < n_items; item += n_workers) {
-    const long long blk = item / n_groups, grp = item - blk * n_groups;
+    const long long n_steps = a.item_order ? n_blk * (own + 1) : (n_blk * n_groups - worker + n_workers - 1) / n_workers;
+    for (long long step = 0; step < n_steps; ++step) {
+    long long blk, grp;
+    if (a.item_order) {                              // owned groups, left-over groups rotating
+        blk = step / (own + 1);
+        const long long o = step - blk * (own + 1);
+        grp = worker + o * n_workers;
+        if (o == own) {
+            const long long j = (worker + n_workers - (extra * blk) % n_workers) % n_workers;
+            if (j >= extra) continue;
+            grp = own * n_workers + j;
+        }
+    } else {                                         // items w, w + W, ... of the list ordered by (block, group)
+        const long long item = worker + step * n_workers;
+        blk = item / n_groups;
+        grp = item - blk * n_groups;
+    }
     tid = grp * 32 + lane;
     const bool live = tid < a.n_chains;
     chain = static_cast<uint32_t>(a.chain0 + static_cast<unsigned long long>(tid));
