@@ -394,7 +394,7 @@ def measure_pipe_peaks(torch, dev):
     blocks, threads, iters = sms * 8, 256, 20000
     out = {}
     for kind, name in ((0, "ffma"), (1, "mufu"), (2, "philox_mix"), (3, "issue"), (6, "imad"), (7, "lop3"),
-                       (8, "ffma2"), (9, "imad_wide"), (11, "imad_wide_plus_2ffma")):
+                       (8, "ffma2"), (9, "imad_wide"), (11, "imad_wide_plus_2ffma"), (16, "dfma")):
         ops = lib.bmc_probe_ops_per_iteration(kind)
         best = None
         for _ in range(3):
@@ -408,6 +408,7 @@ def measure_pipe_peaks(torch, dev):
         thread_ops = float(blocks) * threads * iters * ops
         out[name] = {"Gwarp_inst_per_s": thread_ops / 32 / (best * 1e-3) / 1e9, "ms": best}
     out["ffma"]["TFLOP_per_s"] = out["ffma"]["Gwarp_inst_per_s"] * 32 * 2 / 1e3
+    out["dfma"]["TFLOP_per_s"] = out["dfma"]["Gwarp_inst_per_s"] * 32 * 2 / 1e3
     out["sms"] = sms
     return out
 
@@ -462,20 +463,35 @@ def sampler_roofline(b, key, kernel_name, rate_per_gpu, ms_step, kept_bytes_per_
                     "fp64_instructions_per_warp_iteration": fp64_slots,
                     "mufu_per_warp_iteration": entry.get("mufu_per_unit"),
                     "warp_inst_per_warp_iteration": entry.get("warp_inst_per_warp_unit")})
+        if entry.get("mufu_per_unit"):
+            xu = float(entry["mufu_per_unit"]) * rate_per_gpu / 32 / 1e9
+            out["xu"] = {"achieved": xu, "peak": pk["mufu"]["Gwarp_inst_per_s"], "frac": xu / pk["mufu"]["Gwarp_inst_per_s"],
+                         "unit": "Gwarp-inst/s (MUFU)", "note": "second pipe above half load: 8 cycles per MUFU and scheduler"}
         inst = entry.get("warp_inst_per_warp_unit")
         if inst:
             issue_peak = max(pk["issue"]["Gwarp_inst_per_s"], ffma)
             out["issue"] = {"achieved": inst * rate_per_gpu / 32 / 1e9, "peak": issue_peak,
                             "frac": inst * rate_per_gpu / 32 / 1e9 / issue_peak, "unit": "Gwarp-inst/s"}
+    if real_bytes == 8 and entry.get("fp64_per_unit"):
+        # the fp64 kernels: the same construction on the fp64 pipe (DFMA / DMUL / DADD per warp-iteration of the
+        # capture x the live rate, against the DFMA rate measured in this run); the FMA-pipe view (Philox) beside it
+        dp, dpeak = float(entry["fp64_per_unit"]), pk["dfma"]["Gwarp_inst_per_s"]
+        out["fma_pipe"] = {k: out[k] for k in ("achieved", "peak", "frac", "unit")}
+        out.update({"bound": "fp64-pipe", "unit": "Gwarp-inst/s (fp64 instructions)", "achieved": dp * rate_per_gpu / 32 / 1e9,
+                    "peak": dpeak, "frac": dp * rate_per_gpu / 32 / 1e9 / dpeak,
+                    "peak_source": "DFMA rate measured in this run by libbmc_probe (independent streams, all SMs)"})
     out["counters"] = counters_view(entry)
-    if out["counters"] and "fma_pipe_cycles_active_pct" in out["counters"]:
-        out["frac_by_counter"] = out["counters"]["fma_pipe_cycles_active_pct"] / 100.0
+    ckey = "fp64_pipe_cycles_active_pct" if out["bound"] == "fp64-pipe" else "fma_pipe_cycles_active_pct"
+    if out["counters"] and ckey in out["counters"]:
+        out["frac_by_counter"] = out["counters"][ckey] / 100.0
     out["traffic"] = entry.get("dram_bytes_per_launch")
-    alg = CHAINS_PER_GPU * (KEEP_PER_CHAIN * kept_bytes_per_chain * real_bytes + 54 * 8 * 2 * (ITERATIONS // 64))
+    # what HAS to cross HBM: the kept draws and one copy of the moment rows (the 156 flushes of a launch are
+    # reductions into rows that stay in L2: 28 MB)
+    alg = CHAINS_PER_GPU * (KEEP_PER_CHAIN * kept_bytes_per_chain * real_bytes + 54 * 8)
     out["hbm"] = {"algorithmic_bytes_per_launch": alg, "achieved": alg / (ms_step * 1e-3) / 1e9,
                   "peak": float(b.peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
                   "frac": alg / (ms_step * 1e-3) / 1e9 / float(b.peaks.get("hbm_gbs", 6650.0)),
-                  "note": "kept samples + fp64 moment flushes; not the bound (SURVEY.md section 8d)"}
+                  "note": "kept samples + one copy of the fp64 moment rows; not the bound (SURVEY.md section 8d)"}
     out["pipe_peaks_measured"] = pk
     return out
 

@@ -41,12 +41,15 @@ except ValueError:
 # ---- nuclei sharded: broadcast of the draws, packed all-gather ---------------------------------------------------------
 theta = pb.run_gibbs(o["y"], o["U_hat"], 4000, prior, n_chains=1, seed=6).samples
 n_pts = 1003
-full = par.sharded_predictive_summary(preds[:n_pts], theta if rank == 0 else np.zeros_like(theta), o["Vt_hat"],
-                                      truth=truth[:n_pts], seed=9, dtype="float64")
 ref = PredictiveProblem(preds[:n_pts], theta, o["Vt_hat"], truth=truth[:n_pts], dtype="float64").run(seed=9)
-checks["predict gathered"] = (np.array_equal(full.percentiles, ref.percentiles) and np.array_equal(full.c_lt, ref.c_lt)
-                              and np.array_equal(full.c_le, ref.c_le) and np.allclose(full.mean, ref.mean, rtol=1e-13)
-                              and np.allclose(full.var, ref.var, rtol=1e-12))
+# (a) only rank 0's values count: broadcast; (b) every rank holds the rows: 1/N uploaded each, all-gather
+for name, kw, th_in in (("predict gathered (broadcast)", dict(draws_from=0), theta if rank == 0 else np.zeros_like(theta)),
+                        ("predict gathered (split upload)", dict(), theta)):
+    full = par.sharded_predictive_summary(preds[:n_pts], th_in, o["Vt_hat"], truth=truth[:n_pts], seed=9,
+                                          dtype="float64", **kw)
+    checks[name] = (np.array_equal(full.percentiles, ref.percentiles) and np.array_equal(full.c_lt, ref.c_lt)
+                    and np.array_equal(full.c_le, ref.c_le) and np.allclose(full.mean, ref.mean, rtol=1e-13)
+                    and np.allclose(full.var, ref.var, rtol=1e-12))
 plo, phi = par.point_range(n_pts)
 mine = par.sharded_predictive_summary(preds[plo:phi], theta, o["Vt_hat"], truth=truth[plo:phi], seed=9, dtype="float32",
                                       gather=False, n_points_total=n_pts)

@@ -26,6 +26,22 @@ __global__ void probe_ffma(long long iters, float* sink) {
     if (s == 123.456f) sink[0] = s;
 }
 
+// fp64 FMA pipe (the bound of the fp64 samplers)
+__global__ void probe_dfma(long long iters, float* sink) {
+    double a[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) a[i] = 1.0 + 1e-3 * (threadIdx.x + i);
+    const double m = 0.999999, c = 1e-7;
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) a[i] = fma(a[i], m, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i];
+    if (s == 123.456) sink[0] = static_cast<float>(s);
+}
+
 __global__ void probe_mufu(long long iters, float* sink) {
     float a[kChains];
 #pragma unroll
@@ -184,12 +200,13 @@ int bmc_probe_ops_per_iteration(int kind) {
         case 13: return 5 * kChains;     // MUFU + 4 FFMA
         case 14: return 3 * kChains;     // MUFU + 2 IMAD.WIDE
         case 15: return 2 * kChains;     // FFMA2 + FFMA
+        case 16: return kChains;         // DFMA
         default: return 0;
     }
 }
 
 int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, void* stream) {
-    if (!(kind >= 0 && kind <= 15 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink)) return -1;
+    if (!(kind >= 0 && kind <= 16 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink)) return -1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (kind) {
         case 0: probe_ffma<<<blocks, threads, 0, st>>>(iters, sink); break;
@@ -207,6 +224,7 @@ int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, voi
         case 12: probe_mix<1, 0, 1, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
         case 13: probe_mix<0, 4, 0, 1, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
         case 14: probe_mix<2, 0, 0, 1, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 16: probe_dfma<<<blocks, threads, 0, st>>>(iters, sink); break;
         default: probe_mix<0, 1, 1, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;

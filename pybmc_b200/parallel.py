@@ -223,11 +223,14 @@ def broadcast_draws(theta, k, *, src=0, group=None, device=None, split_upload=Tr
 
 
 def sharded_predictive_summary(preds, theta, Vt_hat, *, truth=None, percentiles=(2.5, 50.0, 97.5), seed=0,
-                               dtype="float32", group=None, device=None, gather=True, n_points_total=None):
+                               dtype="float32", group=None, device=None, gather=True, n_points_total=None,
+                               draws_from=None):
     """Fused prediction with the nuclei split over ranks.  ``preds`` / ``truth`` are the FULL tables (every
     rank slices its own 4-aligned block of nuclei); ``theta`` are the posterior rows to use (already
-    selected), identical on all ranks -- each rank uploads 1/N of the rows and ``broadcast_draws`` completes the table
-    with one all-gather over NVLink.
+    selected).  ``draws_from=None``: every rank holds them -- each uploads 1/N of the rows and ``broadcast_draws``
+    completes the table with one all-gather over NVLink (rank r contributes rows [r S/N, (r+1) S/N) of ITS array, so
+    ranks holding different draws of the same posterior end up with one common table).  ``draws_from=r``: only rank
+    r's values count; it uploads them all and broadcasts.
 
     ``gather=True``: every rank returns the full-length outputs (ONE all-gather of the packed per-nucleus block
     [mean | var | percentiles | c_lt | c_le], (4 + Q) x 8 bytes per nucleus); ``gather=False``: each rank
@@ -245,7 +248,7 @@ def sharded_predictive_summary(preds, theta, Vt_hat, *, truth=None, percentiles=
         raise ValueError(f"rank {rank} was given {np.asarray(preds).shape[0]} rows for its block [{lo}, {hi})")
     k = int(np.asarray(Vt_hat).shape[0])
     nq = len(tuple(percentiles))
-    th = broadcast_draws(theta, k, group=group, device=dev)
+    th = broadcast_draws(theta, k, group=group, device=dev, src=draws_from or 0, split_upload=draws_from is None)
     with D.on(dev):
         rows = 2 + nq + 2
         per = point_range(n, 0, world)[1]
