@@ -12,8 +12,17 @@ using namespace bmc;
 namespace {
 
 constexpr int kMaxPasses = 64;
-constexpr double kWindowSigmas = 4.0;   // half-width in sampling standard errors of the order statistic
-constexpr double kWindowSlack = 0.005;  // plus this fraction of the predictive spread (model error of the guess)
+#ifndef BMC_WINDOW_SIGMAS
+#define BMC_WINDOW_SIGMAS 3.0
+#endif
+#ifndef BMC_WINDOW_SLACK
+#define BMC_WINDOW_SLACK 0.002
+#endif
+// Round 2: 4.0 / 0.005 -> 3.0 / 0.002 (a third fewer candidates: 1e5 x 1e5 31.0 -> 29.4 ms, still one pass: the
+// guess is built from the moments of the same draws, so it follows the sample quantile more closely than an
+// independent estimate would; a miss only costs a retry pass over the nuclei concerned).
+constexpr double kWindowSigmas = BMC_WINDOW_SIGMAS;   // half-width in sampling standard errors of the order statistic
+constexpr double kWindowSlack = BMC_WINDOW_SLACK;     // plus this fraction of the predictive spread (model error of the guess)
 
 // Acklam's rational approximation of the standard normal quantile (|rel err| < 1.2e-9): only used to
 // place the first window, never in a result.

@@ -169,12 +169,14 @@ __device__ __forceinline__ void lane_init(const PredictArgs& a, const LaneCtx& c
     st.nle = 0u;
 }
 
-// x[0..3] are draws s .. s+3 of nucleus c.n (FLT_MAX = no such draw)
-template <typename real, int NQ, bool FULL = false>
+// x[0..3] are draws s .. s+3 of nucleus c.n (FLT_MAX = no such draw).
+// FAST: the caller has checked once (per eight draws) that this is a first pass that does not materialise the
+// draws -- a.first and a.draws_out are then compile-time facts instead of two uniform branches per four draws.
+template <typename real, int NQ, bool FULL = false, bool FAST = false>
 __device__ __forceinline__ void consume4(const PredictArgs& a, const LaneCtx& c, LaneAcc<real, NQ>& st,
                                          const real (&x)[4], long long s, real tc, real ctr) {
     using M = Math<real>;
-    if (a.first) {
+    if (FAST || a.first) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const bool valid = FULL || x[r] < real(FLT_MAX);      // FULL: all four draws exist, no padding marks
@@ -182,33 +184,32 @@ __device__ __forceinline__ void consume4(const PredictArgs& a, const LaneCtx& c,
             st.sx += dv;
             st.sxx = M::fma(dv, dv, st.sxx);
             count_step<real>(x[r], tc, st.nlt, st.nle);
-            if (a.draws_out && valid && c.live)
-                a.draws_out[(s + r) * a.ld_out + c.n] = static_cast<double>(x[r]) + c.mu_d;
+            if constexpr (!FAST) {
+                if (a.draws_out && valid && c.live)
+                    a.draws_out[(s + r) * a.ld_out + c.n] = static_cast<double>(x[r]) + c.mu_d;
+            }
         }
     }
-    // windows: two compares and a predicated add per (draw, window); hits only set a bit
+    // windows: two compares and a predicated add per (draw, window); hits only set a bit (bit 4 j + r)
     unsigned int hits = 0u;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
-            window_step<real>(x[r], st.wlo[j], st.whi[j], st.below[j], hits, 1u << (r * NQ + j));
+            window_step<real>(x[r], st.wlo[j], st.whi[j], st.below[j], hits, 1u << (4 * j + r));
         }
     }
     while (hits) {                                  // rare per lane: store the draw, count it
         const int bit = __ffs(hits) - 1;
         hits &= hits - 1u;
-        const int r = bit / NQ, j = bit - r * NQ;
+        const int r = bit & 3, j = bit >> 2;
         const real xv = r == 0 ? x[0] : (r == 1 ? x[1] : (r == 2 ? x[2] : x[3]));
         unsigned int have = 0u;
-        real lo_j = real(0), hi_j = real(1);
 #pragma unroll
         for (int jj = 0; jj < NQ; ++jj) {
             if (jj == j) {
                 have = st.inwin[jj];
                 st.inwin[jj] = have + 1u;
-                lo_j = st.wlo[jj];
-                hi_j = st.whi[jj];
             }
         }
         if (have < c.seg)
@@ -216,6 +217,14 @@ __device__ __forceinline__ void consume4(const PredictArgs& a, const LaneCtx& c,
         if (a.count_slices) {
             // which 1/32 slice of the window: lets an overflowing window be narrowed with exact
             // counts whatever the distribution (atoms, gaps, heavy tails)
+            real lo_j = real(0), hi_j = real(1);
+#pragma unroll
+            for (int jj = 0; jj < NQ; ++jj) {
+                if (jj == j) {
+                    lo_j = st.wlo[jj];
+                    hi_j = st.whi[jj];
+                }
+            }
             const real rel = (xv - lo_j) * (real(kSubBins) / (hi_j - lo_j));
             int bin = static_cast<int>(rel);
             bin = bin < 0 ? 0 : (bin > kSubBins - 1 ? kSubBins - 1 : bin);

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kTcThreads + 32, 1) predict_pass_tc_kernel(con
                 const int st = t & 1;
                 const uint32_t ph = static_cast<uint32_t>(t >> 1) & 1u;
                 mbar_wait_backoff(&full_bar[st], ph);               // operands of tile t are in shared memory
-                if (t >= 2) mbar_wait_backoff(&empty_bar[st], ph ^ 1u);   // tile t-2 left this accumulator buffer
+                if (t >= 2) mbar_wait_backoff(&empty_bar[st], ph ^ 1u, 512);   // tile t-2 left this accumulator buffer
                 tc_fence_after();
                 const uint32_t d = tmem_base + static_cast<uint32_t>(st * kTcTile);
                 const uint32_t bhi = smem_u32(stage0 + st * IM::kTileBytes), blo = bhi + IM::kOperandBytes;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kTcThreads + 32, 1) predict_pass_tc_kernel(con
                 }
                 umma_commit(&done_bar[st]);
                 if (t + 2 < n_tiles) {
-                    mbar_wait_backoff(&done_bar[st], ph);           // the MMAs have read the stage: refill it
+                    mbar_wait_backoff(&done_bar[st], ph, 256);      // the MMAs have read the stage: refill it
                     issue_tma(t + 2);
                 }
             }
@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(kTcThreads + 32, 1) predict_pass_tc_kernel(con
         LaneAcc<float, NQ> acc;
         lane_init<float, NQ>(a, c, acc);
         const uint32_t nglob = static_cast<uint32_t>(a.point0 + static_cast<unsigned long long>(n));
+        const bool fast_first = a.first && !a.draws_out;
 
         for (int t = 0; t < n_tiles; ++t) {
             const int st = t & 1;
@@ -310,8 +311,13 @@ __global__ void __launch_bounds__(kTcThreads + 32, 1) predict_pass_tc_kernel(con
                     unpack2(fma2(pack2(s_b.x, s_b.y), Math<float>::box_muller2(rb.x, rb.y), pack2(xs[4], xs[5])), x[4], x[5]);
                     unpack2(fma2(pack2(s_b.z, s_b.w), Math<float>::box_muller2(rb.z, rb.w), pack2(xs[6], xs[7])), x[6], x[7]);
                     const float xa[4] = {x[0], x[1], x[2], x[3]}, xb[4] = {x[4], x[5], x[6], x[7]};
-                    consume4<float, NQ, true>(a, c, acc, xa, s0 + g, tc, ctr);
-                    consume4<float, NQ, true>(a, c, acc, xb, s0 + g + 4, tc, ctr);
+                    if (fast_first) {            // first pass, draws not materialised: no per-draw flag tests
+                        consume4<float, NQ, true, true>(a, c, acc, xa, s0 + g, tc, ctr);
+                        consume4<float, NQ, true, true>(a, c, acc, xb, s0 + g + 4, tc, ctr);
+                    } else {
+                        consume4<float, NQ, true>(a, c, acc, xa, s0 + g, tc, ctr);
+                        consume4<float, NQ, true>(a, c, acc, xb, s0 + g + 4, tc, ctr);
+                    }
                     continue;
                 }
                 // tail of the draw range, or a pass without noise
