@@ -1,6 +1,6 @@
 """Regenerate profiles/kernel_constants.json FROM the .ncu-rep files of a capture (run here, no GPU needed).
 
-    python profiles/make_kernel_constants.py [--dir gpurun_out] [--tag r2]
+    python profiles/make_kernel_constants.py [--dir gpurun_out] [--tag r2b,r2c]
 
 bench.py divides by nothing in this file; it QUOTES it: the pipe counters that corroborate (or correct) the
 live roofline of each kernel, the per-unit instruction counts, the opcode mix and the DRAM traffic, each with
@@ -204,8 +204,13 @@ def main():
     out = {"_source": f"profiles/make_kernel_constants.py --tag {args.tag} over {os.path.relpath(args.dir, ROOT)}/*.ncu-rep "
                       f"(ncu --set full + pipe-cycle counters, --clock-control none, B200); regenerated "
                       f"{time.strftime('%Y-%m-%dT%H:%M:%SZ', time.gmtime())} at git {rev}"}
+    tags = args.tag.split(",")                   # several captures: the LAST tag that has a report for a stem wins
     for key, (stem, kre, units, unit_name) in CAPTURES.items():
-        e = summarise(key, stem, kre, units, unit_name, args.dir, args.tag)
+        e = None
+        for tag in reversed(tags):
+            e = summarise(key, stem, kre, units, unit_name, args.dir, tag)
+            if e is not None:
+                break
         if e is None:
             print(f"[skip] {key}: no {args.tag}_{stem}.ncu-rep with a kernel matching /{kre}/", file=sys.stderr)
             continue

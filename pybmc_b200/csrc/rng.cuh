@@ -138,11 +138,17 @@ struct Math<float> {
     // (A Box-Muller pair with N equally spaced angles has exactly normal marginals up to angular harmonics of
     //  order N, ~ (r/2)^N / N!: nothing at N = 65,536.  48 bits per pair instead of 64 is a quarter fewer Philox
     //  calls, the largest item of the thread-per-chain sampler.)
+    // a 16-bit integer as a float, exactly, without the conversion unit: I2F.U16 runs on the XU pipe (a quarter of
+    // the MUFU rate, and MUFU is the busiest pipe of the samplers); 2^23 + h as a bit pattern, minus 2^23, is one
+    // LOP3 and one FADD
+    static __device__ __forceinline__ float half_word_to_float(uint32_t h) {
+        return __uint_as_float(h | 0x4B000000u) - 8388608.0f;
+    }
     static __device__ __forceinline__ void box_muller_h(uint32_t ra, uint32_t h, float& za, float& zb) {
         float l2, rad, sn, cs;
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u01(ra)));
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(l2 * -1.3862943611198906f));
-        const float ang = fmaf(__uint2float_rn(h), 9.587379924285257e-05f, 4.7936899621426287e-05f);
+        const float ang = fmaf(half_word_to_float(h), 9.587379924285257e-05f, 4.7936899621426287e-05f);
         asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
         asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
         za = rad * cs;
@@ -151,7 +157,7 @@ struct Math<float> {
     // the same pair, bit for bit, with the conversions packed: {za, zb}
     static __device__ __forceinline__ f32x2 box_muller2_h(uint32_t ra, uint32_t h) {
         float ua, ang, l2, rad, sn, cs;
-        unpack2(fma2(pack2(__uint2float_rn(ra), __uint2float_rn(h)),
+        unpack2(fma2(pack2(__uint2float_rn(ra), half_word_to_float(h)),
                      pack2(2.3283064365386963e-10f, 9.587379924285257e-05f),
                      pack2(1.1641532182693481e-10f, 4.7936899621426287e-05f)), ua, ang);
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(ua));
