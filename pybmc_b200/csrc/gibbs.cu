@@ -61,7 +61,9 @@ int launch_thread_kernel(GibbsArgs a, int threads, size_t smem, void* workspace,
             size_t smem_launch = smem;
             const int nb = static_cast<int>(2 * per_sched);
             if (nb < per_sm) {
-                const size_t each = (static_cast<size_t>(228) * 1024 / nb - 1024) / 128 * 128;
+                cudaFuncAttributes fa{};
+                BMC_CUDA(cudaFuncGetAttributes(&fa, kern));         // static shared memory counts against the same budget
+                const size_t each = (static_cast<size_t>(228) * 1024 / nb - 1024 - fa.sharedSizeBytes) / 128 * 128;
                 smem_launch = std::max(smem, each);
                 if (smem_launch > 48 * 1024)
                     BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
