@@ -45,7 +45,9 @@ int launch_thread_kernel(GibbsArgs a, int threads, size_t smem, void* workspace,
         // the plain launch 9.06)
         const long long per_sched = std::min<long long>(per_sm / 2, groups / sched);
         const long long workers = per_sched * sched;
-        if (per_sched >= 1 && groups % workers != 0) {
+        // (one worker per scheduler would serialise what the plain launch overlaps -- K = 64, 32,768 chains: 6.8 ms
+        //  against 4.0 -- so at least two)
+        if (per_sched >= 2 && groups % workers != 0) {
             const size_t flags = (static_cast<size_t>(groups) * sizeof(unsigned) + 255) / 256 * 256;
             a.item_its = kItemIterations;
             // who takes which item (gibbs_kernels.cuh): list order, or owned groups with the left-over ones going
