@@ -23,6 +23,13 @@
 #pragma once
 #include "rng.cuh"
 
+#ifndef BMC_F32_MIN_BLOCKS
+// Blocks of 128 threads per SM the fp32 thread-per-chain kernels (K <= 16) are compiled for.  The persistent launch
+// runs three warps per scheduler, so the kernel may have 168 registers instead of the 128 that four warps allowed:
+// 65,536 x 10,000 with histograms 8.21 -> 7.89 ms, without 8.21 -> 7.67 ms (255 registers / two warps: 8.11 ms).
+#define BMC_F32_MIN_BLOCKS 3
+#endif
+
 
 namespace bmc {
 
@@ -138,7 +145,7 @@ struct StatCount {
 //
 // HIST: marginal histograms on (a second instantiation, so that the plain kernel's code is untouched by them).
 template <typename real, int KP, int MODE, bool HIST = false>
-__global__ void __launch_bounds__(128, (sizeof(real) == 4 && KP <= 16) ? 4 : 2) gibbs_conjugate_kernel(const GibbsArgs a) {
+__global__ void __launch_bounds__(128, (sizeof(real) == 4 && KP <= 16) ? BMC_F32_MIN_BLOCKS : 2) gibbs_conjugate_kernel(const GibbsArgs a) {
     using M = Math<real>;
     extern __shared__ unsigned hist_s[];                  // [k+1][kHistBins] when histograms are on
     if constexpr (HIST) hist_zero(hist_s, a.k + 1);
