@@ -15,7 +15,7 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libbmc_b200.so")
 PROBE_LIB = os.path.join(CSRC, "bench", "libbmc_probe.so")     # benchmark tooling, separate from the product ABI
 UNITS = ["linalg.cu", "gibbs.cu", "simplex.cu", "predict.cu", "literal.cu"]
-HEADERS = ["common.h", "rng.cuh", "gibbs_kernels.cuh", "linalg_kernels.cuh", "predict_kernels.cuh", "predict_tc_kernels.cuh",
+HEADERS = ["common.h", "rng.cuh", "fp64_tables.cuh", "gibbs_kernels.cuh", "linalg_kernels.cuh", "predict_kernels.cuh", "predict_tc_kernels.cuh",
            "literal_kernels.cuh", "tma.cuh", "select_logic.h", os.path.join("..", "..", "include", "bmc_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
