@@ -129,6 +129,13 @@ class ClockSampler:
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+            # nvidia-smi attaches to every GPU of the node while it starts (hundreds of ms, and it holds driver locks
+            # that delay launches on ALL of them: with the start-up inside the five timed steps the 8-GPU headline
+            # step read 9.2-9.9 ms instead of 8.5).  The recipe says "start before": wait for its first line, then
+            # only the 100 ms polls of this one GPU fall into the timed region.
+            t_end = time.time() + 5.0
+            while not self.lines and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.02)
         except OSError:
             self.proc = None
         return self
@@ -138,7 +145,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -147,12 +154,16 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pass
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -239,8 +250,8 @@ def workload_config(n_gpus, dtype="f32"):
                        "iterations, then added to fp64 rows in HBM",
             "histograms": f"marginal histograms of (b, sigma), 512 bins, every {HIST_EVERY}th state",
             "sharding": f"chains over {n_gpus} GPU(s) via pybmc_b200.parallel.sharded_gibbs, no data-path collective; "
-                        "per step one all-reduce of the 54 moment sums + count (fp64) and one of the 9 x 512 "
-                        "histogram counts (int64)",
+                        "per step ONE all-reduce: the 54 moment sums + count and the 9 x 512 histogram counts "
+                        "(as fp64, exact)",
             "l2": "512 MiB buffer rewritten between timed steps (working set is K-sized, not L2-resident data)"}
 
 
@@ -359,9 +370,19 @@ class Bench:
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
         self.barrier()
+        self.last_local_ms = float(np.median(ms)) if robust else float(np.sum(ms)) / steps
         if robust:
             return self.max_over_ranks(float(np.median(ms)))
         return self.max_over_ranks(float(np.sum(ms))) / steps
+
+    def per_rank(self, info):
+        """One small dict per rank, gathered on every rank (the spread between GPUs of one node: a step ends with
+        collectives, so every rank's step time contains the slowest GPU's kernel)."""
+        if self.world == 1:
+            return None
+        out = [None] * self.world
+        self.dist.all_gather_object(out, info)
+        return out
 
     def wall(self, step_fn, steps, warmup):
         """End-to-end steps by the host clock (host arrays in, host results out), max over ranks.  The warm-up
@@ -531,6 +552,19 @@ class SamplerWorkload:
         clocks = ClockSampler(b.local).start() if (with_clocks and b.rank == 0) else None
         ms_step = b.timed(lambda: self.step_resident(torch_dtype), steps, warmup)
         clock_info = clocks.stop() if clocks else None
+        ranks = None
+        if with_clocks and b.world > 1:
+            # the kernel alone on every GPU (no collective inside the events): which GPU sets the pace, and at what clock
+            ks = ClockSampler(b.local).start()
+            k_ms = b.timed(lambda: self.sampler.run(ITERATIONS, CHAINS_PER_GPU, SEED, torch_dtype, self.thin, 0, True,
+                                                    "full", b.rank * CHAINS_PER_GPU, None, HIST_EVERY), steps, 1)
+            kc = ks.stop()
+            ranks = b.per_rank({"rank": b.rank, "step_ms": round(float(np.float64(b.last_local_ms)), 3),
+                                "kernel_only_ms": None, "sm_mhz": kc.get("sm_mhz"), "power_w_max": kc.get("power_w_max"),
+                                "reasons": kc.get("reasons")})
+            for r in ranks:
+                r["kernel_only_ms"] = r.pop("step_ms")
+            del k_ms
         units = CHAINS_PER_GPU * b.world * ITERATIONS
         value = units / (ms_step * 1e-3)
         e2e_s, out = b.wall(lambda: self.step_e2e(torch_dtype), steps, max(3, warmup))
@@ -555,6 +589,8 @@ class SamplerWorkload:
         block["roofline"] = sampler_roofline(b, key, kernel, value / b.world, ms_step, 9, real_bytes)
         if clock_info is not None:
             block["clocks"] = clock_info
+        if ranks is not None:
+            block["per_rank"] = ranks
         return block
 
 

@@ -217,31 +217,36 @@ struct Math<double> {
     // of libm's general-argument ::log (~40 instructions) and ::sincospi (~50).  Accuracy ~1e-16 absolute (the
     // oracle's math.log / math.cos on the rounded angle differ from these by <= 3e-15): the 2e-9 value-by-value
     // parity of the fp64 chains is untouched.  Tables: fp64_tables.cuh (generated, 2 x 2 KB, read through L1).
-    // log of m 2^k: `mant` = the 52 fraction bits of m in [1, 2)
-    static __device__ __forceinline__ double log_parts(unsigned long long mant, int k2) {
-        const int i = static_cast<int>(mant >> 45);
-        const int up = i >= 53;                                                      // centre above sqrt 2: take m / 2
-        const double m = __longlong_as_double(static_cast<long long>(
-            mant | (static_cast<unsigned long long>(1023 - up) << 52)));
+    // log of the positive normal double with words (hi, lo), plus k_off ln 2.  Everything before the series is
+    // 32-bit integer work on the upper word -- table index, "centre above sqrt 2" flag, the mantissa with its
+    // exponent replaced -- and the exponent reaches the fp64 pipe through the 2^52 bit pattern (one DADD) instead of
+    // an I2F conversion.  (Round 2a did the same on 64-bit integers: shifts, a count-leading-zeros and carries, ~31
+    // dependent integer instructions per log with 2-5 cycles of stall each -- a quarter of the fp64 iteration's
+    // statically scheduled stall cycles, and that kernel runs two warps per scheduler.)  Same values, bit for bit.
+    static __device__ __forceinline__ double log_words(uint32_t hi, uint32_t lo, double k_off) {
+        const uint32_t i = (hi >> 13) & 0x7Fu;
+        const uint32_t up = i >= 53u ? 1u : 0u;                                       // centre above sqrt 2: take m / 2
+        const double m = __hiloint2double(static_cast<int>((hi & 0x000FFFFFu) | (up ? 0x3FE00000u : 0x3FF00000u)),
+                                          static_cast<int>(lo));
         const double2 t = __ldg(&kLogTab[i]);
         const double q = ::fma(m, t.x, -1.0);                                        // m / c_i - 1, one rounding
         double p = ::fma(q, -1.0 / 6.0, 0.2);
         p = ::fma(q, p, -0.25);
         p = ::fma(q, p, 1.0 / 3.0);
         p = ::fma(q, p, -0.5);
-        const double k = static_cast<double>(k2 + up);
+        // k = (biased exponent + up) - 1023 + k_off, exactly: 2^52 + n has n in its low word
+        const double k = __hiloint2double(0x43300000, static_cast<int>((hi >> 20) + up)) - (4503599627370496.0 + 1023.0 - k_off);
         return ::fma(k, 0.6931471805599453, t.y) + ::fma(q * q, p, q);               // (k ln 2 + ln c_i) + log1p(q)
     }
-    // log((r + 1/2) 2^-32)
+    // log((r + 1/2) 2^-32) = log(x) - 33 ln 2 with x = 2r + 1 (33 bits): 2^52 + x is a bit pattern, x one DADD away
     static __device__ __forceinline__ double log_u01(uint32_t r) {
-        const unsigned long long x = 2ull * r + 1ull;
-        const int e = 63 - __clzll(static_cast<long long>(x));                       // floor(log2 x): 0 .. 32
-        return log_parts((x << (52 - e)) & 0x000FFFFFFFFFFFFFull, e - 33);
+        const double x = __hiloint2double(static_cast<int>(0x43300000u | (r >> 31)), static_cast<int>((r << 1) | 1u)) -
+                         4503599627370496.0;
+        return log_words(static_cast<uint32_t>(__double2hiint(x)), static_cast<uint32_t>(__double2loint(x)), -33.0);
     }
     // natural log of a positive normal double, the same way (exponent and fraction straight from its bits)
     static __device__ __forceinline__ double log(double x) {
-        const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
-        return log_parts(b & 0x000FFFFFFFFFFFFFull, static_cast<int>(b >> 52) - 1023);
+        return log_words(static_cast<uint32_t>(__double2hiint(x)), static_cast<uint32_t>(__double2loint(x)), 0.0);
     }
     // sine and cosine of 2 pi (r + 1/2) 2^-BITS for a BITS-bit integer r (32: a whole word, 16: half a word)
     template <int BITS>

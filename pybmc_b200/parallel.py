@@ -149,8 +149,8 @@ def sharded_gibbs(y, X, iterations, prior_info, n_chains_total, *, seed, dtype="
     ``local.quantiles(q)`` are the credible-interval endpoints of the whole run on every rank.
     ``sampler``: a ``ConjugateSampler`` already built for (y, X, prior_info) on this rank (skips the set-up).
 
-    Collectives: all-reduce(sum, fp64) of [moment sums, count] -- 55 doubles at K = 8 -- and, with histograms,
-    all-reduce(sum, int64) of (K+1) x 512 counts (36 KB at K = 8)."""
+    Collective: ONE all-reduce(sum, fp64) of [moment sums, count, histogram counts] -- 55 doubles at K = 8 plus,
+    with histograms, (K+1) x 512 counts (36 KB at K = 8; exact in fp64)."""
     from . import _device as D
     from .inference_utils import ConjugateSampler, GibbsResult, _finish_samples, _moments_from_stats
     rank, world = _world(group)
@@ -168,14 +168,22 @@ def sharded_gibbs(y, X, iterations, prior_info, n_chains_total, *, seed, dtype="
     samples, cstats, meta = sampler.run(iterations, hi - lo, seed, dtype, thin, discard, keep_samples, stats, lo,
                                         None, hist_every)
     with D.on(dev):
-        total, count = merge_moment_sums(cstats.sum(dim=1), float(iterations) * (hi - lo), group)
+        # ONE collective and ONE read-back per step: [moment sums | count | histogram counts] travel together as
+        # fp64 (a bin holds at most iterations / hist_every x chains draws, far below 2^53: the sum is exact)
         hist = meta["hist"]
-        if hist is not None and world > 1:
-            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        n_mom = int(cstats.shape[0])
+        parts = [cstats.sum(dim=1), torch.full((1,), float(iterations) * (hi - lo), dtype=torch.float64, device=dev)]
+        if hist is not None:
+            parts.append(hist.reshape(-1).to(torch.float64))
+        vec = torch.cat(parts)
+        if world > 1:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        host = vec.cpu().numpy()
+        total, count = host[:n_mom], float(host[n_mom])
         k, kp = sampler.k, meta["kp"]
-        mean_e, cov_e = _moments_from_stats(total.cpu().numpy(), k, kp, meta["mode"], count)
+        mean_e, cov_e = _moments_from_stats(total, k, kp, meta["mode"], count)
         rows = _finish_samples(samples, as_numpy)
-        hist = None if hist is None else hist.cpu().numpy()
+        hist = None if hist is None else np.rint(host[n_mom + 1:]).astype(np.int64).reshape(tuple(hist.shape))
     jac = np.zeros((k + 1, k + 1))
     jac[:k, :k] = sampler.w
     jac[k, k] = 1.0
