@@ -415,7 +415,8 @@ def measure_pipe_peaks(torch, dev):
     blocks, threads, iters = sms * 8, 256, 20000
     out = {}
     for kind, name in ((0, "ffma"), (1, "mufu"), (2, "philox_mix"), (3, "issue"), (6, "imad"), (7, "lop3"),
-                       (8, "ffma2"), (9, "imad_wide"), (11, "imad_wide_plus_2ffma"), (16, "dfma")):
+                       (8, "ffma2"), (9, "imad_wide"), (11, "imad_wide_plus_2ffma"), (16, "dfma"),
+                       (17, "dfma_three_registers")):
         ops = lib.bmc_probe_ops_per_iteration(kind)
         best = None
         for _ in range(3):
@@ -501,6 +502,15 @@ def sampler_roofline(b, key, kernel_name, rate_per_gpu, ms_step, kept_bytes_per_
         out.update({"bound": "fp64-pipe", "unit": "Gwarp-inst/s (fp64 instructions)", "achieved": dp * rate_per_gpu / 32 / 1e9,
                     "peak": dpeak, "frac": dp * rate_per_gpu / 32 / 1e9 / dpeak,
                     "peak_source": "DFMA rate measured in this run by libbmc_probe (independent streams, all SMs)"})
+        # The quoted peak is DFMA with its multiplier and addend shared by every instruction (one per 2.05
+        # scheduler-cycles).  With three DISTINCT register operands -- what the sampler's arithmetic mostly is -- B200
+        # issues one DFMA per 3.03 cycles (register-operand bandwidth; profiles/probe_dfma.py): the realistic ceiling.
+        d3 = pk.get("dfma_three_registers", {}).get("Gwarp_inst_per_s")
+        if d3:
+            out["fp64_three_register_operands"] = {
+                "achieved": out["achieved"], "peak": d3, "frac": out["achieved"] / d3, "unit": out["unit"],
+                "note": "same instruction count against the DFMA rate with three distinct register operands "
+                        "(measured in this run): the ceiling real fp64 code has on this part"}
     out["counters"] = counters_view(entry)
     ckey = "fp64_pipe_cycles_active_pct" if out["bound"] == "fp64-pipe" else "fma_pipe_cycles_active_pct"
     if out["counters"] and ckey in out["counters"]:

@@ -42,6 +42,36 @@ __global__ void probe_dfma(long long iters, float* sink) {
     if (s == 123.456) sink[0] = static_cast<float>(s);
 }
 
+// DFMA with three DISTINCT register operands per instruction (what real code issues: probe_dfma's multiplier and
+// addend are the same two registers in every instruction), and the same interleaved with LOP3
+template <int WITH_LOP>
+__global__ void probe_dfma3(long long iters, float* sink) {
+    double a[kChains], b[kChains], c[kChains];
+    unsigned x[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        a[i] = 1.0 + 1e-3 * (threadIdx.x + i);
+        b[i] = 0.999999 - 1e-9 * (threadIdx.x + 3 * i);
+        c[i] = 1e-7 * (1 + threadIdx.x + i);
+        x[i] = threadIdx.x * 2654435761u + i;
+    }
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+            a[i] = fma(a[i], b[i], c[(i + 1) % kChains]);
+            if (WITH_LOP) x[i] = (x[i] ^ x[(i + 3) % kChains]) & (x[(i + 5) % kChains] | 0x55555555u);
+        }
+    }
+    double s = 0.0;
+    unsigned t = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        s += a[i];
+        t ^= x[i];
+    }
+    if (s == 123.456 || t == 0x12345u) sink[0] = static_cast<float>(s);
+}
+
 __global__ void probe_mufu(long long iters, float* sink) {
     float a[kChains];
 #pragma unroll
@@ -201,12 +231,14 @@ int bmc_probe_ops_per_iteration(int kind) {
         case 14: return 3 * kChains;     // MUFU + 2 IMAD.WIDE
         case 15: return 2 * kChains;     // FFMA2 + FFMA
         case 16: return kChains;         // DFMA
+        case 17: return kChains;         // DFMA, three distinct register operands
+        case 18: return 2 * kChains;     // the same + one LOP3 each
         default: return 0;
     }
 }
 
 int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, void* stream) {
-    if (!(kind >= 0 && kind <= 16 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink)) return -1;
+    if (!(kind >= 0 && kind <= 18 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink)) return -1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (kind) {
         case 0: probe_ffma<<<blocks, threads, 0, st>>>(iters, sink); break;
@@ -225,6 +257,8 @@ int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, voi
         case 13: probe_mix<0, 4, 0, 1, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
         case 14: probe_mix<2, 0, 0, 1, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
         case 16: probe_dfma<<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 17: probe_dfma3<0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 18: probe_dfma3<1><<<blocks, threads, 0, st>>>(iters, sink); break;
         default: probe_mix<0, 1, 1, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;

@@ -342,19 +342,22 @@ def _chain_diagnostics(cstats, comp, second, jac_d, chain_mean_d, iterations):
     d = len(comp)
     idx = [[second.get((min(a, b), max(a, b))) for b in comp] for a in comp]
     m1 = cstats[comp, :].t() / float(iterations)
+    # W, the mean over chains of the within-chain variances, is linear in the second-moment sums: only their TOTALS
+    # over the chains are needed, together with the per-chain first moments (one [d, d] matrix instead of a
+    # [chains, d, d] intermediate).
+    scale = iterations / (iterations - 1.0)
     if any(i is None for row in idx for i in row):
         # diagonal moments only: enough when the coordinates are not rotated (diagonal W)
         if bool((jac_d - torch.diag(torch.diagonal(jac_d))).abs().max() > 0):
             return None, None
         diag_rows = torch.tensor([second[(a, a)] for a in comp], device=cstats.device)
-        var_e = cstats[diag_rows, :].t() / float(iterations) - m1 * m1
-        var_b = var_e * torch.diagonal(jac_d)[None, :] ** 2 * (iterations / (iterations - 1.0))
+        var_e = cstats[diag_rows, :].sum(dim=1) / (float(iterations) * n_chains) - (m1 * m1).mean(dim=0)
+        w = var_e * torch.diagonal(jac_d) ** 2 * scale
     else:
         flat = torch.tensor([i for row in idx for i in row], device=cstats.device)
-        m2 = cstats[flat, :].t().reshape(n_chains, d, d) / float(iterations)      # E[e e'] per chain
-        cov_e = m2 - m1[:, :, None] * m1[:, None, :]
-        var_b = torch.einsum("ra,cab,rb->cr", jac_d, cov_e, jac_d) * (iterations / (iterations - 1.0))
-    w = var_b.mean(dim=0)
+        m2 = cstats[flat, :].sum(dim=1).reshape(d, d) / (float(iterations) * n_chains)     # E[e e'], all chains
+        cov_e = m2 - (m1[:, :, None] * m1[:, None, :]).mean(dim=0)                          # mean within-chain covariance
+        w = (jac_d[:, :, None] * cov_e[None, :, :] * jac_d[:, None, :]).sum(dim=(1, 2)) * scale   # diag(J C J'), no cuBLAS
     b_over_n = chain_mean_d.var(dim=0, unbiased=True)
     var_plus = (iterations - 1.0) / iterations * w + b_over_n
     rhat = torch.sqrt(var_plus / w)
