@@ -9,7 +9,9 @@ dev = torch.device("cuda", 0)
 sink = torch.zeros(1, dtype=torch.float32, device=dev)
 st = torch.cuda.current_stream(dev).cuda_stream
 sms = torch.cuda.get_device_properties(dev).multi_processor_count
-for kind, name in ((16, "DFMA a = fma(a, m, c), m and c shared"), (17, "DFMA, three distinct registers"), (18, "DFMA + LOP3")):
+for kind, name in ((16, "DFMA a = fma(a, m, c), m and c shared"), (17, "DFMA, three distinct registers"), (18, "DFMA + LOP3"),
+                   (0, "FFMA a = fma(a, m, c), m and c shared"), (19, "FFMA, three distinct registers"),
+                   (8, "FFMA2, m and c shared"), (20, "FFMA2, three distinct register pairs")):
     for blocks_per_sm, threads in ((8, 256), (3, 128), (2, 128), (1, 128)):
         ops = lib.bmc_probe_ops_per_iteration(kind)
         iters = 20000

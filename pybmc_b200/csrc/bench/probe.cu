@@ -210,6 +210,33 @@ __global__ void probe_mix(long long iters, float* sink) {
     if (s == 123.456f) sink[0] = s;
 }
 
+// FFMA (PACKED = 0) / FFMA2 (PACKED = 1) with three DISTINCT register operands per instruction
+template <int PACKED>
+__global__ void probe_fma3(long long iters, float* sink) {
+    float a[kChains], b[kChains], c[kChains];
+    unsigned long long ha[kChains], hb[kChains], hc[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        a[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+        b[i] = 0.999999f - 1e-7f * (threadIdx.x + 3 * i);
+        c[i] = 1e-7f * (1 + threadIdx.x + i);
+        ha[i] = (static_cast<unsigned long long>(__float_as_uint(a[i])) << 32) | __float_as_uint(a[i]);
+        hb[i] = (static_cast<unsigned long long>(__float_as_uint(b[i])) << 32) | __float_as_uint(b[i]);
+        hc[i] = (static_cast<unsigned long long>(__float_as_uint(c[i])) << 32) | __float_as_uint(c[i]);
+    }
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+            if (PACKED) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(ha[i]) : "l"(hb[i]), "l"(hc[(i + 1) % kChains]));
+            else asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b[i]), "f"(c[(i + 1) % kChains]));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += a[i] + static_cast<float>(ha[i] & 1ull);
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -233,12 +260,14 @@ int bmc_probe_ops_per_iteration(int kind) {
         case 16: return kChains;         // DFMA
         case 17: return kChains;         // DFMA, three distinct register operands
         case 18: return 2 * kChains;     // the same + one LOP3 each
+        case 19: return kChains;         // FFMA, three distinct register operands
+        case 20: return kChains;         // FFMA2, three distinct register pairs
         default: return 0;
     }
 }
 
 int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, void* stream) {
-    if (!(kind >= 0 && kind <= 18 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink)) return -1;
+    if (!(kind >= 0 && kind <= 20 && iters > 0 && blocks > 0 && threads > 0 && threads <= 1024 && sink)) return -1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (kind) {
         case 0: probe_ffma<<<blocks, threads, 0, st>>>(iters, sink); break;
@@ -259,6 +288,8 @@ int bmc_probe(int kind, int64_t iters, int blocks, int threads, float* sink, voi
         case 16: probe_dfma<<<blocks, threads, 0, st>>>(iters, sink); break;
         case 17: probe_dfma3<0><<<blocks, threads, 0, st>>>(iters, sink); break;
         case 18: probe_dfma3<1><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 19: probe_fma3<0><<<blocks, threads, 0, st>>>(iters, sink); break;
+        case 20: probe_fma3<1><<<blocks, threads, 0, st>>>(iters, sink); break;
         default: probe_mix<0, 1, 1, 0, 0><<<blocks, threads, 0, st>>>(iters, sink); break;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
