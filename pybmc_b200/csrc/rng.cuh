@@ -216,7 +216,8 @@ struct Math<double> {
     // degree-6 series on |q| <= 2^-8 (log) and degree-7/8 series on |delta| <= 2 pi / 256 (sine, cosine), instead
     // of libm's general-argument ::log (~40 instructions) and ::sincospi (~50).  Accuracy ~1e-16 absolute (the
     // oracle's math.log / math.cos on the rounded angle differ from these by <= 3e-15): the 2e-9 value-by-value
-    // parity of the fp64 chains is untouched.  Tables: fp64_tables.cuh (generated, 2 x 2 KB, read through L1).
+    // parity of the fp64 chains is untouched.  Tables: fp64_tables.cuh (generated: 2 x 2 KB for the log and the
+    // whole-word angles, 2 x 4 KB for the samplers' half-word angles; read through L1).
     // log of the positive normal double with words (hi, lo), plus k_off ln 2.  Everything before the series is
     // 32-bit integer work on the upper word -- table index, "centre above sqrt 2" flag, the mantissa with its
     // exponent replaced -- and the exponent reaches the fp64 pipe through the 2^52 bit pattern (one DADD) instead of
