@@ -236,7 +236,7 @@ def pred_config(n_gpus):
                         "mean / variance / 5 percentiles / coverage counts, no materialised S x N matrix",
             "n_points": PRED_POINTS, "n_draws": PRED_DRAWS, "components": PRED_K, "percentiles": PRED_Q,
             "sharding": f"nuclei over {n_gpus} GPU(s); e2e: each rank uploads 1/N of the posterior rows, one all-gather "
-                        "over NVLink completes them everywhere, one all-gather of the packed per-nucleus outputs",
+                        "over NVLink completes them everywhere, one gather of the packed per-nucleus outputs to rank 0",
             "l2": "512 MiB buffer rewritten between timed steps"}
 
 
@@ -626,11 +626,11 @@ class PredictWorkload:
 
     def step_e2e(self):
         """Host arrays in (this rank's block of predictions and truth; the posterior rows -- 1/N uploaded per rank,
-        all-gathered), host results out: every rank ends with the full-length outputs."""
+        all-gathered), host results out: rank 0 ends with the full-length outputs (one reader on the host link instead of N)."""
         from pybmc_b200 import parallel as par
         return par.sharded_predictive_summary(self.p_h, self.theta, self.vt, truth=self.t_h, percentiles=PRED_Q,
                                               seed=SEED, dtype="float32", device=self.b.dev,
-                                              n_points_total=PRED_POINTS)
+                                              n_points_total=PRED_POINTS, gather="root")
 
     def measure(self, steps, warmup):
         b = self.b
@@ -638,13 +638,13 @@ class PredictWorkload:
         units = PRED_POINTS * PRED_DRAWS
         value = units / (ms * 1e-3)
         e2e_s, res = b.wall(self.step_e2e, steps, max(2, warmup))
-        assert res.mean.shape[0] == PRED_POINTS
+        assert b.rank != 0 or res.mean.shape[0] == PRED_POINTS
         h2d = self.p_h.nbytes + self.t_h.nbytes + self.vt.nbytes + -(-self.theta.shape[0] // b.world) * self.theta.shape[1] * 8
         block = {"metric": PRED_METRIC, "value": value, "unit": PRED_UNIT, "ms_per_step": ms, "dtype": "f32",
                  "higher_is_better": True, "passes": self.last.passes, "config": pred_config(b.world),
                  "e2e": {"value": units / e2e_s, "unit": PRED_UNIT, "ms_per_step": 1e3 * e2e_s,
                          "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(PRED_POINTS * 8 * (4 + len(PRED_Q))),
-                         "collectives": "all_gather(theta: each rank uploads 1/N of the 13.6 MB fp64 rows) + all_gather(9 x nuclei fp64)" if b.world > 1
+                         "collectives": "all_gather(theta: each rank uploads 1/N of the 13.6 MB fp64 rows) + gather(9 x nuclei fp64) to rank 0, which alone reads the full-length results back" if b.world > 1
                          else "none (1 GPU)",
                          "api": "pybmc_b200.parallel.sharded_predictive_summary from host NumPy arrays"},
                  "roofline": self.roofline(value / b.world)}

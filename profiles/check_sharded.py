@@ -50,6 +50,12 @@ for name, kw, th_in in (("predict gathered (broadcast)", dict(draws_from=0), the
     checks[name] = (np.array_equal(full.percentiles, ref.percentiles) and np.array_equal(full.c_lt, ref.c_lt)
                     and np.array_equal(full.c_le, ref.c_le) and np.allclose(full.mean, ref.mean, rtol=1e-13)
                     and np.allclose(full.var, ref.var, rtol=1e-12))
+# results gathered to rank 0 only: the same values there, nothing on the other ranks
+rooted = par.sharded_predictive_summary(preds[:n_pts], theta, o["Vt_hat"], truth=truth[:n_pts], seed=9, dtype="float64",
+                                        gather="root")
+checks["predict gathered to rank 0"] = (
+    (np.array_equal(rooted.percentiles, ref.percentiles) and np.array_equal(rooted.c_lt, ref.c_lt)
+     and np.allclose(rooted.mean, ref.mean, rtol=1e-13)) if rank == 0 else (rooted.mean is None and rooted.percentiles is None))
 plo, phi = par.point_range(n_pts)
 mine = par.sharded_predictive_summary(preds[plo:phi], theta, o["Vt_hat"], truth=truth[plo:phi], seed=9, dtype="float32",
                                       gather=False, n_points_total=n_pts)

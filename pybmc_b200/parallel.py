@@ -241,9 +241,11 @@ def sharded_predictive_summary(preds, theta, Vt_hat, *, truth=None, percentiles=
     r's values count; it uploads them all and broadcasts.
 
     ``gather=True``: every rank returns the full-length outputs (ONE all-gather of the packed per-nucleus block
-    [mean | var | percentiles | c_lt | c_le], (4 + Q) x 8 bytes per nucleus); ``gather=False``: each rank
-    returns its own block (``PredictiveResult`` over nuclei ``point_range(...)``), no collective after the
-    broadcast.  ``n_points_total``: ``preds`` / ``truth`` are ALREADY this rank's block ``point_range(n_points_total)``
+    [mean | var | percentiles | c_lt | c_le], (4 + Q) x 8 bytes per nucleus); ``gather="root"``: one gather to rank 0
+    of the group, which alone copies the full-length outputs to its host (the other ranks return a result whose
+    arrays are None) -- eight ranks reading 7 MB each back at once share the host link, one reads at full speed;
+    ``gather=False``: each rank returns its own block (``PredictiveResult`` over nuclei ``point_range(...)``), no
+    collective after the broadcast.  ``n_points_total``: ``preds`` / ``truth`` are ALREADY this rank's block ``point_range(n_points_total)``
     (tables too large to replicate on every host process)."""
     from . import _device as D
     from .sampling_utils import PredictiveProblem, PredictiveResult
@@ -275,12 +277,28 @@ def sharded_predictive_summary(preds, theta, Vt_hat, *, truth=None, percentiles=
             if truth is not None:       # int64 counts travel as their bit patterns
                 block[2 + nq, : hi - lo] = res.c_lt.view(torch.float64)
                 block[3 + nq, : hi - lo] = res.c_le.view(torch.float64)
+        to_root = isinstance(gather, str)
+        if to_root and gather != "root":
+            raise ValueError(f"gather must be True, False or 'root', got {gather!r}")
+        holder = True
         if gather and world > 1:
-            parts = torch.empty((world, rows, per), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(parts, block, group=group)
-            block = parts.permute(1, 0, 2).reshape(rows, world * per)[:, :n]
-        else:
+            if to_root:
+                holder = rank == 0
+                parts = torch.empty((world, rows, per), dtype=torch.float64, device=dev) if holder else None
+                root = dist.get_global_rank(group, 0) if group is not None else 0
+                dist.gather(block, list(parts.unbind(0)) if holder else None, dst=root, group=group)
+            else:
+                parts = torch.empty((world, rows, per), dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(parts, block, group=group)
+            if holder:
+                block = parts.permute(1, 0, 2).reshape(rows, world * per)[:, :n]
+        elif not gather:
             block = block[:, : hi - lo]
+        else:
+            block = block[:, :n]
+        if not holder:
+            return PredictiveResult(mean=None, var=None, percentiles=None, c_lt=None, c_le=None, draws=None,
+                                    n_draws=int(np.shape(theta)[0]), passes=passes, seed=int(seed))
         out = D.to_host(block.contiguous()) if block.numel() else block.cpu().numpy()
     counts = None if truth is None else out[2 + nq:].view(np.int64)
     return PredictiveResult(mean=out[0], var=out[1], percentiles=out[2:2 + nq],
