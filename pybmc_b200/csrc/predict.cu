@@ -206,7 +206,10 @@ Layout make_layout(long long nc, int nq, int cand_stride, size_t sz, size_t imag
     return l;
 }
 
-constexpr long long kChunkPoints = 32768;     // nuclei per chunk when the workspace allows
+#ifndef BMC_CHUNK_POINTS
+#define BMC_CHUNK_POINTS 32768
+#endif
+constexpr long long kChunkPoints = BMC_CHUNK_POINTS;     // nuclei per chunk when the workspace allows
 
 template <typename real>
 __global__ void copy_guess_kernel(const double* c, const double* s, long long n, void* center, void* scale) {
