@@ -79,6 +79,14 @@ __device__ __forceinline__ unsigned hist_bin(const double* lo, const double* inv
     return static_cast<unsigned>(static_cast<int>(t));
 }
 
+// the same with the edges already in the kernel's arithmetic type (shared-memory copies, see gibbs_conjugate_kernel)
+template <typename real>
+__device__ __forceinline__ unsigned hist_bin_typed(real lo, real inv, real v) {
+    real t = (v - lo) * inv;
+    t = fmin(fmax(t, real(0)), real(kHistBins - 1));
+    return static_cast<unsigned>(static_cast<int>(t));
+}
+
 // block-level histogram (dynamic shared memory, uint32 [coords][kHistBins]) -> global 64-bit counts
 __device__ __forceinline__ void hist_zero(unsigned* hist_s, int coords) {
     for (int i = threadIdx.x; i < coords * kHistBins; i += blockDim.x) hist_s[i] = 0u;
@@ -148,7 +156,32 @@ template <typename real, int KP, int MODE, bool HIST = false>
 __global__ void __launch_bounds__(128, (sizeof(real) == 4 && KP <= 16) ? BMC_F32_MIN_BLOCKS : 2) gibbs_conjugate_kernel(const GibbsArgs a) {
     using M = Math<real>;
     extern __shared__ unsigned hist_s[];                  // [k+1][kHistBins] when histograms are on
-    if constexpr (HIST) hist_zero(hist_s, a.k + 1);
+    // What the binning needs, once per block in the kernel's arithmetic type: W (zero-padded KP x KP; the diagonal
+    // form on its diagonal), g_ols, the lower edges and 1 / widths.  The flush points used to read these as fp64 from
+    // global memory and convert them every time -- 64 + 8 + 18 F2F on the XU pipe per flush in the fp32 kernel, one per
+    // iteration on the pipe that is already at 57 %.  Same values, so the bins are the same.
+    constexpr int HW = KP * KP, HG = HW + KP, HL = HG + KP + 1, HN = HL + KP + 1;
+    __shared__ real hist_c[HIST ? HN : 1];
+    if constexpr (HIST) {
+        for (int i = threadIdx.x; i < HN; i += blockDim.x) {
+            real v = real(0);
+            if (i < HW) {
+                const int r = i / KP, c = i % KP;
+                if (r < a.k && c < a.k) {
+                    if (a.dense_w) v = static_cast<real>(a.w[r * a.k + c]);
+                    else if (r == c) v = static_cast<real>(a.w[r]);
+                }
+            } else if (i < HG) {
+                if (i - HW < a.k) v = static_cast<real>(a.g_ols[i - HW]);
+            } else if (i < HL) {
+                if (i - HG <= a.k) v = static_cast<real>(a.hist_lo[i - HG]);
+            } else {
+                if (i - HL <= a.k) v = static_cast<real>(a.hist_inv[i - HL]);
+            }
+            hist_c[i] = v;
+        }
+        hist_zero(hist_s, a.k + 1);                       // ends with the block barrier
+    }
     const uint32_t total = static_cast<uint32_t>(a.iterations);          // < 2^32 (checked by the host)
     const unsigned lane = threadIdx.x & 31u;
     const long long worker = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -536,24 +569,19 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4 && KP <= 16) ? BMC_F32
             if (a.dense_w) {
 #pragma unroll
                 for (int r = 0; r < KP; ++r) {
-                    real b = real(0);
-                    if (r < a.k) {
+                    real b = real(0);                      // padded rows and columns of W are zero: they add nothing
 #pragma unroll
-                        for (int k = 0; k < KP; ++k)
-                            if (k < a.k)
-                                b = M::fma(static_cast<real>(a.w[r * a.k + k]), static_cast<real>(a.g_ols[k]) + e[k], b);
-                    }
+                    for (int k = 0; k < KP; ++k) b = M::fma(hist_c[r * KP + k], hist_c[HW + k] + e[k], b);
                     bv[r] = b;
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < KP; ++r)
-                    bv[r] = r < a.k ? static_cast<real>(a.w[r]) * (static_cast<real>(a.g_ols[r]) + e[r]) : real(0);
+                for (int r = 0; r < KP; ++r) bv[r] = hist_c[r * KP + r] * (hist_c[HW + r] + e[r]);
             }
             unsigned bin[KP];
 #pragma unroll
-            for (int r = 0; r < KP; ++r) bin[r] = r < a.k ? hist_bin<real>(a.hist_lo, a.hist_inv, r, bv[r]) : 0u;
-            const unsigned bin_s = hist_bin<real>(a.hist_lo, a.hist_inv, a.k, sig);
+            for (int r = 0; r < KP; ++r) bin[r] = hist_bin_typed<real>(hist_c[HG + r], hist_c[HL + r], bv[r]);
+            const unsigned bin_s = hist_bin_typed<real>(hist_c[HG + a.k], hist_c[HL + a.k], sig);
 #pragma unroll
             for (int r = 0; r < KP; ++r)
                 if (r < a.k) atomicAdd(hist_s + r * kHistBins + bin[r], 1u);
