@@ -38,6 +38,17 @@ try:        # fewer chains than ranks: every rank raises, nobody hangs in a coll
 except ValueError:
     checks["empty share raises"] = True
 
+# ---- simplex chains sharded: moment sums, count and accepted proposals in one all-reduce ------------------------------
+ms_, cs_, acc_, loc_ = par.sharded_gibbs_simplex(o["y"], o["U_hat"], o["Vt_hat"], o["S_hat"], 400, [1.0, 0.02], 2048, burn=200,
+                                                 stepsize=0.02, seed=8, dtype="float64", keep_samples=True, thin=100)
+one_s = pb.run_gibbs_simplex(o["y"], o["U_hat"], o["Vt_hat"], o["S_hat"], 400, [1.0, 0.02], burn=200, stepsize=0.02,
+                             n_chains=2048, seed=8, dtype="float64", thin=100)
+clo, chi = par.chain_range(2048)
+checks["simplex: moments"] = np.allclose(ms_, one_s.mean, rtol=1e-10, atol=1e-12) and np.allclose(cs_, one_s.cov, rtol=1e-8, atol=1e-14)
+checks["simplex: acceptance"] = (abs(acc_ - one_s.acceptance.mean()) < 1e-12
+                                 and np.array_equal(loc_.acceptance, one_s.acceptance[clo:chi]))
+checks["simplex: kept samples"] = np.array_equal(loc_.samples, one_s.samples.reshape(2048, -1, o["U_hat"].shape[1] + 1)[clo:chi]
+                                                 .reshape(-1, o["U_hat"].shape[1] + 1))
 # ---- nuclei sharded: broadcast of the draws, packed all-gather ---------------------------------------------------------
 theta = pb.run_gibbs(o["y"], o["U_hat"], 4000, prior, n_chains=1, seed=6).samples
 n_pts = 1003

@@ -133,7 +133,7 @@ def posterior_from_sums(sums, count, k):
 
 
 # ------------------------------------------------------------------------------------------------
-# the two sharded entry points (one process per GPU; call them from every rank)
+# the sharded entry points (one process per GPU; call them from every rank)
 # ------------------------------------------------------------------------------------------------
 def sharded_gibbs(y, X, iterations, prior_info, n_chains_total, *, seed, dtype="float32", thin=1, discard=0,
                   keep_samples=False, group=None, device=None, rows_sharded=False, hist_every=0, as_numpy=True,
@@ -194,6 +194,48 @@ def sharded_gibbs(y, X, iterations, prior_info, n_chains_total, *, seed, dtype="
                         hist_lo=sampler.hist_lo if hist is not None else None,
                         hist_width=sampler.hist_width if hist is not None else None)
     return base + jac @ mean_e, jac @ cov_e @ jac.T, local
+
+
+def sharded_gibbs_simplex(y, X, Vt_hat, S_hat, iterations, prior_info, n_chains_total, *, burn=10000, stepsize=0.001,
+                          seed, dtype="float32", thin=1, keep_samples=False, group=None, device=None, as_numpy=True,
+                          sampler=None):
+    """This rank's share of ``n_chains_total`` simplex-constrained chains (pybmc/inference_utils.py:59-144, every
+    chain with its own burn-in) and ONE all-reduce (sum, fp64) of [moment sums | count | accepted proposals] --
+    SURVEY.md section 8e's sufficient statistics and accept counts.  Every rank returns the same posterior mean /
+    covariance of [b, sigma] and the overall acceptance rate of the sampling phase (what upstream prints, :143),
+    plus its own ``GibbsResult`` (kept samples and per-chain acceptance of ITS chains)."""
+    from . import _device as D
+    from .inference_utils import GibbsResult, SimplexSampler, _finish_samples, _moments_from_stats
+    if burn < 0:
+        raise ValueError("Burn-in iterations must be non-negative.")
+    if stepsize <= 0:
+        raise ValueError("Stepsize must be positive.")
+    rank, world = _world(group)
+    if int(n_chains_total) < world:
+        raise ValueError(f"sharded_gibbs_simplex: {n_chains_total} chains do not cover all {world} ranks")
+    lo, hi = chain_range(n_chains_total, rank, world)
+    if sampler is None:
+        sampler = SimplexSampler(y, X, Vt_hat, S_hat, prior_info, stepsize, device)
+    dev = sampler.dev
+    samples, cstats, accepted, meta = sampler.run(iterations, burn, hi - lo, seed, dtype, thin, keep_samples, "auto", lo)
+    with D.on(dev):
+        n_mom = int(cstats.shape[0])
+        vec = torch.cat([cstats.sum(dim=1),
+                         torch.full((1,), float(iterations) * (hi - lo), dtype=torch.float64, device=dev),
+                         accepted.sum(dtype=torch.float64).reshape(1)])
+        if world > 1:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        host = vec.cpu().numpy()
+        count = float(host[n_mom])
+        mean_e, cov_e = _moments_from_stats(host[:n_mom], sampler.k, meta["kp"], meta["mode"], count)
+        rows = _finish_samples(samples, as_numpy)
+        acc_local = D.to_host(accepted).astype(np.float64) / max(int(iterations), 1)
+    sig_ref = np.sqrt(sampler.rss_zero / sampler.n) if sampler.rss_zero > 0 else 1.0
+    base = np.concatenate([sampler.b_ols, [sig_ref]])
+    local = GibbsResult(samples=rows, mean=None, cov=None, chain_mean=None, n_chains=hi - lo,
+                        iterations=int(iterations), n_kept=meta["n_kept"], seed=int(seed), dtype=str(dtype),
+                        acceptance=acc_local, info=dict(chain_range=(lo, hi)))
+    return base + mean_e, cov_e, float(host[n_mom + 1]) / max(count, 1.0), local
 
 
 def broadcast_draws(theta, k, *, src=0, group=None, device=None, split_upload=True):
