@@ -802,11 +802,19 @@ def extras_samplers(out, b, sw, timed):
     o = pb.orthogonalize_arrays(preds[idx], truth[idx], 3, device=dev)
     simplex = SimplexSampler(o["y"], o["U_hat"], o["Vt_hat"], o["S_hat"], [1.0, 0.02], 0.001, device=dev)
     burn, iters, chains = 10000, 50000, 4096
-    ms = timed(lambda: simplex.run(iters, burn, chains, SEED, "float32", iters // 10, True, "full", rank * chains))
+    from pybmc_b200 import parallel as par
+
+    def simplex_step(dt):      # this rank's chains + the all-reduce of moment sums, count and accepted proposals
+        return par.sharded_gibbs_simplex(None, None, None, None, iters, [1.0, 0.02], chains * world, burn=burn,
+                                         stepsize=0.001, seed=SEED, dtype=dt, thin=iters // 10, keep_samples=True,
+                                         as_numpy=False, sampler=simplex, device=dev)
+    ms = timed(lambda: simplex_step("float32"))
+    acc_rate = simplex_step("float32")[2]
     out["simplex_f32"] = {"value": chains * world * (burn + iters) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                          "acceptance_rate": acc_rate, "api": "pybmc_b200.parallel.sharded_gibbs_simplex (device-resident problem)",
                           "config": "configs[1] surrogate: 377 x 15, K=3, 4096 chains/GPU x (10000 burn + 50000)",
                           "counters": counters_view(b.constants.get("gibbs_simplex_group16_f32_k4"))}
-    ms = timed(lambda: simplex.run(iters, burn, chains, SEED, "float64", iters // 10, True, "full", rank * chains))
+    ms = timed(lambda: simplex_step("float64"))
     out["simplex_f64"] = {"value": chains * world * (burn + iters) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                           "config": "the same in fp64"}
     # the literal one-chain-per-warp kernel (parity anchor): redoes the O(nK) residual every iteration
