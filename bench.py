@@ -26,6 +26,7 @@ Per metric:  value  device-timed (CUDA events), inputs resident in HBM;
 One JSON line on stdout (rank 0).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -361,14 +362,19 @@ class Bench:
             step_fn()
         self.barrier()
         ms = []
-        for _ in range(steps):
-            self.flush.add_(1)          # 512 MiB read + write > 126 MB L2
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step_fn()
-            e1.record()
-            e1.synchronize()
-            ms.append(e0.elapsed_time(e1))
+        gc.collect()
+        gc.disable()                    # no collector pause inside a timed step (the steps allocate a few tensors each)
+        try:
+            for _ in range(steps):
+                self.flush.add_(1)          # 512 MiB read + write > 126 MB L2
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step_fn()
+                e1.record()
+                e1.synchronize()
+                ms.append(e0.elapsed_time(e1))
+        finally:
+            gc.enable()
         self.barrier()
         self.last_local_ms = float(np.median(ms)) if robust else float(np.sum(ms)) / steps
         if robust:
@@ -391,11 +397,17 @@ class Bench:
         keep = [step_fn() for _ in range(max(warmup, 3))]
         del keep
         self.barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            out = step_fn()
-        self.torch.cuda.synchronize()
-        s = self.max_over_ranks(time.perf_counter() - t0) / steps
+        gc.collect()
+        gc.disable()
+        try:
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                out = step_fn()
+            self.torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        finally:
+            gc.enable()
+        s = self.max_over_ranks(dt) / steps
         self.barrier()
         return s, out
 
